@@ -1,0 +1,214 @@
+"""Host-side mirror of the reference's rhs / LSRK interface over the C ABI.
+
+The reference's boundary is the Julia call shape
+
+    rhsQ, rhstest = rhs(Q, md::MeshData, ops, flux_fun, compute_rhstest=false)
+        examples/dg2D_euler_quad.jl:141 ; dg2D_euler_tri.jl:130 ; dg3D_euler_hex.jl:167
+    for INTRK = 1:5 ... resQ = rk4a*resQ + dt*rhsQ ; Q += rk4b*resQ      (:198-207)
+
+``rhs`` / ``lsrk45!``-style functions below take the same arguments (``Q`` a list
+of Nfields ``Ns x K`` arrays, ``md`` with the MeshData field names, ``ops`` the
+operator bundle) and marshal them exactly as the Julia ``ccall`` shim of
+INTEGRATION.md does.  All arithmetic happens in libesdg_b200.so on the GPU.
+"""
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _lib as L
+
+ELEM_CODE = {"tri": L.ESDG_TRI, "quad": L.ESDG_QUAD, "hex": L.ESDG_HEX}
+
+
+def rk45_coeffs():
+    """Carpenter-Kennedy LSRK45 (src/CommonUtils.jl:29-49); the library holds the same literals."""
+    rk4a = np.array([0.0, -567301805773.0 / 1357537059087.0, -2404267990393.0 / 2016746695238.0,
+                     -3550918686646.0 / 2091501179385.0, -1275806237668.0 / 842570457699.0])
+    rk4b = np.array([1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0,
+                     1720146321549.0 / 2090206949498.0, 3134564353537.0 / 4481467310338.0,
+                     2277821191437.0 / 14882151754819.0])
+    rk4c = np.array([0.0, 1432997174477.0 / 9575080441755.0, 2526269341429.0 / 6820363962896.0,
+                     2006345519317.0 / 3224310063776.0, 2802321613138.0 / 2924317926251.0, 1.0])
+    return rk4a, rk4b, rk4c
+
+
+def euler_fluxes(*_a, **_k):
+    """Marker for the ``flux_fun`` argument of ``rhs``: the entropy-conservative flux of
+    examples/EntropyStableEuler/euler_fluxes.jl is compiled into the kernels."""
+    raise NotImplementedError("euler_fluxes is evaluated on the GPU; pass it to rhs() as flux_fun")
+
+
+class Solver:
+    """One GPU context: operators, geometry and maps resident in HBM."""
+
+    def __init__(self, md, ops, device=0, n_halo=0, stream=None, map_index_base=0):
+        lib = L.load()
+        self._lib = lib
+        self._ctx = C.c_void_p()
+        dim = 3 if ops.elem == "hex" else 2
+        nf = dim + 2
+        self.nf = nf
+        collocated = 1 if ops.elem in ("quad", "hex") else 0
+        Nq = int(np.asarray(ops.wq).size)
+        Nfq = int(np.asarray(ops.Lf).shape[1])
+        Ns = int(np.asarray(ops.Ph).shape[0])
+        self.Ns, self.K = Ns, int(md.K)
+        d = L.esdg_desc(dim=dim, elem=ELEM_CODE[ops.elem], N=int(ops.N), Nfields=nf, Ns=Ns, Nq=Nq, Nfq=Nfq,
+                        Nfaces=int(ops.Nfaces), collocated=collocated, affine=1, K=int(md.K), n_halo=int(n_halo),
+                        gamma=1.4, lf_scale=float(ops.lf_scale), volume_scale=float(ops.volume_scale))
+        self.desc = d
+        code = lib.esdg_create(C.byref(d), int(device), C.byref(self._ctx))
+        if code != L.ESDG_OK:
+            msg = lib.esdg_last_error(self._ctx) if self._ctx else b"esdg_create failed"
+            lib.esdg_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+            raise L.EsdgError(code, (msg or b"").decode())
+        self._finalizer = weakref.finalize(self, lib.esdg_destroy, self._ctx)
+        if stream is not None:
+            self._ck(lib.esdg_set_stream(self._ctx, C.c_void_p(int(stream))))
+        # operators (Julia: Matrix(A) of the ops tuple / rd fields)
+        names = ["Qrh", "Qsh", "Qth"][:dim]
+        for n, A in zip(names, ops.Qskew):
+            self._set_op(n, A)
+        self._set_op("Ph", ops.Ph)
+        self._set_op("Lf", ops.Lf)
+        self._set_op("wq", np.asarray(ops.wq).reshape(-1, 1))
+        if collocated:
+            self._set_op("Ef", ops.Ef)
+        else:
+            self._set_op("Vq", ops.Vq)
+            self._set_op("VhP", ops.VhP)
+        # geometry
+        gnames = ["rxJ", "sxJ", "ryJ", "syJ", "J", "nxJ", "nyJ", "sJ"] if dim == 2 else \
+                 ["rxJ", "sxJ", "txJ", "ryJ", "syJ", "tyJ", "rzJ", "szJ", "tzJ", "J", "nxJ", "nyJ", "nzJ", "sJ"]
+        for n in gnames:
+            a = L.f64(np.atleast_2d(getattr(md, n)))
+            self._ck(lib.esdg_set_geometry(self._ctx, n.encode(), a.ctypes.data, a.shape[0], a.shape[1]))
+        mapP = np.asfortranarray(np.asarray(md.mapP, dtype=np.int64) + (1 - map_index_base))
+        self._ck(lib.esdg_set_maps(self._ctx, mapP.ctypes.data, mapP.size))
+        self._ck(lib.esdg_finalize(self._ctx))
+
+    # -- helpers ---------------------------------------------------------------
+    def _ck(self, code):
+        L.check(self._ctx, code)
+
+    def _set_op(self, name, A):
+        a = L.f64(np.atleast_2d(A))
+        self._ck(self._lib.esdg_set_operator(self._ctx, name.encode(), a.ctypes.data, a.shape[0], a.shape[1]))
+
+    def _host_fields(self, Q):
+        arrs = [L.f64(q) for q in Q]
+        if len(arrs) != self.nf or any(a.shape != (self.Ns, self.K) for a in arrs):
+            raise ValueError(f"Q must be {self.nf} arrays of shape ({self.Ns},{self.K})")
+        return arrs
+
+    # -- hot path ----------------------------------------------------------------
+    def rhs(self, Q=None, compute_rhstest=False):
+        """Drop-in for ``rhs(Q,md,ops,flux,compute_rhstest)``: returns (rhsQ, rhstest)."""
+        out = [np.empty((self.Ns, self.K), order="F") for _ in range(self.nf)]
+        rt = (C.c_double * 2)(0.0, 0.0)
+        if Q is None:
+            qp = None
+        else:
+            qin = self._host_fields(Q)
+            qp = L.ptr_array(qin)
+        self._ck(self._lib.esdg_rhs(self._ctx, qp, L.ptr_array(out), int(bool(compute_rhstest)), rt))
+        return out, float(rt[0])
+
+    def upload(self, Q):
+        qin = self._host_fields(Q)
+        self._ck(self._lib.esdg_upload_state(self._ctx, L.ptr_array(qin)))
+        self._ck(self._lib.esdg_sync(self._ctx))
+
+    def download(self, out=None):
+        if out is None:
+            out = [np.empty((self.Ns, self.K), order="F") for _ in range(self.nf)]
+        self._ck(self._lib.esdg_download_state(self._ctx, L.ptr_array(out)))
+        return out
+
+    def lsrk45(self, dt, nsteps=1, want_rhstest=False):
+        """``nsteps`` LSRK45 steps on the resident state (dg2D_euler_quad.jl:196-207)."""
+        if want_rhstest:
+            rt = C.c_double(0.0)
+            self._ck(self._lib.esdg_lsrk45_step(self._ctx, float(dt), int(nsteps), C.byref(rt)))
+            return float(rt.value)
+        self._ck(self._lib.esdg_lsrk45_step(self._ctx, float(dt), int(nsteps), None))
+        return None
+
+    def sync(self):
+        self._ck(self._lib.esdg_sync(self._ctx))
+
+    # -- multi-GPU plumbing --------------------------------------------------------
+    def set_send_list(self, idx0):
+        idx = np.ascontiguousarray(np.asarray(idx0, dtype=np.int64) + 1)
+        self._ck(self._lib.esdg_set_send_list(self._ctx, idx.ctypes.data, idx.size))
+
+    def compute_traces(self):
+        self._ck(self._lib.esdg_compute_traces(self._ctx))
+
+    def pack_send(self, dev_ptr):
+        self._ck(self._lib.esdg_pack_send(self._ctx, C.c_void_p(int(dev_ptr))))
+
+    def halo_ptr(self):
+        p = C.c_void_p()
+        s = C.c_int64()
+        self._ck(self._lib.esdg_halo_ptr(self._ctx, C.byref(p), C.byref(s)))
+        return int(p.value), int(s.value)
+
+    def stage_update(self, stage, dt, compute_rhstest=False):
+        self._ck(self._lib.esdg_stage_update(self._ctx, int(stage), float(dt), int(bool(compute_rhstest))))
+
+    def read_rhstest(self):
+        rt = C.c_double(0.0)
+        self._ck(self._lib.esdg_read_rhstest(self._ctx, C.byref(rt)))
+        return float(rt.value)
+
+    # -- introspection ---------------------------------------------------------------
+    def kernel_launches(self):
+        return int(self._lib.esdg_kernel_launches(self._ctx))
+
+    def enable_timing(self, on=True):
+        self._ck(self._lib.esdg_enable_timing(self._ctx, int(on)))
+
+    def kernel_time_ms(self, name):
+        t = C.c_double()
+        n = C.c_int64()
+        self._ck(self._lib.esdg_kernel_time_ms(self._ctx, name.encode(), C.byref(t), C.byref(n)))
+        return float(t.value), int(n.value)
+
+    def close(self):
+        self._finalizer()
+
+
+_solver_cache = []   # [(md, ops, Solver)], most recent last; the functional API keeps 4 contexts alive
+
+
+def _cached_solver(md, ops):
+    for ent in _solver_cache:
+        if ent[0] is md and ent[1] is ops:
+            return ent[2]
+    ent = (md, ops, Solver(md, ops))
+    _solver_cache.append(ent)
+    while len(_solver_cache) > 4:
+        _solver_cache.pop(0)[2].close()
+    return ent[2]
+
+
+def rhs(Q, md, ops, flux_fun=euler_fluxes, compute_rhstest=False):
+    """``rhsQ, rhstest = rhs(Q, md, ops, flux_fun, compute_rhstest)`` on the GPU.
+
+    Same call shape as the reference scripts; ``flux_fun`` must be ``euler_fluxes``
+    (the only flux the reference passes).
+    """
+    if flux_fun is not euler_fluxes:
+        raise NotImplementedError("only the entropy-conservative euler_fluxes is compiled into the kernels")
+    return _cached_solver(md, ops).rhs(Q, compute_rhstest)
+
+
+def lsrk45_steps(Q, md, ops, dt, nsteps=1, want_rhstest=False):
+    """The reference time loop (dg2D_euler_quad.jl:196-212) for ``nsteps`` steps; returns (Q, rhstest)."""
+    s = _cached_solver(md, ops)
+    s.upload(Q)
+    rt = s.lsrk45(dt, nsteps, want_rhstest)
+    return s.download(), rt

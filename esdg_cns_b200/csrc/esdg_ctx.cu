@@ -1,0 +1,622 @@
+// libesdg_b200.so -- C ABI implementation (see include/esdg_b200.h).
+#include "esdg_ctx.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "kernels_generic.cuh"
+
+using namespace esdg;
+
+#define ESDG_VERSION "esdg_b200 0.1 (sm_100a)"
+
+namespace {
+
+int fail(esdg_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? ESDG_ENOMEM : ESDG_ECUDA,             \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                         \
+    } while (0)
+
+template <class T>
+int dev_alloc(esdg_ctx* ctx, T** p, size_t n) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return fail(ctx, ESDG_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    ctx->allocs.push_back(q);
+    *p = (T*)q;
+    return ESDG_OK;
+}
+
+template <class T>
+int dev_upload(esdg_ctx* ctx, T** p, const std::vector<T>& h) {
+    int rc = dev_alloc(ctx, p, h.size());
+    if (rc) return rc;
+    if (!h.empty()) CK(cudaMemcpy(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return ESDG_OK;
+}
+
+// dense column-major -> ELL with the reference's drop tolerance
+int build_ell(esdg_ctx* ctx, const HostMat& A, double tol, DevEll* out) {
+    const int rows = (int)A.rows, cols = (int)A.cols;
+    std::vector<int> cnt(rows, 0);
+    int width = 0;
+    for (int i = 0; i < rows; ++i) {
+        for (int j = 0; j < cols; ++j)
+            if (std::fabs(A.at(i, j)) > tol) cnt[i]++;
+        width = std::max(width, cnt[i]);
+    }
+    width = std::max(width, 1);
+    std::vector<int> col((size_t)rows * width, 0);
+    std::vector<double> val((size_t)rows * width, 0.0);
+    for (int i = 0; i < rows; ++i) {
+        int k = 0;
+        for (int j = 0; j < cols; ++j)
+            if (std::fabs(A.at(i, j)) > tol) {
+                col[(size_t)i * width + k] = j;
+                val[(size_t)i * width + k] = A.at(i, j);
+                ++k;
+            }
+    }
+    out->rows = rows;
+    out->width = width;
+    int rc;
+    if ((rc = dev_upload(ctx, &out->cnt, cnt))) return rc;
+    if ((rc = dev_upload(ctx, &out->col, col))) return rc;
+    if ((rc = dev_upload(ctx, &out->val, val))) return rc;
+    return ESDG_OK;
+}
+
+const HostMat* find(const std::map<std::string, HostMat>& m, const char* name) {
+    auto it = m.find(name);
+    return it == m.end() ? nullptr : &it->second;
+}
+
+void tick(esdg_ctx* ctx, const char* name) {
+    ctx->launches++;
+    if (ctx->timing) {
+        KernelTimer t;
+        t.name = name;
+        cudaEventCreate(&t.a);
+        cudaEventCreate(&t.b);
+        cudaEventRecord(t.a, ctx->stream);
+        ctx->timers.push_back(t);
+    }
+}
+void tock(esdg_ctx* ctx) {
+    if (ctx->timing) cudaEventRecord(ctx->timers.back().b, ctx->stream);
+}
+
+void fill_params(esdg_ctx* ctx, GenericParams& p) {
+    const esdg_desc& d = ctx->d;
+    p.Ns = d.Ns; p.Nq = d.Nq; p.Nfq = d.Nfq; p.Nh = ctx->Nh; p.Nfaces = d.Nfaces; p.Nfp = ctx->Nfp;
+    p.collocated = d.collocated;
+    p.EB = ctx->EB;
+    p.K = d.K;
+    p.trace_stride = ctx->trace_stride;
+    p.gamma = d.gamma; p.lf_scale = d.lf_scale; p.volume_scale = d.volume_scale;
+    p.Vq = ctx->Vq.view();
+    p.Proj = ctx->Proj.view();
+    p.Ph = ctx->Ph.view();
+    p.Lf = ctx->Lf.view();
+    p.Qp = PairEll{ctx->Nh, ctx->qp_width, ctx->qp_cnt, ctx->qp_col, ctx->qp_c};
+    p.wq = ctx->wq;
+    p.geo = ctx->geo;
+    p.geo_stride = ctx->geo_stride;
+    p.mapP = ctx->mapP;
+    p.Q = ctx->Q;
+    p.q_stride = (long long)d.Ns * d.K;
+    p.traces = ctx->traces;
+    p.rhs = ctx->rhs;
+    p.Qout = ctx->Q;
+    p.res = ctx->res;
+    p.rk_a = 0; p.rk_b = 0; p.dt = 0;
+    p.mode = 0;
+    p.want_rhstest = 0;
+    p.rhstest_partial = ctx->partials;
+    p.bad_flag = ctx->bad_flag;
+}
+
+int grid_blocks(const esdg_ctx* ctx) { return (int)((ctx->d.K + ctx->EB - 1) / ctx->EB); }
+
+int launch_traces(esdg_ctx* ctx, const double* Qsrc) {
+    GenericParams p;
+    fill_params(ctx, p);
+    p.Q = Qsrc;
+    tick(ctx, "generic_traces");
+    if (ctx->d.dim == 2)
+        k_generic_traces<2><<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(p);
+    else
+        k_generic_traces<3><<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(p);
+    tock(ctx);
+    CK(cudaGetLastError());
+    return ESDG_OK;
+}
+
+int launch_rhs(esdg_ctx* ctx, const double* Qsrc, int mode, double a, double b, double dt, int want_rhstest) {
+    GenericParams p;
+    fill_params(ctx, p);
+    p.Q = Qsrc;
+    p.mode = mode;
+    p.rk_a = a; p.rk_b = b; p.dt = dt;
+    p.want_rhstest = want_rhstest;
+    tick(ctx, "generic_rhs");
+    if (ctx->d.dim == 2)
+        k_generic_rhs<2><<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(p);
+    else
+        k_generic_rhs<3><<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(p);
+    tock(ctx);
+    CK(cudaGetLastError());
+    if (want_rhstest) {
+        tick(ctx, "reduce_partials");
+        k_reduce_partials<<<1, 256, 0, ctx->stream>>>(ctx->partials, grid_blocks(ctx), ctx->rhstest_dev);
+        tock(ctx);
+        CK(cudaGetLastError());
+    }
+    return ESDG_OK;
+}
+
+int check_bad(esdg_ctx* ctx) {
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, ctx->bad_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (flag) {
+        CK(cudaMemsetAsync(ctx->bad_flag, 0, sizeof(int), ctx->stream));
+        return fail(ctx, ESDG_ESTATE, "non-positive density or internal energy met in rhs (Julia: DomainError)");
+    }
+    return ESDG_OK;
+}
+
+const double RK4A[5] = {0.0, -567301805773.0 / 1357537059087.0, -2404267990393.0 / 2016746695238.0,
+                        -3550918686646.0 / 2091501179385.0, -1275806237668.0 / 842570457699.0};
+const double RK4B[5] = {1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0,
+                        1720146321549.0 / 2090206949498.0, 3134564353537.0 / 4481467310338.0,
+                        2277821191437.0 / 14882151754819.0};  // src/CommonUtils.jl:29-49
+
+}  // namespace
+
+extern "C" {
+
+const char* esdg_version(void) { return ESDG_VERSION; }
+
+int esdg_create(const esdg_desc* desc, int device, esdg_ctx** out) {
+    if (!desc || !out) return ESDG_EINVAL;
+    *out = nullptr;
+    esdg_ctx* ctx = new esdg_ctx();
+    ctx->d = *desc;
+    ctx->device = device;
+    *out = ctx;  // returned even on failure so that esdg_last_error works
+    const esdg_desc& d = ctx->d;
+    if (!(d.dim == 2 || d.dim == 3) || d.Nfields != d.dim + 2 || d.K <= 0 || d.Ns <= 0 || d.Nq <= 0 ||
+        d.Nfq <= 0 || d.Nfaces <= 0 || d.Nfq % d.Nfaces != 0 || d.n_halo < 0)
+        return fail(ctx, ESDG_EINVAL, "esdg_create: inconsistent descriptor");
+    if (d.affine != 1) return fail(ctx, ESDG_EINVAL, "esdg_create: only affine meshes are supported (desc.affine must be 1)");
+    if (d.collocated && d.Ns != d.Nq) return fail(ctx, ESDG_EINVAL, "esdg_create: collocated needs Ns == Nq");
+    if ((double)d.Nfq * (double)d.K + (double)d.n_halo > 2.0e9)
+        return fail(ctx, ESDG_EINVAL, "esdg_create: Nfq*K+n_halo exceeds 32-bit trace indexing");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(ctx, ESDG_ECUDA, "esdg_create: no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(ctx, ESDG_EINVAL, "esdg_create: bad device ordinal");
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+    ctx->Nh = d.Nq + d.Nfq;
+    ctx->Nfp = d.Nfq / d.Nfaces;
+    ctx->NF = d.Nfields;
+    ctx->trace_stride = (long long)d.Nfq * d.K + d.n_halo;
+    return ESDG_OK;
+}
+
+int esdg_destroy(esdg_ctx* ctx) {
+    if (!ctx) return ESDG_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& t : ctx->timers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (void* p : ctx->allocs) cudaFree(p);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return ESDG_OK;
+}
+
+const char* esdg_last_error(const esdg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int esdg_set_stream(esdg_ctx* ctx, void* s) {
+    if (!ctx) return ESDG_EINVAL;
+    if (ctx->own_stream && ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    ctx->stream = (cudaStream_t)s;
+    ctx->own_stream = false;
+    return ESDG_OK;
+}
+
+int esdg_set_operator(esdg_ctx* ctx, const char* name, const double* a, int64_t rows, int64_t cols) {
+    if (!ctx || !name || !a || rows <= 0 || cols <= 0) return fail(ctx, ESDG_EINVAL, "esdg_set_operator: bad argument");
+    static const char* known[] = {"Ef", "Vq", "VhP", "Ph", "Lf", "Qrh", "Qsh", "Qth", "wq"};
+    bool ok = false;
+    for (const char* k : known) ok = ok || !strcmp(k, name);
+    if (!ok) return fail(ctx, ESDG_EINVAL, std::string("esdg_set_operator: unknown operator ") + name);
+    HostMat m;
+    m.rows = rows; m.cols = cols;
+    m.a.assign(a, a + rows * cols);
+    ctx->ops[name] = std::move(m);
+    ctx->finalized = false;
+    return ESDG_OK;
+}
+
+int esdg_set_geometry(esdg_ctx* ctx, const char* name, const double* a, int64_t rows, int64_t cols) {
+    if (!ctx || !name || !a || rows <= 0) return fail(ctx, ESDG_EINVAL, "esdg_set_geometry: bad argument");
+    if (cols != ctx->d.K) return fail(ctx, ESDG_EINVAL, "esdg_set_geometry: cols must equal desc.K");
+    static const char* known[] = {"rxJ", "sxJ", "txJ", "ryJ", "syJ", "tyJ", "rzJ", "szJ", "tzJ",
+                                  "J", "nxJ", "nyJ", "nzJ", "sJ", "wJq"};
+    bool ok = false;
+    for (const char* k : known) ok = ok || !strcmp(k, name);
+    if (!ok) return fail(ctx, ESDG_EINVAL, std::string("esdg_set_geometry: unknown array ") + name);
+    HostMat m;
+    m.rows = rows; m.cols = cols;
+    m.a.assign(a, a + rows * cols);
+    ctx->geom[name] = std::move(m);
+    ctx->finalized = false;
+    return ESDG_OK;
+}
+
+int esdg_set_maps(esdg_ctx* ctx, const int64_t* mapP, int64_t n) {
+    if (!ctx || !mapP) return fail(ctx, ESDG_EINVAL, "esdg_set_maps: bad argument");
+    if (n != (int64_t)ctx->d.Nfq * ctx->d.K) return fail(ctx, ESDG_EINVAL, "esdg_set_maps: mapP must hold Nfq*K entries");
+    ctx->mapP_host.assign(mapP, mapP + n);
+    ctx->finalized = false;
+    return ESDG_OK;
+}
+
+int esdg_finalize(esdg_ctx* ctx) {
+    if (!ctx) return ESDG_EINVAL;
+    const esdg_desc& d = ctx->d;
+    const int DIM = d.dim, NF = d.Nfields, Nh = ctx->Nh;
+    CK(cudaSetDevice(ctx->device));
+    // ---- operators -----------------------------------------------------------
+    auto need = [&](const char* n, int64_t r, int64_t c) -> const HostMat* {
+        const HostMat* m = find(ctx->ops, n);
+        if (!m) { fail(ctx, ESDG_EINVAL, std::string("esdg_finalize: operator missing: ") + n); return nullptr; }
+        if (m->rows != r || m->cols != c) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "esdg_finalize: operator %s is %lldx%lld, expected %lldx%lld", n,
+                     (long long)m->rows, (long long)m->cols, (long long)r, (long long)c);
+            fail(ctx, ESDG_EINVAL, buf);
+            return nullptr;
+        }
+        return m;
+    };
+    const double TOL = 1e-12;  // droptol of dg2D_euler_quad.jl:62-63,76-78
+    int rc;
+    if (d.collocated) {
+        const HostMat* Ef = need("Ef", d.Nfq, d.Nq);
+        if (!Ef) return ESDG_EINVAL;
+        if ((rc = build_ell(ctx, *Ef, TOL, &ctx->Proj))) return rc;
+        HostMat eye; eye.rows = eye.cols = 1; eye.a = {1.0};
+        if ((rc = build_ell(ctx, eye, TOL, &ctx->Vq))) return rc;
+    } else {
+        const HostMat* Vq = need("Vq", d.Nq, d.Ns);
+        const HostMat* VhP = need("VhP", Nh, d.Nq);
+        if (!Vq || !VhP) return ESDG_EINVAL;
+        if ((rc = build_ell(ctx, *Vq, 0.0, &ctx->Vq))) return rc;
+        if ((rc = build_ell(ctx, *VhP, 0.0, &ctx->Proj))) return rc;
+    }
+    const HostMat* Ph = need("Ph", d.Ns, Nh);
+    const HostMat* Lf = need("Lf", d.Ns, d.Nfq);
+    const HostMat* wq = need("wq", d.Nq, 1);
+    if (!Ph || !Lf || !wq) return ESDG_EINVAL;
+    if ((rc = build_ell(ctx, *Ph, d.collocated ? TOL : 0.0, &ctx->Ph))) return rc;
+    if ((rc = build_ell(ctx, *Lf, d.collocated ? TOL : 0.0, &ctx->Lf))) return rc;
+    if ((rc = dev_upload(ctx, &ctx->wq, wq->a))) return rc;
+    const char* qn[3] = {"Qrh", "Qsh", "Qth"};
+    const HostMat* Qm[3] = {nullptr, nullptr, nullptr};
+    for (int k = 0; k < DIM; ++k)
+        if (!(Qm[k] = need(qn[k], Nh, Nh))) return ESDG_EINVAL;
+    {
+        std::vector<int> cnt(Nh, 0);
+        int width = 1;
+        auto nz = [&](int i, int j) {
+            for (int k = 0; k < DIM; ++k)
+                if (std::fabs(Qm[k]->at(i, j)) > TOL) return true;
+            return false;
+        };
+        for (int i = 0; i < Nh; ++i) {
+            for (int j = 0; j < Nh; ++j) cnt[i] += nz(i, j);
+            width = std::max(width, cnt[i]);
+        }
+        std::vector<int> col((size_t)Nh * width, 0);
+        std::vector<double> c((size_t)Nh * width * 3, 0.0);
+        for (int i = 0; i < Nh; ++i) {
+            int k = 0;
+            for (int j = 0; j < Nh; ++j)
+                if (nz(i, j)) {
+                    col[(size_t)i * width + k] = j;
+                    for (int q = 0; q < DIM; ++q) {
+                        const double v = Qm[q]->at(i, j);
+                        c[((size_t)i * width + k) * 3 + q] = std::fabs(v) > TOL ? v : 0.0;
+                    }
+                    ++k;
+                }
+        }
+        ctx->qp_width = width;
+        if ((rc = dev_upload(ctx, &ctx->qp_cnt, cnt))) return rc;
+        if ((rc = dev_upload(ctx, &ctx->qp_col, col))) return rc;
+        if ((rc = dev_upload(ctx, &ctx->qp_c, c))) return rc;
+    }
+    // ---- geometry (affine: one record per element) -----------------------------
+    static const char* g2[4] = {"rxJ", "sxJ", "ryJ", "syJ"};
+    static const char* g3[9] = {"rxJ", "sxJ", "txJ", "ryJ", "syJ", "tyJ", "rzJ", "szJ", "tzJ"};
+    static const char* nn[4] = {"nxJ", "nyJ", "nzJ", "sJ"};
+    ctx->geo_stride = DIM * DIM + 1 + d.Nfaces * (DIM + 1);
+    std::vector<double> geo((size_t)d.K * ctx->geo_stride);
+    {
+        const HostMat* G[9];
+        for (int k = 0; k < DIM * DIM; ++k) {
+            G[k] = find(ctx->geom, DIM == 2 ? g2[k] : g3[k]);
+            if (!G[k]) return fail(ctx, ESDG_EINVAL, std::string("esdg_finalize: geometry missing: ") + (DIM == 2 ? g2[k] : g3[k]));
+        }
+        const HostMat* J = find(ctx->geom, "J");
+        if (!J) return fail(ctx, ESDG_EINVAL, "esdg_finalize: geometry missing: J");
+        const HostMat* Nn[4];
+        for (int k = 0; k <= DIM; ++k) {
+            const char* nm = (k == DIM) ? "sJ" : nn[k];
+            Nn[k] = find(ctx->geom, nm);
+            if (!Nn[k]) return fail(ctx, ESDG_EINVAL, std::string("esdg_finalize: geometry missing: ") + nm);
+            if (Nn[k]->rows != d.Nfq && Nn[k]->rows != d.Nfaces)
+                return fail(ctx, ESDG_EINVAL, std::string("esdg_finalize: rows of ") + nm + " must be Nfq or Nfaces");
+        }
+        for (int64_t e = 0; e < d.K; ++e) {
+            double* g = &geo[(size_t)e * ctx->geo_stride];
+            for (int k = 0; k < DIM * DIM; ++k) g[k] = G[k]->at(0, e);        // `[1,e]`, dg2D_euler_quad.jl:175
+            g[DIM * DIM] = J->at(0, e);
+            if (!(g[DIM * DIM] > 0.0)) return fail(ctx, ESDG_EINVAL, "esdg_finalize: non-positive Jacobian J");
+            for (int f = 0; f < d.Nfaces; ++f)
+                for (int k = 0; k <= DIM; ++k) {
+                    const int64_t row0 = (Nn[k]->rows == d.Nfaces) ? f : (int64_t)f * ctx->Nfp;
+                    const double v0 = Nn[k]->at(row0, e);
+                    g[DIM * DIM + 1 + f * (DIM + 1) + k] = v0;
+                    if (Nn[k]->rows == d.Nfq) {  // affine check: constant along the face
+                        for (int q = 1; q < ctx->Nfp; ++q)
+                            if (std::fabs(Nn[k]->at(row0 + q, e) - v0) > 1e-10 * (std::fabs(v0) + g[DIM * DIM]))
+                                return fail(ctx, ESDG_EINVAL, "esdg_finalize: face normals vary along a face (mesh not affine)");
+                    }
+                }
+            // affine check on the volume geofacs / J when full arrays were given
+            for (int k = 0; k < DIM * DIM; ++k)
+                for (int64_t r = 1; r < G[k]->rows; ++r)
+                    if (std::fabs(G[k]->at(r, e) - g[k]) > 1e-10 * (std::fabs(g[k]) + 1e-300 + std::fabs(g[DIM * DIM])))
+                        return fail(ctx, ESDG_EINVAL, "esdg_finalize: volume geometric factors vary inside an element (mesh not affine)");
+        }
+    }
+    if ((rc = dev_upload(ctx, &ctx->geo, geo))) return rc;
+    // ---- maps ------------------------------------------------------------------
+    if ((int64_t)ctx->mapP_host.size() != (int64_t)d.Nfq * d.K)
+        return fail(ctx, ESDG_EINVAL, "esdg_finalize: mapP missing (esdg_set_maps)");
+    {
+        std::vector<int> mp(ctx->mapP_host.size());
+        for (size_t i = 0; i < mp.size(); ++i) {
+            const int64_t v = ctx->mapP_host[i] - 1;  // Julia 1-based
+            if (v < 0 || v >= ctx->trace_stride) return fail(ctx, ESDG_EINVAL, "esdg_finalize: mapP entry out of range");
+            mp[i] = (int)v;
+        }
+        if ((rc = dev_upload(ctx, &ctx->mapP, mp))) return rc;
+    }
+    // ---- launch shape ------------------------------------------------------------
+    int maxsm = 0;
+    CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    int EB = std::max(1, ESDG_GENERIC_MAX_THREADS / Nh);
+    EB = std::min<int64_t>(EB, 16);
+    while (EB > 1 && generic_smem_bytes(DIM, EB, d.Ns, d.Nq, d.Nfq, Nh, d.collocated) > (size_t)maxsm / 2) --EB;
+    ctx->EB = EB;
+    ctx->smem_bytes = generic_smem_bytes(DIM, EB, d.Ns, d.Nq, d.Nfq, Nh, d.collocated);
+    if (ctx->smem_bytes > (size_t)maxsm) return fail(ctx, ESDG_EINVAL, "esdg_finalize: element too large for shared memory");
+    ctx->threads = std::min(ESDG_GENERIC_MAX_THREADS, ((EB * Nh + 31) / 32) * 32);
+    if (DIM == 2) {
+        CK(cudaFuncSetAttribute(k_generic_traces<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+        CK(cudaFuncSetAttribute(k_generic_rhs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+    } else {
+        CK(cudaFuncSetAttribute(k_generic_traces<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+        CK(cudaFuncSetAttribute(k_generic_rhs<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+    }
+    // ---- state -------------------------------------------------------------------
+    const size_t nstate = (size_t)NF * d.Ns * d.K;
+    if ((rc = dev_alloc(ctx, &ctx->Q, nstate))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->res, nstate))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->rhs, nstate))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->Qin, nstate))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->traces, (size_t)NF * ctx->trace_stride))) return rc;
+    ctx->n_partials = grid_blocks(ctx);
+    if ((rc = dev_alloc(ctx, &ctx->partials, (size_t)ctx->n_partials))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->rhstest_dev, 2))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->bad_flag, 1))) return rc;
+    CK(cudaMemset(ctx->bad_flag, 0, sizeof(int)));
+    CK(cudaMemset(ctx->res, 0, nstate * sizeof(double)));
+    CK(cudaMemset(ctx->traces, 0, (size_t)NF * ctx->trace_stride * sizeof(double)));
+    CK(cudaMemset(ctx->rhstest_dev, 0, 2 * sizeof(double)));
+    ctx->finalized = true;
+    return ESDG_OK;
+}
+
+static int require_ready(esdg_ctx* ctx, const char* who) {
+    if (!ctx) return ESDG_EINVAL;
+    if (!ctx->finalized) return fail(ctx, ESDG_EINVAL, std::string(who) + ": esdg_finalize has not been called");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return fail(ctx, ESDG_ECUDA, cudaGetErrorString(e));
+    return ESDG_OK;
+}
+
+int esdg_upload_state(esdg_ctx* ctx, const double* const* Q) {
+    int rc = require_ready(ctx, "esdg_upload_state");
+    if (rc) return rc;
+    if (!Q) return fail(ctx, ESDG_EINVAL, "esdg_upload_state: Q is NULL");
+    const size_t n = (size_t)ctx->d.Ns * ctx->d.K;
+    for (int f = 0; f < ctx->NF; ++f)
+        CK(cudaMemcpyAsync(ctx->Q + f * n, Q[f], n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->res, 0, ctx->NF * n * sizeof(double), ctx->stream));
+    ctx->traces_valid = false;
+    return ESDG_OK;
+}
+
+int esdg_download_state(esdg_ctx* ctx, double* const* Q) {
+    int rc = require_ready(ctx, "esdg_download_state");
+    if (rc) return rc;
+    if (!Q) return fail(ctx, ESDG_EINVAL, "esdg_download_state: Q is NULL");
+    const size_t n = (size_t)ctx->d.Ns * ctx->d.K;
+    for (int f = 0; f < ctx->NF; ++f)
+        CK(cudaMemcpyAsync(Q[f], ctx->Q + f * n, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return check_bad(ctx);
+}
+
+int esdg_rhs(esdg_ctx* ctx, const double* const* Q, double* const* rhs_out, int compute_rhstest, double* rhstest) {
+    int rc = require_ready(ctx, "esdg_rhs");
+    if (rc) return rc;
+    if (!rhs_out) return fail(ctx, ESDG_EINVAL, "esdg_rhs: rhs_out is NULL");
+    if (ctx->d.n_halo != 0)
+        return fail(ctx, ESDG_EINVAL, "esdg_rhs: context has halo points; drive it with esdg_compute_traces / esdg_stage_update");
+    const size_t n = (size_t)ctx->d.Ns * ctx->d.K;
+    const double* src = ctx->Q;
+    if (Q) {
+        for (int f = 0; f < ctx->NF; ++f)
+            CK(cudaMemcpyAsync(ctx->Qin + f * n, Q[f], n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        src = ctx->Qin;
+    }
+    if ((rc = launch_traces(ctx, src))) return rc;
+    if ((rc = launch_rhs(ctx, src, 0, 0, 0, 0, compute_rhstest))) return rc;
+    ctx->traces_valid = false;
+    for (int f = 0; f < ctx->NF; ++f)
+        CK(cudaMemcpyAsync(rhs_out[f], ctx->rhs + f * n, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    double t[2] = {0, 0};
+    if (compute_rhstest) CK(cudaMemcpyAsync(t, ctx->rhstest_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = check_bad(ctx))) return rc;
+    if (rhstest) { rhstest[0] = t[0]; }
+    return ESDG_OK;
+}
+
+int esdg_lsrk45_step(esdg_ctx* ctx, double dt, int nsteps, double* rhstest_last) {
+    int rc = require_ready(ctx, "esdg_lsrk45_step");
+    if (rc) return rc;
+    if (ctx->d.n_halo != 0)
+        return fail(ctx, ESDG_EINVAL, "esdg_lsrk45_step: context has halo points; drive stages with esdg_stage_update");
+    for (int s = 0; s < nsteps; ++s)
+        for (int k = 0; k < 5; ++k) {
+            const int want = (rhstest_last != nullptr) && (s == nsteps - 1) && (k == 4);  // dg2D_euler_quad.jl:202
+            if ((rc = launch_traces(ctx, ctx->Q))) return rc;
+            if ((rc = launch_rhs(ctx, ctx->Q, 1, RK4A[k], RK4B[k], dt, want))) return rc;
+        }
+    if (rhstest_last) {
+        CK(cudaMemcpyAsync(rhstest_last, ctx->rhstest_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        return check_bad(ctx);
+    }
+    return ESDG_OK;
+}
+
+int esdg_sync(esdg_ctx* ctx) {
+    int rc = require_ready(ctx, "esdg_sync");
+    if (rc) return rc;
+    return check_bad(ctx);
+}
+
+// ---- multi-GPU plumbing ----------------------------------------------------------
+int esdg_set_send_list(esdg_ctx* ctx, const int64_t* idx, int64_t n) {
+    int rc = require_ready(ctx, "esdg_set_send_list");
+    if (rc) return rc;
+    std::vector<int> h((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t v = idx[i] - 1;
+        if (v < 0 || v >= (int64_t)ctx->d.Nfq * ctx->d.K) return fail(ctx, ESDG_EINVAL, "esdg_set_send_list: index out of range");
+        h[(size_t)i] = (int)v;
+    }
+    ctx->n_send = n;
+    return dev_upload(ctx, &ctx->send_idx, h);
+}
+
+__global__ void k_pack_send(const double* __restrict__ traces, long long stride, const int* __restrict__ idx,
+                            long long n, int nf, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int j = idx[i];
+    for (int f = 0; f < nf; ++f) out[f * n + i] = traces[f * stride + j];
+}
+
+int esdg_compute_traces(esdg_ctx* ctx) {
+    int rc = require_ready(ctx, "esdg_compute_traces");
+    if (rc) return rc;
+    return launch_traces(ctx, ctx->Q);
+}
+
+int esdg_pack_send(esdg_ctx* ctx, void* send_dev) {
+    int rc = require_ready(ctx, "esdg_pack_send");
+    if (rc) return rc;
+    if (ctx->n_send == 0) return ESDG_OK;
+    tick(ctx, "pack_send");
+    k_pack_send<<<(unsigned)((ctx->n_send + 255) / 256), 256, 0, ctx->stream>>>(ctx->traces, ctx->trace_stride, ctx->send_idx,
+                                                                               ctx->n_send, ctx->NF, (double*)send_dev);
+    tock(ctx);
+    CK(cudaGetLastError());
+    return ESDG_OK;
+}
+
+int esdg_halo_ptr(esdg_ctx* ctx, void** halo_dev, int64_t* field_stride) {
+    int rc = require_ready(ctx, "esdg_halo_ptr");
+    if (rc) return rc;
+    if (halo_dev) *halo_dev = ctx->traces + (long long)ctx->d.Nfq * ctx->d.K;
+    if (field_stride) *field_stride = ctx->trace_stride;
+    return ESDG_OK;
+}
+
+int esdg_stage_update(esdg_ctx* ctx, int stage, double dt, int compute_rhstest) {
+    int rc = require_ready(ctx, "esdg_stage_update");
+    if (rc) return rc;
+    if (stage < 0 || stage > 4) return fail(ctx, ESDG_EINVAL, "esdg_stage_update: stage must be 0..4");
+    return launch_rhs(ctx, ctx->Q, 1, RK4A[stage], RK4B[stage], dt, compute_rhstest);
+}
+
+int esdg_read_rhstest(esdg_ctx* ctx, double* rhstest) {
+    int rc = require_ready(ctx, "esdg_read_rhstest");
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(rhstest, ctx->rhstest_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return check_bad(ctx);
+}
+
+// ---- introspection ---------------------------------------------------------------
+int64_t esdg_kernel_launches(const esdg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int esdg_enable_timing(esdg_ctx* ctx, int on) {
+    if (!ctx) return ESDG_EINVAL;
+    ctx->timing = on != 0;
+    return ESDG_OK;
+}
+
+int esdg_kernel_time_ms(esdg_ctx* ctx, const char* kernel, double* total_ms, int64_t* launches) {
+    if (!ctx || !kernel) return ESDG_EINVAL;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& t : ctx->timers) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t.a, t.b);
+        auto& acc = ctx->time_acc[t.name];
+        acc.first += ms;
+        acc.second += 1;
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    ctx->timers.clear();
+    auto it = ctx->time_acc.find(kernel);
+    if (total_ms) *total_ms = it == ctx->time_acc.end() ? 0.0 : it->second.first;
+    if (launches) *launches = it == ctx->time_acc.end() ? 0 : it->second.second;
+    return ESDG_OK;
+}
+
+}  // extern "C"

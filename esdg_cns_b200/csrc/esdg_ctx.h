@@ -1,0 +1,77 @@
+// Host-side context behind the opaque `esdg_ctx` of include/esdg_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/esdg_b200.h"
+#include "device_tables.h"
+
+struct HostMat {
+    int64_t rows = 0, cols = 0;
+    std::vector<double> a;  // column-major
+    double at(int64_t i, int64_t j) const { return a[i + rows * j]; }
+};
+
+struct DevEll {
+    int rows = 0, width = 0;
+    int* cnt = nullptr;
+    int* col = nullptr;
+    double* val = nullptr;
+    esdg::Ell view() const { return esdg::Ell{rows, width, cnt, col, val}; }
+};
+
+struct KernelTimer {
+    std::string name;
+    cudaEvent_t a, b;
+};
+
+struct esdg_ctx {
+    esdg_desc d{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    bool finalized = false;
+    std::string err;
+
+    std::map<std::string, HostMat> ops, geom;
+    std::vector<int64_t> mapP_host;
+    std::vector<int64_t> send_list;
+
+    // derived sizes
+    int Nh = 0, Nfp = 0, NF = 0, EB = 1, threads = 256, geo_stride = 0;
+    size_t smem_bytes = 0;
+    long long trace_stride = 0;
+
+    // device tables
+    DevEll Vq, Proj, Ph, Lf;
+    int *qp_cnt = nullptr, *qp_col = nullptr;
+    double* qp_c = nullptr;
+    int qp_width = 0;
+    double* wq = nullptr;
+    double* geo = nullptr;
+    int* mapP = nullptr;
+    int* send_idx = nullptr;
+    long long n_send = 0;
+
+    // state
+    double *Q = nullptr, *res = nullptr, *rhs = nullptr, *traces = nullptr;
+    double *Qin = nullptr;  // staging for esdg_rhs(Q given)
+    double *partials = nullptr, *rhstest_dev = nullptr;
+    int n_partials = 0;
+    int* bad_flag = nullptr;
+    bool traces_valid = false;
+
+    // specialised hex path (kernels_hex.cuh); null if the operators do not match
+    struct HexFast* hex = nullptr;
+
+    // accounting
+    int64_t launches = 0;
+    bool timing = false;
+    std::vector<KernelTimer> timers;
+    std::map<std::string, std::pair<double, int64_t>> time_acc;
+
+    std::vector<void*> allocs;
+};

@@ -1,0 +1,350 @@
+// Generic (operator-table driven) kernels: any element type whose operators
+// arrive through esdg_set_operator -- quads, hexes in any node ordering, and
+// modal triangles.  One CTA owns a batch of EB consecutive elements; every
+// phase is a strided loop over (element, row) items followed by a barrier, all
+// element data staged in shared memory.
+//
+// Path covered (reference call stack):
+//   phase 1  VU = v_ufun(Q) [tri: v_ufun(Vq*Q)]              dg2D_euler_quad.jl:149 / tri :138
+//   phase 2  Uf = u_vfun(Ef*VU) [tri: Uh = u_vfun(VhP*VU)]    :150 / tri :139-140
+//            Qh = (rho,u,v[,w],beta), logs                     :154-155, :111
+//   phase 3  QP = QM[mapP]; LF; flux*                          :158-168
+//   phase 4  sparse/dense Hadamard sum                         :102-138 / tri :88-126
+//   phase 5  rhs = -(Lf*flux + vs*Ph*QF)/J                     :170,180,184
+//   phase 6  rhstest / fused LSRK stage                        :186-191 / :205-206
+#pragma once
+#include "device_tables.h"
+#include "physics.cuh"
+
+#define ESDG_GENERIC_MAX_THREADS 320
+
+namespace esdg {
+
+template <int DIM>
+struct GenericSmem {
+    static constexpr int NF = DIM + 2;
+    double *U, *V, *W, *Uf, *Fl, *QF, *VP, *R;
+    __device__ GenericSmem(double* base, const GenericParams& p) {
+        const int EB = p.EB;
+        U = base;                         // [EB][NF][Ns]
+        V = U + EB * NF * p.Ns;           // [EB][NF][Nq]
+        W = V + EB * NF * p.Nq;           // [EB][NF+2][Nh]
+        Uf = W + EB * (NF + 2) * p.Nh;    // [EB][NF][Nfq]
+        Fl = Uf + EB * NF * p.Nfq;        // [EB][NF][Nfq]
+        QF = Fl + EB * NF * p.Nfq;        // [EB][NF][Nh]
+        VP = QF + EB * NF * p.Nh;         // [EB][NF][Nq] (modal only: projected entropy vars, volume rows)
+        R = VP + EB * NF * p.Nq;          // [EB][NF][Ns] (modal only: rhs for the rhstest quadrature)
+    }
+};
+
+inline size_t generic_smem_bytes(int DIM, int EB, int Ns, int Nq, int Nfq, int Nh, int collocated) {
+    const int NF = DIM + 2;
+    size_t n = (size_t)EB * (NF * Ns + NF * Nq + (NF + 2) * Nh + 2 * NF * Nfq + NF * Nh + (collocated ? 0 : NF * (Ns + Nq)));
+    return n * sizeof(double);
+}
+
+// Phases 0-2: stage Q, entropy-project, build Qh (+logs) at all hybridized points.
+template <int DIM>
+__device__ __forceinline__ void project_batch(const GenericParams& p, GenericSmem<DIM>& s, long long e0, int nb,
+                                              bool& bad) {
+    constexpr int NF = DIM + 2;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    // phase 0: Q -> smem (contiguous per field across the batch: coalesced)
+    for (int f = 0; f < NF; ++f) {
+        const double* src = p.Q + f * p.q_stride + e0 * p.Ns;
+        for (int i = tid; i < nb * p.Ns; i += nt) {
+            const int eb = i / p.Ns, k = i - eb * p.Ns;
+            s.U[(eb * NF + f) * p.Ns + k] = src[i];
+        }
+    }
+    __syncthreads();
+    // phase 1: entropy variables at the volume quadrature points
+    for (int i = tid; i < nb * p.Nq; i += nt) {
+        const int eb = i / p.Nq, q = i - eb * p.Nq;
+        double U[NF], V[NF];
+        if (p.collocated) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) U[f] = s.U[(eb * NF + f) * p.Ns + q];
+        } else {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) U[f] = 0.0;
+            const int n = p.Vq.cnt[q];
+            for (int k = 0; k < n; ++k) {
+                const int c = p.Vq.col[q * p.Vq.width + k];
+                const double a = p.Vq.val[q * p.Vq.width + k];
+#pragma unroll
+                for (int f = 0; f < NF; ++f) U[f] = fma(a, s.U[(eb * NF + f) * p.Ns + c], U[f]);
+            }
+        }
+        v_of_u<DIM>(U, p.gamma, V, bad);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) s.V[(eb * NF + f) * p.Nq + q] = V[f];
+    }
+    __syncthreads();
+    // phase 2: projected conservative variables -> primitive + logs
+    for (int i = tid; i < nb * p.Nh; i += nt) {
+        const int eb = i / p.Nh, r = i - eb * p.Nh;
+        double U[NF];
+        if (p.collocated && r < p.Nq) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) U[f] = s.U[(eb * NF + f) * p.Ns + r];
+        } else {
+            const int pr = p.collocated ? r - p.Nq : r;
+            double V[NF];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) V[f] = 0.0;
+            const int n = p.Proj.cnt[pr];
+            for (int k = 0; k < n; ++k) {
+                const int c = p.Proj.col[pr * p.Proj.width + k];
+                const double a = p.Proj.val[pr * p.Proj.width + k];
+#pragma unroll
+                for (int f = 0; f < NF; ++f) V[f] = fma(a, s.V[(eb * NF + f) * p.Nq + c], V[f]);
+            }
+            u_of_v<DIM>(V, p.gamma, U);
+            if (!p.collocated && r < p.Nq) {
+                // projected entropy variables at volume points are the rhstest weights (tri :180)
+#pragma unroll
+                for (int f = 0; f < NF; ++f) s.VP[(eb * NF + f) * p.Nq + r] = V[f];
+            }
+        }
+        Prim<DIM> P;
+        prim_of_u<DIM>(U, p.gamma, P);
+        double* w = s.W + (size_t)eb * (NF + 2) * p.Nh + r;
+        w[0] = P.rho;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) w[(1 + d) * p.Nh] = P.vel[d];
+        w[(1 + DIM) * p.Nh] = P.beta;
+        w[(2 + DIM) * p.Nh] = P.lrho;
+        w[(3 + DIM) * p.Nh] = P.lbeta;
+        if (r >= p.Nq) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) s.Uf[(eb * NF + f) * p.Nfq + (r - p.Nq)] = U[f];
+        }
+    }
+    __syncthreads();
+}
+
+// Kernel A: face traces of the (projected) conservative variables.
+template <int DIM>
+__global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_traces(const __grid_constant__ GenericParams p) {
+    constexpr int NF = DIM + 2;
+    extern __shared__ double smem[];
+    GenericSmem<DIM> s(smem, p);
+    const long long e0 = (long long)blockIdx.x * p.EB;
+    const int nb = (int)min((long long)p.EB, p.K - e0);
+    bool bad = false;
+    project_batch<DIM>(p, s, e0, nb, bad);
+    for (int f = 0; f < NF; ++f) {
+        double* dst = p.traces + f * p.trace_stride + e0 * p.Nfq;
+        for (int i = threadIdx.x; i < nb * p.Nfq; i += blockDim.x) {
+            const int eb = i / p.Nfq, k = i - eb * p.Nfq;
+            dst[i] = s.Uf[(eb * NF + f) * p.Nfq + k];
+        }
+    }
+    if (bad) atomicOr(p.bad_flag, 1);
+}
+
+// Kernel B: surface + volume + lift + (rhs | LSRK stage).
+template <int DIM>
+__global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_rhs(const __grid_constant__ GenericParams p) {
+    constexpr int NF = DIM + 2;
+    extern __shared__ double smem[];
+    GenericSmem<DIM> s(smem, p);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const long long e0 = (long long)blockIdx.x * p.EB;
+    const int nb = (int)min((long long)p.EB, p.K - e0);
+    bool bad = false;
+    project_batch<DIM>(p, s, e0, nb, bad);
+
+    // phase 3: surface flux at face points
+    for (int i = tid; i < nb * p.Nfq; i += nt) {
+        const int eb = i / p.Nfq, k = i - eb * p.Nfq;
+        const long long e = e0 + eb;
+        const int face = k / p.Nfp;
+        const double* g = p.geo + e * p.geo_stride + DIM * DIM + 1 + face * (DIM + 1);
+        double nJ[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) nJ[d] = g[d];
+        const double sJ = g[DIM];
+        const double isJ = 1.0 / sJ;
+        // exterior state
+        const long long ip = p.mapP[e * p.Nfq + k];
+        double UP[NF], UM[NF];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            UP[f] = p.traces[f * p.trace_stride + ip];
+            UM[f] = s.Uf[(eb * NF + f) * p.Nfq + k];
+        }
+        Prim<DIM> PM, PP;
+        const double* w = s.W + (size_t)eb * (NF + 2) * p.Nh + p.Nq + k;
+        PM.rho = w[0];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) PM.vel[d] = w[(1 + d) * p.Nh];
+        PM.beta = w[(1 + DIM) * p.Nh];
+        PM.lrho = w[(2 + DIM) * p.Nh];
+        PM.lbeta = w[(3 + DIM) * p.Nh];
+        prim_of_u<DIM>(UP, p.gamma, PP);
+        double F[NF];
+        ec_flux_dot<DIM>(PM, PP, nJ, 2.0 * (p.gamma - 1.0), F);
+        if (p.lf_scale != 0.0) {
+            double unM = 0.0, unP = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+                unM = fma(UM[1 + d], nJ[d], unM);
+                unP = fma(UP[1 + d], nJ[d], unP);
+            }
+            const double lamM = wavespeed_1d(UM[0], unM * isJ, UM[1 + DIM], p.gamma);
+            const double lamP = wavespeed_1d(UP[0], unP * isJ, UP[1 + DIM], p.gamma);
+            const double LFc = p.lf_scale * fmax(lamM, lamP) * sJ;
+#pragma unroll
+            for (int f = 0; f < NF; ++f) F[f] -= LFc * (UP[f] - UM[f]);
+        }
+#pragma unroll
+        for (int f = 0; f < NF; ++f) s.Fl[(eb * NF + f) * p.Nfq + k] = F[f];
+    }
+
+    // phase 4: Hadamard sum, one hybridized row per item
+    for (int i = tid; i < nb * p.Nh; i += nt) {
+        const int eb = i / p.Nh, r = i - eb * p.Nh;
+        const long long e = e0 + eb;
+        const double* G = p.geo + e * p.geo_stride;
+        const double* w = s.W + (size_t)eb * (NF + 2) * p.Nh;
+        Prim<DIM> Pi;
+        Pi.rho = w[r];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) Pi.vel[d] = w[(1 + d) * p.Nh + r];
+        Pi.beta = w[(1 + DIM) * p.Nh + r];
+        Pi.lrho = w[(2 + DIM) * p.Nh + r];
+        Pi.lbeta = w[(3 + DIM) * p.Nh + r];
+        double acc[NF];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) acc[f] = 0.0;
+        const int n = p.Qp.cnt[r];
+        for (int k = 0; k < n; ++k) {
+            const int j = p.Qp.col[r * p.Qp.width + k];
+            const double* cq = p.Qp.c + (size_t)(r * p.Qp.width + k) * 3;
+            // c_d = sum_k G[d][k] * Q_k[i,j]   (Fr = rxJ*Fx + ryJ*Fy ..., :126-129)
+            double c[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+                double a = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < DIM; ++kk) a = fma(G[d * DIM + kk], cq[kk], a);
+                c[d] = a;
+            }
+            Prim<DIM> Pj;
+            Pj.rho = w[j];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) Pj.vel[d] = w[(1 + d) * p.Nh + j];
+            Pj.beta = w[(1 + DIM) * p.Nh + j];
+            Pj.lrho = w[(2 + DIM) * p.Nh + j];
+            Pj.lbeta = w[(3 + DIM) * p.Nh + j];
+            double F[NF];
+            ec_flux_dot<DIM>(Pi, Pj, c, 2.0 * (p.gamma - 1.0), F);
+#pragma unroll
+            for (int f = 0; f < NF; ++f) acc[f] += F[f];
+        }
+#pragma unroll
+        for (int f = 0; f < NF; ++f) s.QF[(eb * NF + f) * p.Nh + r] = acc[f];
+    }
+    __syncthreads();
+
+    // phase 5: test with Ph, lift, scale by -1/J; phase 6: output
+    double tsum = 0.0;
+    for (int i = tid; i < nb * p.Ns; i += nt) {
+        const int eb = i / p.Ns, r = i - eb * p.Ns;
+        const long long e = e0 + eb;
+        const double J = p.geo[e * p.geo_stride + DIM * DIM];
+        double a[NF], b[NF];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) a[f] = b[f] = 0.0;
+        int n = p.Ph.cnt[r];
+        for (int k = 0; k < n; ++k) {
+            const int c = p.Ph.col[r * p.Ph.width + k];
+            const double v = p.Ph.val[r * p.Ph.width + k];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) a[f] = fma(v, s.QF[(eb * NF + f) * p.Nh + c], a[f]);
+        }
+        n = p.Lf.cnt[r];
+        for (int k = 0; k < n; ++k) {
+            const int c = p.Lf.col[r * p.Lf.width + k];
+            const double v = p.Lf.val[r * p.Lf.width + k];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) b[f] = fma(v, s.Fl[(eb * NF + f) * p.Nfq + c], b[f]);
+        }
+        const double mJ = -1.0 / J;
+        double rr[NF];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) rr[f] = (b[f] + p.volume_scale * a[f]) * mJ;
+        const long long g = e * p.Ns + r;
+        if (p.want_rhstest) {
+            if (p.collocated) {
+                const double wJ = p.wq[r] * J;
+#pragma unroll
+                for (int f = 0; f < NF; ++f) tsum += wJ * s.V[(eb * NF + f) * p.Nq + r] * rr[f];
+            } else {
+#pragma unroll
+                for (int f = 0; f < NF; ++f) s.R[(eb * NF + f) * p.Ns + r] = rr[f];
+            }
+        }
+        if (p.mode == 0) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) p.rhs[f * p.q_stride + g] = rr[f];
+        } else {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                const double res = p.rk_a * p.res[f * p.q_stride + g] + p.dt * rr[f];
+                p.res[f * p.q_stride + g] = res;
+                p.Qout[f * p.q_stride + g] = s.U[(eb * NF + f) * p.Ns + r] + p.rk_b * res;
+            }
+        }
+    }
+    if (p.want_rhstest) {
+        __syncthreads();
+        if (!p.collocated) {
+            // tri: sum wJq .* VU[1:Nq] .* (Vq*rhs)   (dg2D_euler_tri.jl:177-183)
+            for (int i = tid; i < nb * p.Nq; i += nt) {
+                const int eb = i / p.Nq, q = i - eb * p.Nq;
+                const long long e = e0 + eb;
+                const double J = p.geo[e * p.geo_stride + DIM * DIM];
+                const double wJ = p.wq[q] * J;
+                const int n = p.Vq.cnt[q];
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    double v = 0.0;
+                    for (int k = 0; k < n; ++k)
+                        v = fma(p.Vq.val[q * p.Vq.width + k],
+                                s.R[(eb * NF + f) * p.Ns + p.Vq.col[q * p.Vq.width + k]], v);
+                    tsum += wJ * s.VP[(eb * NF + f) * p.Nq + q] * v;
+                }
+            }
+        }
+        // deterministic block reduction -> one partial per CTA
+        __shared__ double red[32];
+        for (int o = 16; o > 0; o >>= 1) tsum += __shfl_down_sync(0xffffffffu, tsum, o);
+        if ((tid & 31) == 0) red[tid >> 5] = tsum;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int wv = 0; wv < (nt + 31) / 32; ++wv) t += red[wv];
+            p.rhstest_partial[blockIdx.x] = t;
+        }
+    }
+    if (bad) atomicOr(p.bad_flag, 1);
+}
+
+// Deterministic final sum of the per-CTA partials (fixed order).
+__global__ void k_reduce_partials(const double* partial, int n, double* out) {
+    __shared__ double sh[256];
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) t += partial[i];
+    sh[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+}  // namespace esdg

@@ -1,0 +1,305 @@
+"""Host-side setup for uniform quad / hex meshes (not on the hot path).
+
+In a Julia deployment ``rd``/``md``/``ops`` come from the reference's own
+``SetupDG.jl`` and script-level operator assembly and are handed to the library
+through the C ABI.  This module plays that role for the Python host, tests and
+benchmarks.  It is written tensor-product-first (everything derives from the
+1D Gauss rule, the 1D Lagrange derivative matrix and the two end-point
+interpolation vectors) and builds connectivity analytically, so a 128^3 mesh
+sets up in seconds -- the reference's generic ``build_node_maps`` is
+O(faces*Nfp^2) with dense distance matrices (src/node_map_functions.jl:35-51).
+Array names, shapes and orderings are the reference's:
+
+* quad: volume nodes s-fastest (src/SetupDG.jl:244-246), faces CCW (:235-239)
+* hex : volume nodes r-fastest (the H2 fix), faces r-,r+,s-,s+,t-,t+ with the
+  on-face ordering of src/SetupDG.jl:345-357
+* ``mapP`` is 0-based here; the binding adds 1 (Julia convention) at the ABI.
+
+tests/test_setup_parity.py checks every array against the oracle's literal
+restatement of SetupDG.jl on small meshes.
+"""
+from types import SimpleNamespace
+
+import numpy as np
+
+
+# ------------------------------------------------------------------ 1D pieces
+def gauss_1d(N):
+    x, w = np.polynomial.legendre.leggauss(N + 1)
+    return x, w
+
+
+def lagrange_eval(x, y):
+    """L[i,j] = l_j(y_i) for the Lagrange basis on nodes x."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.atleast_1d(np.asarray(y, dtype=np.float64))
+    n = x.size
+    L = np.ones((y.size, n))
+    for j in range(n):
+        for m in range(n):
+            if m != j:
+                L[:, j] *= (y - x[m]) / (x[j] - x[m])
+    return L
+
+
+def lagrange_deriv(x):
+    """D[i,j] = l_j'(x_i) (barycentric form)."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.size
+    c = np.array([np.prod([x[j] - x[m] for m in range(n) if m != j]) for j in range(n)])
+    D = np.zeros((n, n))
+    for i in range(n):
+        for j in range(n):
+            if i != j:
+                D[i, j] = c[i] / (c[j] * (x[i] - x[j]))
+        D[i, i] = -np.sum(D[i, :])
+    return D
+
+
+# --------------------------------------------------------- reference elements
+def _hybridize(Qs, Ef, wf, normals):
+    out = []
+    for Q, n in zip(Qs, normals):
+        B = np.diag(wf * n)
+        Qh = .5 * np.block([[Q - Q.T, Ef.T @ B], [-B @ Ef, B]])   # dg2D_euler_quad.jl:53-56
+        out.append(.5 * (Qh - Qh.T))                               # :60-61
+    return out
+
+
+def reference_quad(N, lf_scale=.5):
+    """Collocated Gauss quad element in the quadrature-node basis (dg2D_euler_quad.jl:47-78)."""
+    x, w = gauss_1d(N)
+    n = N + 1
+    D = lagrange_deriv(x)
+    lm, lp = lagrange_eval(x, -1.0)[0], lagrange_eval(x, 1.0)[0]
+    I = np.eye(n)
+    # k = i + n*j with s = x[i] (fastest), r = x[j]
+    rq, sq = np.repeat(x, n), np.tile(x, n)
+    wq = np.repeat(w, n) * np.tile(w, n)
+    Dr = np.kron(D, I)          # acts on j
+    Ds = np.kron(I, D)          # acts on i
+    Ef = np.zeros((4 * n, n * n))
+    k = lambda i, j: i + n * j
+    for m in range(n):
+        for a in range(n):
+            Ef[m, k(a, m)] = lm[a]                      # f1: s=-1, r=x[m]
+            Ef[n + m, k(m, a)] = lp[a]                  # f2: r=+1, s=x[m]
+            Ef[2 * n + m, k(a, n - 1 - m)] = lp[a]      # f3: s=+1, r=-x[m]
+            Ef[3 * n + m, k(n - 1 - m, a)] = lm[a]      # f4: r=-1, s=-x[m]
+    e, z = np.ones(n), np.zeros(n)
+    rd = SimpleNamespace(elem="quad", N=N, Nfaces=4, rq=rq, sq=sq, wq=wq, wf=np.tile(w, 4),
+                         rf=np.concatenate([x, e, -x, -e]), sf=np.concatenate([-e, x, e, -x]),
+                         nrJ=np.concatenate([z, e, z, -e]), nsJ=np.concatenate([-e, z, e, z]))
+    W = np.diag(wq)
+    Qskew = _hybridize([W @ Dr, W @ Ds], Ef, rd.wf, [rd.nrJ, rd.nsJ])
+    Vh = np.vstack([np.eye(n * n), Ef])
+    ops = SimpleNamespace(elem="quad", N=N, Nfaces=4, wq=wq, Ef=Ef, Qskew=Qskew, Vh=Vh,
+                          Ph=np.diag(1 / wq) @ Vh.T, Lf=np.diag(1 / wq) @ (Ef.T @ np.diag(rd.wf)),
+                          volume_scale=2.0, lf_scale=lf_scale)
+    return rd, ops
+
+
+def reference_hex(N, lf_scale=.25):
+    """Collocated Gauss hex element, r-fastest nodes (dg3D_euler_hex.jl:34-58,94-98 with the H2 fix)."""
+    x, w = gauss_1d(N)
+    n = N + 1
+    D = lagrange_deriv(x)
+    lm, lp = lagrange_eval(x, -1.0)[0], lagrange_eval(x, 1.0)[0]
+    I = np.eye(n)
+    # k = a + n*b + n^2*c with r=x[a], s=x[b], t=x[c]
+    rq = np.tile(x, n * n)
+    sq = np.tile(np.repeat(x, n), n)
+    tq = np.repeat(x, n * n)
+    wq = np.tile(w, n * n) * np.tile(np.repeat(w, n), n) * np.repeat(w, n * n)
+    Dr = np.kron(I, np.kron(I, D))
+    Ds = np.kron(I, np.kron(D, I))
+    Dt = np.kron(D, np.kron(I, I))
+    nfp = n * n
+    Ef = np.zeros((6 * nfp, n ** 3))
+    k = lambda a, b, c: a + n * b + n * n * c
+    # face point m = i + n*j carries (rquad, squad) = (x[j], x[i])   (src/SetupDG.jl:346)
+    for j in range(n):
+        for i in range(n):
+            m = i + n * j
+            for a in range(n):
+                Ef[0 * nfp + m, k(a, j, i)] = lm[a]   # f1 r=-1: (s,t)=(x[j],x[i])
+                Ef[1 * nfp + m, k(a, j, i)] = lp[a]   # f2 r=+1
+                Ef[2 * nfp + m, k(j, a, i)] = lm[a]   # f3 s=-1: (r,t)=(x[j],x[i])
+                Ef[3 * nfp + m, k(j, a, i)] = lp[a]   # f4 s=+1
+                Ef[4 * nfp + m, k(j, i, a)] = lm[a]   # f5 t=-1: (r,s)=(x[j],x[i])
+                Ef[5 * nfp + m, k(j, i, a)] = lp[a]   # f6 t=+1
+    rquad, squad = np.repeat(x, n), np.tile(x, n)
+    wquad = np.repeat(w, n) * np.tile(w, n)
+    e, z = np.ones(nfp), np.zeros(nfp)
+    rd = SimpleNamespace(elem="hex", N=N, Nfaces=6, rq=rq, sq=sq, tq=tq, wq=wq, wf=np.tile(wquad, 6),
+                         rf=np.concatenate([-e, e, rquad, rquad, rquad, rquad]),
+                         sf=np.concatenate([rquad, rquad, -e, e, squad, squad]),
+                         tf=np.concatenate([squad, squad, squad, squad, -e, e]),
+                         nrJ=np.concatenate([-e, e, z, z, z, z]), nsJ=np.concatenate([z, z, -e, e, z, z]),
+                         ntJ=np.concatenate([z, z, z, z, -e, e]))
+    W = np.diag(wq)
+    Qskew = _hybridize([W @ Dr, W @ Ds, W @ Dt], Ef, rd.wf, [rd.nrJ, rd.nsJ, rd.ntJ])
+    Vh = np.vstack([np.eye(n ** 3), Ef])
+    ops = SimpleNamespace(elem="hex", N=N, Nfaces=6, wq=wq, Ef=Ef, Qskew=Qskew, Vh=Vh,
+                          Ph=2 * np.diag(1 / wq) @ Vh.T,               # hex folds the 2 into Ph (:96)
+                          Lf=np.diag(1 / wq) @ (Ef.T @ np.diag(rd.wf)),
+                          volume_scale=1.0, lf_scale=lf_scale)
+    return rd, ops
+
+
+# --------------------------------------------------------------------- meshes
+def uniform_quad_mesh_md(rd, Kx, Ky, domain=((-1.0, 1.0), (-1.0, 1.0)), periodic=(True, True)):
+    """MeshData of a uniform Kx x Ky quad mesh (elements x-fastest, UniformQuadMesh.jl:37-44)."""
+    n = rd.N + 1
+    Nfq = 4 * n
+    K = Kx * Ky
+    (x0, x1), (y0, y1) = domain
+    hx, hy = (x1 - x0) / Kx, (y1 - y0) / Ky
+    ex = np.arange(K) % Kx
+    ey = np.arange(K) // Kx
+    md = SimpleNamespace(K=K, dim=2)
+    md.xq = (x0 + hx * ex)[None, :] + hx / 2 * (1 + rd.rq)[:, None]
+    md.yq = (y0 + hy * ey)[None, :] + hy / 2 * (1 + rd.sq)[:, None]
+    one = np.ones((1, K))
+    md.rxJ, md.sxJ, md.ryJ, md.syJ = hy / 2 * one, 0 * one, 0 * one, hx / 2 * one
+    md.J = hx * hy / 4 * one
+    nr = rd.nrJ[::n][:, None]
+    ns = rd.nsJ[::n][:, None]
+    md.nxJ = md.rxJ * nr + md.sxJ * ns          # Nfaces x K (constant per face)
+    md.nyJ = md.ryJ * nr + md.syJ * ns
+    md.sJ = np.sqrt(md.nxJ ** 2 + md.nyJ ** 2)
+    # connectivity: f1(s=-1)<->f3 of (ex,ey-1); f2(r=+1)<->f4 of (ex+1,ey); points reversed
+    mapP = np.arange(Nfq * K, dtype=np.int64).reshape((Nfq, K), order="F")
+    m = np.arange(n)
+    for f, (dx, dy, fn) in enumerate([(0, -1, 2), (1, 0, 3), (0, 1, 0), (-1, 0, 1)]):
+        nx_, ny_ = ex + dx, ey + dy
+        ok = np.ones(K, dtype=bool)
+        if periodic[0]:
+            nx_ = nx_ % Kx
+        else:
+            ok &= (nx_ >= 0) & (nx_ < Kx)
+        if periodic[1]:
+            ny_ = ny_ % Ky
+        else:
+            ok &= (ny_ >= 0) & (ny_ < Ky)
+        en = np.where(ok, nx_ + Kx * ny_, 0)
+        tgt = (fn * n + (n - 1 - m))[:, None] + Nfq * en[None, :]
+        rows = f * n + m
+        mapP[rows[:, None], np.arange(K)[None, :]] = np.where(ok[None, :], tgt, mapP[rows, :])
+    md.mapP = mapP
+    return md
+
+
+def uniform_hex_mesh_md(rd, Kxyz, domain=((-1.0, 1.0),) * 3, periodic=(True, True, True), zslab=None):
+    """MeshData of a uniform hex mesh, elements x-fastest (UniformHexMesh.jl:59-63).
+
+    ``zslab=(rank, nranks)`` builds only the rank's contiguous z-slab: trace
+    points owned by the slab below / above are mapped to halo slots appended after
+    ``Nfq*K`` (lower neighbour's t=+1 faces first, then the upper neighbour's t=-1 faces);
+    ``md.send_lower`` / ``md.send_upper`` list the local trace points each neighbour needs.
+    """
+    n = rd.N + 1
+    nfp = n * n
+    Nfq = 6 * nfp
+    Kx, Ky, Kz = Kxyz
+    (x0, x1), (y0, y1), (z0, z1) = domain
+    hx, hy, hz = (x1 - x0) / Kx, (y1 - y0) / Ky, (z1 - z0) / Kz
+    if zslab is None:
+        k0, k1, nranks = 0, Kz, 1
+    else:
+        rank, nranks = zslab
+        if Kz % nranks:
+            raise ValueError("Kz must be divisible by the number of ranks")
+        k0, k1 = rank * (Kz // nranks), (rank + 1) * (Kz // nranks)
+    Kzl = k1 - k0
+    K = Kx * Ky * Kzl
+    e = np.arange(K)
+    ex, ey, ez = e % Kx, (e // Kx) % Ky, e // (Kx * Ky) + k0
+    md = SimpleNamespace(K=K, dim=3, Kxyz=(Kx, Ky, Kz), zrange=(k0, k1))
+    md.elem_origin = (x0 + hx * ex, y0 + hy * ey, z0 + hz * ez)
+    md.h = (hx, hy, hz)
+    one = np.ones((1, K))
+    zero = 0 * one
+    md.rxJ, md.syJ, md.tzJ = hy * hz / 4 * one, hx * hz / 4 * one, hx * hy / 4 * one
+    md.sxJ = md.txJ = md.ryJ = md.tyJ = md.rzJ = md.szJ = zero
+    md.J = hx * hy * hz / 8 * one
+    nr, ns, nt = rd.nrJ[::nfp][:, None], rd.nsJ[::nfp][:, None], rd.ntJ[::nfp][:, None]
+    md.nxJ = nr * md.rxJ + ns * md.sxJ + nt * md.txJ
+    md.nyJ = nr * md.ryJ + ns * md.syJ + nt * md.tyJ
+    md.nzJ = nr * md.rzJ + ns * md.szJ + nt * md.tzJ
+    md.sJ = np.sqrt(md.nxJ ** 2 + md.nyJ ** 2 + md.nzJ ** 2)
+    # connectivity: opposite faces share the on-face parametrisation, so point m <-> point m
+    mapP = np.empty((Nfq, K), dtype=np.int64)
+    m = np.arange(nfp)
+    split = zslab is not None and (nranks > 1)
+    n_layer = Kx * Ky * nfp
+    for f, (d, sgn, fn) in enumerate([(0, -1, 1), (0, 1, 0), (1, -1, 3), (1, 1, 2), (2, -1, 5), (2, 1, 4)]):
+        c = [ex.copy(), ey.copy(), ez.copy()]
+        c[d] = c[d] + sgn
+        ok = np.ones(K, dtype=bool)
+        for q, Kq in enumerate((Kx, Ky, Kz)):
+            if periodic[q]:
+                c[q] = c[q] % Kq
+            else:
+                ok &= (c[q] >= 0) & (c[q] < Kq)
+        self_idx = (f * nfp + m)[:, None] + Nfq * e[None, :]
+        local = (c[2] >= k0) & (c[2] < k1) if split else np.ones(K, dtype=bool)
+        en = c[0] + Kx * c[1] + Kx * Ky * (c[2] - k0)
+        tgt = (fn * nfp + m)[:, None] + Nfq * np.where(local, en, 0)[None, :]
+        if split and d == 2:
+            slot = (c[0] + Kx * c[1])[None, :] * nfp + m[:, None]
+            halo = Nfq * K + slot + (0 if sgn < 0 else n_layer)
+            tgt = np.where(local[None, :], tgt, halo)
+        mapP[f * nfp:(f + 1) * nfp, :] = np.where(ok[None, :], tgt, self_idx)
+    md.mapP = mapP
+    md.n_halo = 0
+    if split:
+        md.n_halo = 2 * n_layer
+        bottom = np.nonzero(ez == k0)[0]
+        top = np.nonzero(ez == k1 - 1)[0]
+        md.send_lower = ((4 * nfp + m)[None, :] + Nfq * bottom[:, None]).reshape(-1)   # my t=-1 faces
+        md.send_upper = ((5 * nfp + m)[None, :] + Nfq * top[:, None]).reshape(-1)      # my t=+1 faces
+        has_lower = periodic[2] or k0 > 0
+        has_upper = periodic[2] or k1 < Kz
+        md.lower_rank = (rank - 1) % nranks if has_lower else None
+        md.upper_rank = (rank + 1) % nranks if has_upper else None
+    return md
+
+
+def hex_node_coords(rd, md):
+    """Physical coordinates of the volume quadrature nodes (Nq x K each)."""
+    ox, oy, oz = md.elem_origin
+    hx, hy, hz = md.h
+    return (ox[None, :] + hx / 2 * (1 + rd.rq)[:, None],
+            oy[None, :] + hy / 2 * (1 + rd.sq)[:, None],
+            oz[None, :] + hz / 2 * (1 + rd.tq)[:, None])
+
+
+# --------------------------------------------------------- initial conditions
+GAMMA = 1.4
+
+
+def primitive_to_conservative(rho, U, p):
+    """examples/EntropyStableEuler/euler_variables.jl:15-20"""
+    un = sum(u * u for u in U)
+    return [rho] + [rho * u for u in U] + [p / (GAMMA - 1) + .5 * rho * un]
+
+
+def vortex(x, y, t=0.0):
+    """2D isentropic vortex, examples/EntropyStableEuler/EntropyStableEuler.jl:21-35"""
+    r2 = (x - 5 - t) ** 2 + y ** 2
+    b = 5 * np.exp(1 - r2)
+    u = 1 - b * y / (2 * np.pi)
+    v = b * (x - 5 - t) / (2 * np.pi)
+    rho = (1 - (1 / (8 * GAMMA * np.pi ** 2)) * (GAMMA - 1) / 2 * b ** 2) ** (1 / (GAMMA - 1))
+    return rho, u, v, rho ** GAMMA
+
+
+def taylor_green(x, y, z, mach=0.1):
+    """3D Taylor-Green vortex (project-defined IC for config 5)."""
+    rho = np.ones_like(x)
+    u = np.sin(x) * np.cos(y) * np.cos(z)
+    v = -np.cos(x) * np.sin(y) * np.cos(z)
+    w = np.zeros_like(x)
+    p = 1.0 / (GAMMA * mach ** 2) + (np.cos(2 * x) + np.cos(2 * y)) * (np.cos(2 * z) + 2) / 16
+    return rho, u, v, w, p

@@ -1,0 +1,144 @@
+/* esdg_b200.h -- C ABI of libesdg_b200.so
+ *
+ * B200-native (sm_100a) replacement for ONE hot path of yiminllin/ESDG-CNS: the
+ * semi-discrete entropy-stable DG right-hand side and the low-storage RK loop
+ * that drives it.  The reference has no FFI; its boundary is the Julia call
+ * shape
+ *     rhsQ, rhstest = rhs(Q, md::MeshData, ops, flux_fun, compute_rhstest)
+ *         examples/dg2D_euler_quad.jl:141, dg2D_euler_tri.jl:130, dg3D_euler_hex.jl:167
+ *     for INTRK=1:5  resQ = rk4a*resQ + dt*rhsQ ; Q += rk4b*resQ
+ *         examples/dg2D_euler_quad.jl:198-207
+ * A Julia shim pulls the arrays out of rd::RefElemData
+ * (src/SetupDG.jl:38-75), md::MeshData (:77-115) and the `ops` tuple and hands
+ * them over as plain column-major double / int64 arrays.  No torch types, no
+ * exceptions across the boundary; every function returns an esdg_status.
+ *
+ * All matrices are COLUMN-MAJOR doubles exactly as Julia stores them; all index
+ * arrays are int64 and 1-BASED exactly as Julia stores them.  Host pointers are
+ * borrowed for the duration of the call only.
+ */
+#ifndef ESDG_B200_H
+#define ESDG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct esdg_ctx esdg_ctx;
+
+typedef enum {
+    ESDG_OK = 0,
+    ESDG_EINVAL = 1,  /* bad argument / missing operator / non-affine mesh     */
+    ESDG_ECUDA = 2,   /* CUDA runtime error (esdg_last_error has the string)    */
+    ESDG_ENCCL = 3,   /* reserved                                               */
+    ESDG_ENOMEM = 4,  /* device allocation failed                               */
+    ESDG_ESTATE = 5   /* non-positive density/pressure met in rhs: the Julia
+                         DomainError of log/sqrt (euler_variables.jl:67, :8)   */
+} esdg_status;
+
+enum { ESDG_TRI = 0, ESDG_QUAD = 1, ESDG_HEX = 2 };
+
+/* Discretisation descriptor: the script-top globals + array sizes.
+ * (dg2D_euler_quad.jl:21-24,91 ; dg3D_euler_hex.jl:20-23,98) */
+typedef struct {
+    int32_t dim;        /* 2 or 3                                                           */
+    int32_t elem;       /* ESDG_TRI / ESDG_QUAD / ESDG_HEX                                  */
+    int32_t N;          /* polynomial degree                                                */
+    int32_t Nfields;    /* dim + 2                                                          */
+    int32_t Ns;         /* rows of each Q[f]: Nq (quad/hex scripts) or Np (tri/CNS scripts) */
+    int32_t Nq;         /* volume quadrature points  (length of rd.wq)                      */
+    int32_t Nfq;        /* face quadrature points, all faces (length of rd.wf)              */
+    int32_t Nfaces;     /* rd.Nfaces                                                        */
+    int32_t collocated; /* 1: state lives at quadrature nodes, volume part unprojected
+                              (dg2D_euler_quad.jl:149-151, dg3D_euler_hex.jl:176-178)
+                           0: Vq / VhP projection of every hybridized point
+                              (dg2D_euler_tri.jl:138-140)                                   */
+    int32_t affine;     /* must be 1: geofacs constant per element (`vgeo[1,e]`,
+                           dg2D_euler_quad.jl:175).  Curved meshes: SURVEY 8(f) rank 2.    */
+    int64_t K;          /* elements owned by this context (md.K, or the local slab)        */
+    int64_t n_halo;     /* extra trace points appended after Nfq*K that mapP may point to
+                           (neighbour-rank face traces); 0 on a single GPU                  */
+    double gamma;       /* 1.4 (EntropyStableEuler.jl:9)                                    */
+    double lf_scale;    /* c in LFc = c*max(lam,lamP)*sJ : .5 quad(:165) .25 tri(:156) 0 hex(:193) */
+    double volume_scale;/* factor on Ph*QF : 2 (quad :180, tri :171); 1 when the caller's Ph
+                           already holds it (hex, dg3D_euler_hex.jl:96,208)                 */
+} esdg_desc;
+
+/* ---- lifecycle -------------------------------------------------------------- */
+int esdg_create(const esdg_desc* desc, int device, esdg_ctx** out);
+int esdg_destroy(esdg_ctx* ctx);
+const char* esdg_last_error(const esdg_ctx* ctx);
+/* Run all work of this context on an existing CUDA stream (cudaStream_t as void*);
+ * default is a stream the context owns. */
+int esdg_set_stream(esdg_ctx* ctx, void* cuda_stream);
+
+/* ---- setup: replaces the `@unpack ... = rd/md` + `ops` tuple of rhs() ----------
+ * name: "Ef"  (Nfq x Nq, Vf*Pq; dg2D_euler_quad.jl:50)           collocated only
+ *       "Vq"  (Nq x Ns), "VhP" (Nh x Nq)   (dg2D_euler_tri.jl:58)    modal only
+ *       "Ph"  (Ns x Nh)  (dg2D_euler_quad.jl:77 / dg2D_euler_tri.jl:57)
+ *       "Lf"  (Ns x Nfq) quad/hex Lf (:78) or rd.LIFT (SetupDG.jl:192)
+ *       "Qrh","Qsh","Qth" (Nh x Nh) skew hybridized SBP operators (:60-61)
+ *       "wq"  (Nq x 1)   rd.wq  (only used for rhstest through wJq)
+ * Sparse Julia matrices are passed densified (`Matrix(A)`); sparsity is re-detected
+ * with the reference's drop tolerance 1e-12 (dg2D_euler_quad.jl:62-63). */
+int esdg_set_operator(esdg_ctx* ctx, const char* name, const double* colmajor, int64_t rows, int64_t cols);
+
+/* name: "rxJ","sxJ","txJ","ryJ","syJ","tyJ","rzJ","szJ","tzJ" (rows = Nh, Np or 1; row 1 is
+ *        read, the `[1,e]` of dg2D_euler_quad.jl:175), "J" (rows = Ns or 1),
+ *       "nxJ","nyJ","nzJ","sJ" (rows = Nfq, or Nfaces when constant per face),
+ *       "wJq" (Nq x K or 1 x K: then wq[i]*wJq[e] is used; SetupDG.jl:307)
+ * cols must equal desc.K. */
+int esdg_set_geometry(esdg_ctx* ctx, const char* name, const double* colmajor, int64_t rows, int64_t cols);
+
+/* md.mapP (Nfq x K, 1-based linear index into an Nfq x (K [+halo]) array; SetupDG.jl:294-298). */
+int esdg_set_maps(esdg_ctx* ctx, const int64_t* mapP, int64_t n);
+
+/* Validates that everything required by the descriptor was supplied, compresses the
+ * operators and uploads them.  Must be called once before any hot call. */
+int esdg_finalize(esdg_ctx* ctx);
+
+/* ---- hot path ------------------------------------------------------------------
+ * Q / rhs_out: arrays of Nfields HOST pointers, each Ns*K doubles (the Julia
+ * Vector{Matrix{Float64}}).  Q == NULL evaluates the resident state.  Synchronous.
+ * rhstest[0] receives sum_f sum(wJq .* VU[f] .* rhs[f]) when compute_rhstest != 0
+ * (dg2D_euler_quad.jl:186-191). */
+int esdg_rhs(esdg_ctx* ctx, const double* const* Q, double* const* rhs_out, int compute_rhstest, double* rhstest);
+
+/* State residency (Q and the LSRK register resQ live in HBM between calls). */
+int esdg_upload_state(esdg_ctx* ctx, const double* const* Q);   /* also zeroes resQ (:197) */
+int esdg_download_state(esdg_ctx* ctx, double* const* Q);
+
+/* nsteps x 5 stages of LSRK45 on the resident state (dg2D_euler_quad.jl:196-207,
+ * coefficients src/CommonUtils.jl:29-49).  Stream-ordered: returns without waiting
+ * unless rhstest_last != NULL (then rhstest of the final stage is returned). */
+int esdg_lsrk45_step(esdg_ctx* ctx, double dt, int nsteps, double* rhstest_last);
+
+int esdg_sync(esdg_ctx* ctx);   /* waits; reports ESDG_ESTATE if the rhs met rho<=0 or p<=0 */
+
+/* ---- multi-GPU plumbing (one context per GPU; the host exchanges halos) ---------
+ * Face traces (entropy-projected conservative variables at face points,
+ * `Uf` of dg2D_euler_quad.jl:150) live in one device array of
+ * Nfields x (Nfq*K + n_halo) doubles, field-major.  The host library (torch.distributed
+ * / NCCL in the Python mirror, NCCL.jl in Julia) sends packed boundary traces and
+ * receives straight into the halo tail. */
+int esdg_set_send_list(esdg_ctx* ctx, const int64_t* trace_idx /*1-based*/, int64_t n);
+int esdg_compute_traces(esdg_ctx* ctx);                     /* traces of the resident Q      */
+int esdg_pack_send(esdg_ctx* ctx, void* send_dev /* Nfields*n doubles, device */);
+int esdg_halo_ptr(esdg_ctx* ctx, void** halo_dev, int64_t* field_stride);
+/* One LSRK stage whose trace exchange is done by the caller between the two calls:
+ *   esdg_compute_traces ; pack ; <exchange> ; esdg_stage_update(stage) */
+int esdg_stage_update(esdg_ctx* ctx, int stage /*0..4*/, double dt, int compute_rhstest);
+int esdg_read_rhstest(esdg_ctx* ctx, double* rhstest);
+
+/* ---- introspection ---------------------------------------------------------- */
+int64_t esdg_kernel_launches(const esdg_ctx* ctx);          /* kernels launched so far      */
+int esdg_kernel_time_ms(esdg_ctx* ctx, const char* kernel, double* total_ms, int64_t* launches);
+int esdg_enable_timing(esdg_ctx* ctx, int on);              /* CUDA-event timing per kernel */
+const char* esdg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESDG_B200_H */

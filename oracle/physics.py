@@ -9,6 +9,26 @@ import numpy as np
 
 GAMMA = 1.4  # examples/EntropyStableEuler/EntropyStableEuler.jl:9
 
+# Every ``log`` of the path goes through this hook so that tests can measure the
+# formula's own conditioning: ``noise_floor`` (tests/helpers.py) re-evaluates the
+# oracle with each log result moved by a random -1/0/+1 ulp, which is the spread
+# between two faithful libm implementations (Julia's, glibc's, CUDA's).
+LOG_IMPL = np.log
+EXP_IMPL = np.exp
+POW_IMPL = np.power
+
+
+def _log(x):
+    return LOG_IMPL(x)
+
+
+def _exp(x):
+    return EXP_IMPL(x)
+
+
+def _pow(x, y):
+    return POW_IMPL(x, y)
+
 
 # --------------------------------------------------------------------------
 # logmean.jl:14-28
@@ -16,8 +36,8 @@ def logmean(aL, aR, logL=None, logR=None):
     aL = np.asarray(aL, dtype=np.float64)
     aR = np.asarray(aR, dtype=np.float64)
     if logL is None:
-        logL = np.log(aL)  # logmean.jl:5-7
-        logR = np.log(aR)
+        logL = _log(aL)  # logmean.jl:5-7
+        logR = _log(aR)
     da = aR - aL
     aavg = .5 * (aR + aL)
     f = da / aavg
@@ -34,8 +54,8 @@ def euler_fluxes_2d(UL, UR, logL=None, logR=None):
     rhoL, uL, vL, betaL = UL
     rhoR, uR, vR, betaR = UR
     if logL is None:  # euler_fluxes.jl:9-15
-        logL = (np.log(rhoL), np.log(betaL))
-        logR = (np.log(rhoR), np.log(betaR))
+        logL = (_log(rhoL), _log(betaL))
+        logR = (_log(rhoR), _log(betaR))
     rholog = logmean(rhoL, rhoR, logL[0], logR[0])
     betalog = logmean(betaL, betaR, logL[1], logR[1])
     rhoavg = .5 * (rhoL + rhoR)
@@ -59,8 +79,8 @@ def euler_fluxes_3d(UL, UR, logL=None, logR=None):
     rhoL, uL, vL, wL, betaL = UL
     rhoR, uR, vR, wR, betaR = UR
     if logL is None:
-        logL = (np.log(rhoL), np.log(betaL))
-        logR = (np.log(rhoR), np.log(betaR))
+        logL = (_log(rhoL), _log(betaL))
+        logR = (_log(rhoR), _log(betaR))
     rholog = logmean(rhoL, rhoR, logL[0], logR[0])
     betalog = logmean(betaL, betaR, logL[1], logR[1])
     rhoavg = .5 * (rhoL + rhoR)
@@ -135,7 +155,7 @@ def rhoefun(rho, rhoU, E):  # :59-62
 
 def sfun(rho, rhoU, E):  # :65-68
     rhoe = rhoefun(rho, rhoU, E)
-    return np.log((GAMMA - 1) * rhoe / (rho ** GAMMA))
+    return _log((GAMMA - 1) * rhoe / _pow(rho, GAMMA))
 
 
 def Sfun(rho, rhoU, E):  # :71-76
@@ -158,7 +178,7 @@ def s_vfun(v1, vU, vE):  # :95-98
 
 def rhoe_vfun(v1, vU, vE):  # :101-104
     s = s_vfun(v1, vU, vE)
-    return ((GAMMA - 1) / ((-vE) ** GAMMA)) ** (1 / (GAMMA - 1)) * np.exp(-s / (GAMMA - 1))
+    return _pow((GAMMA - 1) / _pow(-vE, GAMMA), 1 / (GAMMA - 1)) * _exp(-s / (GAMMA - 1))
 
 
 def u_vfun(v1, vU, vE):  # :107-113

@@ -70,6 +70,8 @@ def build_sbp_ops(rd):
     tri: dg2D_euler_tri.jl:45-63.
     """
     ops = SimpleNamespace()
+    ops.elem, ops.N, ops.Nfaces, ops.wq = rd.elem, rd.N, rd.Nfaces, rd.wq
+    ops.lf_scale = {"quad": .5, "tri": .25, "hex": .25}[rd.elem]   # quad :165, tri :156, (hex :193 has 0*.25)
     dim = 3 if rd.elem == "hex" else 2
     Ds = [rd.Dr, rd.Ds] + ([rd.Dt] if dim == 3 else [])
     ns = [rd.nrJ, rd.nsJ] + ([rd.ntJ] if dim == 3 else [])
@@ -126,7 +128,7 @@ def sparse_hadamard_sum(Qh, ops, vgeo, dim):
     """
     nf = len(Qh)
     Nh, K = Qh[0].shape
-    Qlog = (np.log(Qh[0]), np.log(Qh[-1]))
+    Qlog = (P._log(Qh[0]), P._log(Qh[-1]))
     out = [np.zeros((Nh, K)) for _ in range(nf)]
     Qs = ops.Qsparse
     for i in range(Nh):
@@ -164,7 +166,7 @@ def dense_hadamard_sum(Qh, ops, vgeo):
     Qr, Qs = ops.Qskew
     nf = len(Qh)
     Nh, K = Qh[0].shape
-    Qlog = (np.log(Qh[0]), np.log(Qh[-1]))
+    Qlog = (P._log(Qh[0]), P._log(Qh[-1]))
     out = [np.zeros((Nh, K)) for _ in range(nf)]
     for i in range(Nh):
         Qi = tuple(q[i] for q in Qh)
