@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- FP64 DOF*RK-stage updates/s of the ESDG rhs + LSRK45 hot path on B200.
+
+Workload (BASELINE.json config 5, the one the north-star target is quoted on): 3D Taylor-Green
+vortex, entropy-stable flux differencing on hexes, N=4, element-partitioned in z-slabs of
+128 x 128 x 16 elements per GPU (weak scaling: 8 GPUs = the full 128^3 mesh).  One "step" is
+one LSRK45 time step = 5 fused rhs+stage updates of every local DOF.
+
+    python bench.py --gpus N --steps K --warmup W            (ours; N>1 under torchrun)
+    python bench.py --impl reference --steps K --warmup W    (reference algorithm on the host CPU)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "FP64 DOF*RK-stage updates/sec (3D Taylor-Green, hex N=4, entropy-stable flux differencing + LSRK45)"
+UNIT = "DOF*stage/s"
+N_DEG = 4
+LOCAL_MESH = (128, 128, 16)       # elements per GPU
+CPU_SAMPLE_MESH = (24, 24, 24)    # bounded CPU sample of the same workload
+CFL = .5
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def alg_bytes_per_element_stage(N, nf=5):
+    """B_alg = 8*Nf*(5*Ns + 2*Nfq) per element-stage (Q,res read+write, traces)."""
+    Ns, Nfq = (N + 1) ** 3, 6 * (N + 1) ** 2
+    return 8 * nf * (5 * Ns + 2 * Nfq)
+
+
+def tgv_dt(N, K1D_global):
+    CN = (N + 1) * (N + 2) * 3 / 2            # dg3D_euler_hex.jl:115-117
+    return CFL * 2 / (CN * K1D_global)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference ALGORITHM (sparse-row Hadamard sum evaluating (i,j) and (j,i), unfused passes,
+    as written in examples/dg3D_euler_hex.jl:122-222) restated in C + OpenMP, on the host cores.
+    Julia is not installed in this image, so this is a port (kind='port'), not the Julia binary."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import c_oracle, physics as P, solvers as SV   # the one other place bench may execute oracle/
+    from esdg_cns_b200 import setup_dg as SD
+    N = N_DEG
+    mesh = CPU_SAMPLE_MESH
+    prd, pops = SD.reference_hex(N)
+    pmd = SD.uniform_hex_mesh_md(prd, mesh, domain=((-np.pi, np.pi),) * 3)
+    x, y, z = SD.hex_node_coords(prd, pmd)
+    rho, u, v, w, p = SD.taylor_green(x, y, z)
+    Q = SD.primitive_to_conservative(rho, (u, v, w), p)
+    co = c_oracle.COracle(pmd, pops)
+    dt = tgv_dt(N, 128)
+    dof = co.nf * co.Nq * co.K
+    for _ in range(args.warmup):
+        co.lsrk45(Q, dt, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        Q, _ = co.lsrk45(Q, dt, 1)
+    el = time.perf_counter() - t0
+    val = dof * 5 * args.steps / el
+    sample = f"{mesh[0]}x{mesh[1]}x{mesh[2]} elements (K={co.K}) of the same TGV hex N={N} workload, {args.steps} LSRK45 steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"tgv_hex_N{N} bounded CPU sample {mesh[0]}x{mesh[1]}x{mesh[2]}", "N": N,
+                   "note": "reference algorithm (dg3D_euler_hex.jl rhs + LSRK45) restated in C/OpenMP; Julia unavailable"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": co.threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(seconds_budget=25.0):
+    from oracle import c_oracle
+    from esdg_cns_b200 import setup_dg as SD
+    N, mesh = N_DEG, CPU_SAMPLE_MESH
+    prd, pops = SD.reference_hex(N)
+    pmd = SD.uniform_hex_mesh_md(prd, mesh, domain=((-np.pi, np.pi),) * 3)
+    x, y, z = SD.hex_node_coords(prd, pmd)
+    Q = SD.primitive_to_conservative(*(lambda r, u, v, w, p: (r, (u, v, w), p))(*SD.taylor_green(x, y, z)))
+    co = c_oracle.COracle(pmd, pops)
+    dt = tgv_dt(N, 128)
+    t0 = time.perf_counter()
+    steps = 0
+    while True:
+        Q, _ = co.lsrk45(Q, dt, 1)
+        steps += 1
+        el = time.perf_counter() - t0
+        if el > seconds_budget / 2 or steps >= 4:
+            break
+    dof = co.nf * co.Nq * co.K
+    return {"value": dof * 5 * steps / el, "unit": UNIT, "cores": co.threads, "kind": "port",
+            "sample": f"{mesh[0]}x{mesh[1]}x{mesh[2]} elements (K={co.K}) of the same TGV hex N={N} workload, "
+                      f"{steps} LSRK45 steps, {el:.1f} s, C/OpenMP restatement of dg3D_euler_hex.jl (Julia unavailable)"}
+
+
+# ------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from esdg_cns_b200 import api, halo as H, setup_dg as SD
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    N = N_DEG
+    Kx, Ky, Kzl = LOCAL_MESH
+    if args.small:
+        Kx, Ky, Kzl = 16, 16, 8
+    Kz = Kzl * world
+    prd, pops = SD.reference_hex(N)
+    # always the periodic box [-pi,pi]^3 so the Taylor-Green field is smooth across the periodic wrap;
+    # with 8 GPUs the mesh is the 128^3 of config 5, with fewer the elements are stretched in z
+    dom = ((-np.pi, np.pi),) * 3
+    md = SD.uniform_hex_mesh_md(prd, (Kx, Ky, Kz), domain=dom, zslab=(rank, world) if world > 1 else None)
+    x, y, z = SD.hex_node_coords(prd, md)
+    rho, u, v, w, p = SD.taylor_green(x, y, z)
+    Q0 = SD.primitive_to_conservative(rho, (u, v, w), p)
+    del x, y, z, rho, u, v, w, p
+    nf, Ns, K = 5, (N + 1) ** 3, md.K
+    dof = nf * Ns * K
+    dt = tgv_dt(N, Kx)
+
+    stream = torch.cuda.current_stream()
+    s = api.Solver(md, pops, device=local_rank, n_halo=md.n_halo, stream=stream.cuda_stream)
+    # pinned host buffers (the user's arrays for the end-to-end leg)
+    pin = [torch.empty((K, Ns), dtype=torch.float64).pin_memory() for _ in range(nf)]
+    host = [t.numpy().T for t in pin]                   # Ns x K column-major views
+    for h, q in zip(host, Q0):
+        h[...] = q
+    del Q0
+    s.upload(host)
+    stepper = H.GpuSlabStepper(s, md, nf, dist, torch, device) if world > 1 else None
+
+    def step():
+        if stepper is None:
+            s.lsrk45(dt, 1)
+        else:
+            stepper.step(dt)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    s.sync()
+    # ---- device-resident timing ---------------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    s.enable_timing(True)
+    l0 = s.kernel_launches()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = s.kernel_launches() - l0
+    s.enable_timing(False)
+    ktimes = {k: s.kernel_time_ms(k) for k in ("hex_stage", "hex_traces", "generic_rhs", "generic_traces", "pack_send")}
+    # ---- end to end through the host-buffer API ---------------------------------------------
+    def e2e_step():
+        s.upload(host)           # H2D of this step's input from pinned memory (+ sync)
+        step()
+        s.download(host)         # D2H of the step's result (synchronous)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+
+    tmax = torch.tensor([ms, e2e_s], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms, e2e_s = float(tmax[0]), float(tmax[1])
+    Qf = s.download()
+    finite = all(np.isfinite(q).all() for q in Qf)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        value = dof * world * 5 * args.steps / (ms * 1e-3)
+        dom_name = max(ktimes, key=lambda k: ktimes[k][0])
+        dom_ms, dom_n = ktimes[dom_name]
+        B_alg = alg_bytes_per_element_stage(N)
+        share = {"hex_stage": 1.0, "generic_rhs": (4 * Ns + 6 * (N + 1) ** 2) / (5 * Ns + 12 * (N + 1) ** 2)}.get(dom_name, 1.0)
+        per_launch_s = dom_ms * 1e-3 / max(dom_n, 1)
+        achieved = B_alg * share * K / per_launch_s / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"tgv_hex_N{N}_{Kx}x{Ky}x{Kzl}_per_gpu", "N": N, "elements_per_gpu": K,
+                       "global_mesh": [Kx, Ky, Kz], "dof_per_gpu": dof, "stages_per_step": 5, "dt": dt,
+                       "l2_policy": f"state {dof * 8 * 2 / 1e9:.2f} GB/GPU streamed every stage (>> 126 MB L2), no flush needed",
+                       "parallelism": f"z-slab x{world}", "finite": finite},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": dom_name, "kernel_ms_per_launch": per_launch_s * 1e3,
+                         "kernel_launches_timed": dom_n, "kernel_share_of_step": dom_ms / ms,
+                         "alg_bytes_per_element_stage": B_alg * share, "peak_source": peak_src,
+                         "ns_per_element_stage": 1e9 * ms * 1e-3 / (args.steps * 5 * K)},
+            "e2e": {"value": dof * world * 5 * e2e_steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": dof * 8, "d2h_bytes_per_step": dof * 8,
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps},
+            "gpu_launches": launches, "clocks": clocks,
+            "kernels_ms": {k: {"total_ms": v[0], "launches": v[1]} for k, v in ktimes.items() if v[1]},
+        }
+        if not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_leg()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--small", action="store_true", help="16x16x8 elements per GPU (debugging only; not a bench number)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

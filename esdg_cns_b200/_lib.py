@@ -58,6 +58,7 @@ _SIGNATURES = {
     "esdg_compute_traces": (C.c_int, [C.c_void_p]),
     "esdg_pack_send": (C.c_int, [C.c_void_p, C.c_void_p]),
     "esdg_halo_ptr": (C.c_int, [C.c_void_p, _PP, C.POINTER(C.c_int64)]),
+    "esdg_unpack_halo": (C.c_int, [C.c_void_p, C.c_void_p]),
     "esdg_stage_update": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int]),
     "esdg_read_rhstest": (C.c_int, [C.c_void_p, C.c_void_p]),
     "esdg_kernel_launches": (C.c_int64, [C.c_void_p]),

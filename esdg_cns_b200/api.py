@@ -156,6 +156,9 @@ class Solver:
         self._ck(self._lib.esdg_halo_ptr(self._ctx, C.byref(p), C.byref(s)))
         return int(p.value), int(s.value)
 
+    def unpack_halo(self, dev_ptr):
+        self._ck(self._lib.esdg_unpack_halo(self._ctx, C.c_void_p(int(dev_ptr))))
+
     def stage_update(self, stage, dt, compute_rhstest=False):
         self._ck(self._lib.esdg_stage_update(self._ctx, int(stage), float(dt), int(bool(compute_rhstest))))
 

@@ -576,6 +576,16 @@ int esdg_halo_ptr(esdg_ctx* ctx, void** halo_dev, int64_t* field_stride) {
     return ESDG_OK;
 }
 
+int esdg_unpack_halo(esdg_ctx* ctx, const void* recv_dev) {
+    int rc = require_ready(ctx, "esdg_unpack_halo");
+    if (rc) return rc;
+    if (ctx->d.n_halo == 0) return ESDG_OK;
+    double* dst = ctx->traces + (long long)ctx->d.Nfq * ctx->d.K;
+    CK(cudaMemcpy2DAsync(dst, ctx->trace_stride * sizeof(double), recv_dev, ctx->d.n_halo * sizeof(double),
+                         ctx->d.n_halo * sizeof(double), ctx->NF, cudaMemcpyDeviceToDevice, ctx->stream));
+    return ESDG_OK;
+}
+
 int esdg_stage_update(esdg_ctx* ctx, int stage, double dt, int compute_rhstest) {
     int rc = require_ready(ctx, "esdg_stage_update");
     if (rc) return rc;

@@ -1,0 +1,67 @@
+"""Face-trace halo exchange for the z-slab element partition.
+
+One process per GPU; ``torch.distributed`` (NCCL over NVLink on the GPU box, gloo in the CPU
+tests) is the plumbing.  Per stage each rank sends the entropy-projected traces of its bottom
+layer's t=-1 faces to the slab below and of its top layer's t=+1 faces to the slab above, and
+receives the matching layers into the halo tail that ``mapP`` points at
+(``setup_dg.uniform_hex_mesh_md(zslab=...)``: lower neighbour's block first, then the upper's).
+"""
+import numpy as np
+
+
+class SlabHalo:
+    def __init__(self, md, nf, dist, torch, device):
+        self.dist, self.torch = dist, torch
+        self.n_lo, self.n_up = int(md.send_lower.size), int(md.send_upper.size)
+        self.n_send = self.n_lo + self.n_up
+        self.n_halo = int(md.n_halo)
+        self.send_list = np.concatenate([md.send_lower, md.send_upper])   # local trace points, 0-based
+        self.lower, self.upper = md.lower_rank, md.upper_rank
+        kw = dict(dtype=torch.float64, device=device)
+        self.send = torch.empty((nf, self.n_send), **kw)
+        self.recv = torch.zeros((nf, self.n_halo), **kw)
+        self._s_lo = torch.empty((nf, self.n_lo), **kw)
+        self._s_up = torch.empty((nf, self.n_up), **kw)
+        self._r_lo = torch.empty((nf, self.n_halo // 2), **kw)
+        self._r_up = torch.empty((nf, self.n_halo // 2), **kw)
+
+    def exchange(self):
+        """self.send (filled by the caller) -> self.recv."""
+        dist = self.dist
+        self._s_lo.copy_(self.send[:, :self.n_lo])
+        self._s_up.copy_(self.send[:, self.n_lo:])
+        ops = []
+        # Sends are posted (to lower, to upper) and receives (from upper, from lower): with two ranks
+        # and a periodic z direction both messages travel between the same pair and match in order.
+        if self.lower is not None:
+            ops.append(dist.P2POp(dist.isend, self._s_lo, self.lower))
+        if self.upper is not None:
+            ops.append(dist.P2POp(dist.isend, self._s_up, self.upper))
+        if self.upper is not None:
+            ops.append(dist.P2POp(dist.irecv, self._r_up, self.upper))
+        if self.lower is not None:
+            ops.append(dist.P2POp(dist.irecv, self._r_lo, self.lower))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        h = self.n_halo // 2
+        self.recv[:, :h].copy_(self._r_lo)
+        self.recv[:, h:].copy_(self._r_up)
+        return self.recv
+
+
+class GpuSlabStepper:
+    """LSRK45 on a z-slab: traces -> pack -> exchange -> fused stage update, per stage."""
+
+    def __init__(self, solver, md, nf, dist, torch, device):
+        self.s = solver
+        self.halo = SlabHalo(md, nf, dist, torch, device)
+        solver.set_send_list(self.halo.send_list)
+
+    def step(self, dt, want_rhstest=False):
+        for k in range(5):
+            self.s.compute_traces()
+            self.s.pack_send(self.halo.send.data_ptr())
+            self.halo.exchange()
+            self.s.unpack_halo(self.halo.recv.data_ptr())
+            self.s.stage_update(k, dt, want_rhstest and k == 4)

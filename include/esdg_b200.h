@@ -127,6 +127,8 @@ int esdg_set_send_list(esdg_ctx* ctx, const int64_t* trace_idx /*1-based*/, int6
 int esdg_compute_traces(esdg_ctx* ctx);                     /* traces of the resident Q      */
 int esdg_pack_send(esdg_ctx* ctx, void* send_dev /* Nfields*n doubles, device */);
 int esdg_halo_ptr(esdg_ctx* ctx, void** halo_dev, int64_t* field_stride);
+/* copy a received buffer of Nfields x n_halo doubles (device) into the halo tail */
+int esdg_unpack_halo(esdg_ctx* ctx, const void* recv_dev);
 /* One LSRK stage whose trace exchange is done by the caller between the two calls:
  *   esdg_compute_traces ; pack ; <exchange> ; esdg_stage_update(stage) */
 int esdg_stage_update(esdg_ctx* ctx, int stage /*0..4*/, double dt, int compute_rhstest);
