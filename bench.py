@@ -192,7 +192,7 @@ def run_ours(args):
         h[...] = q
     del Q0
     s.upload(host)
-    stepper = H.GpuSlabStepper(s, md, nf, dist, torch, device) if world > 1 else None
+    stepper = H.GpuSlabStepper(s, md, dist, torch, device, overlap=not args.no_overlap) if world > 1 else None
 
     def step():
         if stepper is None:
@@ -229,6 +229,8 @@ def run_ours(args):
     # ---- end to end through the host-buffer API ---------------------------------------------
     def e2e_step():
         s.upload(host)           # H2D of this step's input from pinned memory (+ sync)
+        if stepper is not None:
+            stepper.mark_fresh()
         step()
         s.download(host)         # D2H of the step's result (synchronous)
 
@@ -293,6 +295,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--small", action="store_true", help="16x16x8 elements per GPU (debugging only; not a bench number)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange halos without overlapping interior work")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

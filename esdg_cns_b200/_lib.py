@@ -59,7 +59,8 @@ _SIGNATURES = {
     "esdg_pack_send": (C.c_int, [C.c_void_p, C.c_void_p]),
     "esdg_halo_ptr": (C.c_int, [C.c_void_p, _PP, C.POINTER(C.c_int64)]),
     "esdg_unpack_halo": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "esdg_stage_update": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int]),
+    "esdg_stage_update": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int]),
+    "esdg_trace_planes": (C.c_int, [C.c_void_p]),
     "esdg_read_rhstest": (C.c_int, [C.c_void_p, C.c_void_p]),
     "esdg_kernel_launches": (C.c_int64, [C.c_void_p]),
     "esdg_kernel_time_ms": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -159,8 +159,13 @@ class Solver:
     def unpack_halo(self, dev_ptr):
         self._ck(self._lib.esdg_unpack_halo(self._ctx, C.c_void_p(int(dev_ptr))))
 
-    def stage_update(self, stage, dt, compute_rhstest=False):
-        self._ck(self._lib.esdg_stage_update(self._ctx, int(stage), float(dt), int(bool(compute_rhstest))))
+    PART_ALL, PART_BOUNDARY, PART_INTERIOR = 0, 1, 2
+
+    def stage_update(self, stage, dt, compute_rhstest=False, part=0):
+        self._ck(self._lib.esdg_stage_update(self._ctx, int(stage), float(dt), int(bool(compute_rhstest)), int(part)))
+
+    def trace_planes(self):
+        return int(self._lib.esdg_trace_planes(self._ctx))
 
     def read_rhstest(self):
         rt = C.c_double(0.0)

@@ -1,10 +1,6 @@
 // libesdg_b200.so -- C ABI implementation (see include/esdg_b200.h).
-#include "esdg_ctx.h"
-
-#include <algorithm>
-#include <cmath>
-#include <cstdio>
-#include <cstring>
+#include "ctx_util.h"
+#include "hex_fast.h"
 
 #include "kernels_generic.cuh"
 
@@ -12,89 +8,9 @@ using namespace esdg;
 
 #define ESDG_VERSION "esdg_b200 0.1 (sm_100a)"
 
+using namespace esdg_host;
+
 namespace {
-
-int fail(esdg_ctx* c, int code, const std::string& msg) {
-    if (c) c->err = msg;
-    return code;
-}
-
-#define CK(call)                                                                                     \
-    do {                                                                                             \
-        cudaError_t e_ = (call);                                                                     \
-        if (e_ != cudaSuccess)                                                                       \
-            return fail(ctx, e_ == cudaErrorMemoryAllocation ? ESDG_ENOMEM : ESDG_ECUDA,             \
-                        std::string(#call) + ": " + cudaGetErrorString(e_));                         \
-    } while (0)
-
-template <class T>
-int dev_alloc(esdg_ctx* ctx, T** p, size_t n) {
-    void* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
-    if (e != cudaSuccess) return fail(ctx, ESDG_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-    ctx->allocs.push_back(q);
-    *p = (T*)q;
-    return ESDG_OK;
-}
-
-template <class T>
-int dev_upload(esdg_ctx* ctx, T** p, const std::vector<T>& h) {
-    int rc = dev_alloc(ctx, p, h.size());
-    if (rc) return rc;
-    if (!h.empty()) CK(cudaMemcpy(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
-    return ESDG_OK;
-}
-
-// dense column-major -> ELL with the reference's drop tolerance
-int build_ell(esdg_ctx* ctx, const HostMat& A, double tol, DevEll* out) {
-    const int rows = (int)A.rows, cols = (int)A.cols;
-    std::vector<int> cnt(rows, 0);
-    int width = 0;
-    for (int i = 0; i < rows; ++i) {
-        for (int j = 0; j < cols; ++j)
-            if (std::fabs(A.at(i, j)) > tol) cnt[i]++;
-        width = std::max(width, cnt[i]);
-    }
-    width = std::max(width, 1);
-    std::vector<int> col((size_t)rows * width, 0);
-    std::vector<double> val((size_t)rows * width, 0.0);
-    for (int i = 0; i < rows; ++i) {
-        int k = 0;
-        for (int j = 0; j < cols; ++j)
-            if (std::fabs(A.at(i, j)) > tol) {
-                col[(size_t)i * width + k] = j;
-                val[(size_t)i * width + k] = A.at(i, j);
-                ++k;
-            }
-    }
-    out->rows = rows;
-    out->width = width;
-    int rc;
-    if ((rc = dev_upload(ctx, &out->cnt, cnt))) return rc;
-    if ((rc = dev_upload(ctx, &out->col, col))) return rc;
-    if ((rc = dev_upload(ctx, &out->val, val))) return rc;
-    return ESDG_OK;
-}
-
-const HostMat* find(const std::map<std::string, HostMat>& m, const char* name) {
-    auto it = m.find(name);
-    return it == m.end() ? nullptr : &it->second;
-}
-
-void tick(esdg_ctx* ctx, const char* name) {
-    ctx->launches++;
-    if (ctx->timing) {
-        KernelTimer t;
-        t.name = name;
-        cudaEventCreate(&t.a);
-        cudaEventCreate(&t.b);
-        cudaEventRecord(t.a, ctx->stream);
-        ctx->timers.push_back(t);
-    }
-}
-void tock(esdg_ctx* ctx) {
-    if (ctx->timing) cudaEventRecord(ctx->timers.back().b, ctx->stream);
-}
 
 void fill_params(esdg_ctx* ctx, GenericParams& p) {
     const esdg_desc& d = ctx->d;
@@ -165,6 +81,47 @@ int launch_rhs(esdg_ctx* ctx, const double* Qsrc, int mode, double a, double b, 
     return ESDG_OK;
 }
 
+// ---- path selection: tensor-product hex kernels when the operators allow, else generic ----
+int total_partials(const esdg_ctx* ctx) {
+    if (!ctx->hex) return grid_blocks(ctx);
+    const long long EB = ctx->hex->EB, lo = ctx->bnd_lo, hi = ctx->bnd_hi;
+    return (int)((lo + EB - 1) / EB + (hi + EB - 1) / EB + (ctx->d.K - lo - hi + EB - 1) / EB);
+}
+
+int reduce_rhstest(esdg_ctx* ctx, bool split) {
+    // a split stage (boundary + interior launches) lays its partials out per range; an unsplit one
+    // uses ceil(K/EB) slots
+    const int n = ctx->hex ? (split ? total_partials(ctx) : (int)((ctx->d.K + ctx->hex->EB - 1) / ctx->hex->EB))
+                           : grid_blocks(ctx);
+    tick(ctx, "reduce_partials");
+    k_reduce_partials<<<1, 256, 0, ctx->stream>>>(ctx->partials, n, ctx->rhstest_dev);
+    tock(ctx);
+    CK(cudaGetLastError());
+    return ESDG_OK;
+}
+
+// traces (and whatever else the next rhs needs) of state Q
+int do_traces(esdg_ctx* ctx, const double* Q) {
+    if (ctx->hex) return hexfast_traces(ctx, Q);
+    return launch_traces(ctx, Q);
+}
+
+// rhs (mode 0) or fused LSRK stage (mode 1).  After a mode-1 call the traces of the NEW state are
+// valid on both paths (the hex kernel produces them in its epilogue; the generic path launches
+// its trace kernel).
+int do_stage(esdg_ctx* ctx, const double* Q, int mode, double a, double b, double dt, int want, int part) {
+    int rc;
+    if (ctx->hex) {
+        if ((rc = hexfast_stage(ctx, Q, mode, a, b, dt, want, part))) return rc;
+        if (want && part != ESDG_PART_BOUNDARY) return reduce_rhstest(ctx, part == ESDG_PART_INTERIOR);
+        return ESDG_OK;
+    }
+    if (part == ESDG_PART_INTERIOR) return ESDG_OK;   // generic path does not split: all work in the first call
+    if ((rc = launch_rhs(ctx, Q, mode, a, b, dt, want))) return rc;
+    if (mode == 1) return launch_traces(ctx, ctx->Q);
+    return ESDG_OK;
+}
+
 int check_bad(esdg_ctx* ctx) {
     int flag = 0;
     CK(cudaMemcpyAsync(&flag, ctx->bad_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -224,6 +181,7 @@ int esdg_destroy(esdg_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& t : ctx->timers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (void* p : ctx->allocs) cudaFree(p);
+    hexfast_destroy(ctx);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ESDG_OK;
@@ -437,14 +395,23 @@ int esdg_finalize(esdg_ctx* ctx) {
     if ((rc = dev_alloc(ctx, &ctx->rhs, nstate))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->Qin, nstate))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->traces, (size_t)NF * ctx->trace_stride))) return rc;
-    ctx->n_partials = grid_blocks(ctx);
+    ctx->n_partials = (int)std::max<long long>(grid_blocks(ctx), d.K + 4);   // >= blocks of either path, any split
     if ((rc = dev_alloc(ctx, &ctx->partials, (size_t)ctx->n_partials))) return rc;
+    CK(cudaMemset(ctx->partials, 0, (size_t)ctx->n_partials * sizeof(double)));
     if ((rc = dev_alloc(ctx, &ctx->rhstest_dev, 2))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->bad_flag, 1))) return rc;
     CK(cudaMemset(ctx->bad_flag, 0, sizeof(int)));
     CK(cudaMemset(ctx->res, 0, nstate * sizeof(double)));
     CK(cudaMemset(ctx->traces, 0, (size_t)NF * ctx->trace_stride * sizeof(double)));
     CK(cudaMemset(ctx->rhstest_dev, 0, 2 * sizeof(double)));
+    if ((rc = hexfast_try_create(ctx))) return rc;
+    if (ctx->hex) {
+        bool diag = true;
+        for (int64_t e = 0; e < d.K && diag; ++e)
+            for (int k = 0; k < 9; ++k)
+                if (k % 4 != 0 && geo[(size_t)e * ctx->geo_stride + k] != 0.0) { diag = false; break; }
+        ctx->hex->diag = diag && !getenv("ESDG_NO_DIAG");
+    }
     ctx->finalized = true;
     return ESDG_OK;
 }
@@ -492,9 +459,10 @@ int esdg_rhs(esdg_ctx* ctx, const double* const* Q, double* const* rhs_out, int 
             CK(cudaMemcpyAsync(ctx->Qin + f * n, Q[f], n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         src = ctx->Qin;
     }
-    if ((rc = launch_traces(ctx, src))) return rc;
-    if ((rc = launch_rhs(ctx, src, 0, 0, 0, 0, compute_rhstest))) return rc;
-    ctx->traces_valid = false;
+    if (!(src == ctx->Q && ctx->traces_valid))
+        if ((rc = do_traces(ctx, src))) return rc;
+    if ((rc = do_stage(ctx, src, 0, 0, 0, 0, compute_rhstest, ESDG_PART_ALL))) return rc;
+    ctx->traces_valid = (src == ctx->Q);
     for (int f = 0; f < ctx->NF; ++f)
         CK(cudaMemcpyAsync(rhs_out[f], ctx->rhs + f * n, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     double t[2] = {0, 0};
@@ -512,8 +480,11 @@ int esdg_lsrk45_step(esdg_ctx* ctx, double dt, int nsteps, double* rhstest_last)
     for (int s = 0; s < nsteps; ++s)
         for (int k = 0; k < 5; ++k) {
             const int want = (rhstest_last != nullptr) && (s == nsteps - 1) && (k == 4);  // dg2D_euler_quad.jl:202
-            if ((rc = launch_traces(ctx, ctx->Q))) return rc;
-            if ((rc = launch_rhs(ctx, ctx->Q, 1, RK4A[k], RK4B[k], dt, want))) return rc;
+            if (!ctx->traces_valid) {
+                if ((rc = do_traces(ctx, ctx->Q))) return rc;
+                ctx->traces_valid = true;
+            }
+            if ((rc = do_stage(ctx, ctx->Q, 1, RK4A[k], RK4B[k], dt, want, ESDG_PART_ALL))) return rc;
         }
     if (rhstest_last) {
         CK(cudaMemcpyAsync(rhstest_last, ctx->rhstest_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -529,16 +500,31 @@ int esdg_sync(esdg_ctx* ctx) {
 }
 
 // ---- multi-GPU plumbing ----------------------------------------------------------
+static double* cur_traces(esdg_ctx* ctx) { return ctx->hex ? ctx->hex->trace[ctx->hex->prod] : ctx->traces; }
+static int cur_planes(const esdg_ctx* ctx) { return ctx->hex ? ESDG_HEX_TRACE_PLANES : ctx->NF; }
+
+int esdg_trace_planes(esdg_ctx* ctx) { return ctx ? cur_planes(ctx) : 0; }
+
 int esdg_set_send_list(esdg_ctx* ctx, const int64_t* idx, int64_t n) {
     int rc = require_ready(ctx, "esdg_set_send_list");
     if (rc) return rc;
     std::vector<int> h((size_t)n);
+    std::vector<char> is_bnd((size_t)ctx->d.K, 0);
     for (int64_t i = 0; i < n; ++i) {
         const int64_t v = idx[i] - 1;
         if (v < 0 || v >= (int64_t)ctx->d.Nfq * ctx->d.K) return fail(ctx, ESDG_EINVAL, "esdg_set_send_list: index out of range");
         h[(size_t)i] = (int)v;
+        is_bnd[(size_t)(v / ctx->d.Nfq)] = 1;
     }
     ctx->n_send = n;
+    // elements whose traces travel: a leading and a trailing run (z-slab partition); anything else => no split
+    long long lo = 0, hi = 0, cnt = 0;
+    for (char c : is_bnd) cnt += c;
+    while (lo < ctx->d.K && is_bnd[(size_t)lo]) ++lo;
+    while (hi < ctx->d.K - lo && is_bnd[(size_t)(ctx->d.K - 1 - hi)]) ++hi;
+    if (lo + hi != cnt) { lo = ctx->d.K; hi = 0; }   // scattered boundary set: treat every element as boundary
+    ctx->bnd_lo = lo;
+    ctx->bnd_hi = hi;
     return dev_upload(ctx, &ctx->send_idx, h);
 }
 
@@ -553,7 +539,9 @@ __global__ void k_pack_send(const double* __restrict__ traces, long long stride,
 int esdg_compute_traces(esdg_ctx* ctx) {
     int rc = require_ready(ctx, "esdg_compute_traces");
     if (rc) return rc;
-    return launch_traces(ctx, ctx->Q);
+    if ((rc = do_traces(ctx, ctx->Q))) return rc;
+    ctx->traces_valid = true;
+    return ESDG_OK;
 }
 
 int esdg_pack_send(esdg_ctx* ctx, void* send_dev) {
@@ -561,8 +549,8 @@ int esdg_pack_send(esdg_ctx* ctx, void* send_dev) {
     if (rc) return rc;
     if (ctx->n_send == 0) return ESDG_OK;
     tick(ctx, "pack_send");
-    k_pack_send<<<(unsigned)((ctx->n_send + 255) / 256), 256, 0, ctx->stream>>>(ctx->traces, ctx->trace_stride, ctx->send_idx,
-                                                                               ctx->n_send, ctx->NF, (double*)send_dev);
+    k_pack_send<<<(unsigned)((ctx->n_send + 255) / 256), 256, 0, ctx->stream>>>(cur_traces(ctx), ctx->trace_stride, ctx->send_idx,
+                                                                               ctx->n_send, cur_planes(ctx), (double*)send_dev);
     tock(ctx);
     CK(cudaGetLastError());
     return ESDG_OK;
@@ -571,7 +559,7 @@ int esdg_pack_send(esdg_ctx* ctx, void* send_dev) {
 int esdg_halo_ptr(esdg_ctx* ctx, void** halo_dev, int64_t* field_stride) {
     int rc = require_ready(ctx, "esdg_halo_ptr");
     if (rc) return rc;
-    if (halo_dev) *halo_dev = ctx->traces + (long long)ctx->d.Nfq * ctx->d.K;
+    if (halo_dev) *halo_dev = cur_traces(ctx) + (long long)ctx->d.Nfq * ctx->d.K;
     if (field_stride) *field_stride = ctx->trace_stride;
     return ESDG_OK;
 }
@@ -580,17 +568,19 @@ int esdg_unpack_halo(esdg_ctx* ctx, const void* recv_dev) {
     int rc = require_ready(ctx, "esdg_unpack_halo");
     if (rc) return rc;
     if (ctx->d.n_halo == 0) return ESDG_OK;
-    double* dst = ctx->traces + (long long)ctx->d.Nfq * ctx->d.K;
+    double* dst = cur_traces(ctx) + (long long)ctx->d.Nfq * ctx->d.K;
     CK(cudaMemcpy2DAsync(dst, ctx->trace_stride * sizeof(double), recv_dev, ctx->d.n_halo * sizeof(double),
-                         ctx->d.n_halo * sizeof(double), ctx->NF, cudaMemcpyDeviceToDevice, ctx->stream));
+                         ctx->d.n_halo * sizeof(double), cur_planes(ctx), cudaMemcpyDeviceToDevice, ctx->stream));
     return ESDG_OK;
 }
 
-int esdg_stage_update(esdg_ctx* ctx, int stage, double dt, int compute_rhstest) {
+int esdg_stage_update(esdg_ctx* ctx, int stage, double dt, int compute_rhstest, int part) {
     int rc = require_ready(ctx, "esdg_stage_update");
     if (rc) return rc;
     if (stage < 0 || stage > 4) return fail(ctx, ESDG_EINVAL, "esdg_stage_update: stage must be 0..4");
-    return launch_rhs(ctx, ctx->Q, 1, RK4A[stage], RK4B[stage], dt, compute_rhstest);
+    if (part < 0 || part > 2) return fail(ctx, ESDG_EINVAL, "esdg_stage_update: part must be 0 (all), 1 (boundary) or 2 (interior)");
+    if (!ctx->traces_valid) return fail(ctx, ESDG_EINVAL, "esdg_stage_update: call esdg_compute_traces (and exchange halos) after uploading a state");
+    return do_stage(ctx, ctx->Q, 1, RK4A[stage], RK4B[stage], dt, compute_rhstest, part);
 }
 
 int esdg_read_rhstest(esdg_ctx* ctx, double* rhstest) {

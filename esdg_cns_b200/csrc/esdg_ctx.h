@@ -66,6 +66,8 @@ struct esdg_ctx {
 
     // specialised hex path (kernels_hex.cuh); null if the operators do not match
     struct HexFast* hex = nullptr;
+    long long bnd_lo = 0, bnd_hi = 0;   // leading / trailing elements whose traces are sent to neighbours
+    bool res_zero = true;
 
     // accounting
     int64_t launches = 0;

@@ -1,0 +1,313 @@
+// Host side of the tensor-product hex path: structure detection, buffers, launches.
+#include "hex_fast.h"
+
+#include "ctx_util.h"
+#include "kernels_hex.cuh"
+
+using namespace esdg;
+using namespace esdg_host;
+
+namespace {
+
+// Gauss-Legendre nodes/weights on [-1,1], ascending (Newton on P_n).
+void gauss_legendre(int n, double* x, double* w) {
+    for (int i = 0; i < n; ++i) {
+        double z = std::cos(M_PI * (i + 0.75) / (n + 0.5));
+        double pp = 1.0;
+        for (int it = 0; it < 100; ++it) {
+            double p1 = 1.0, p2 = 0.0;
+            for (int j = 0; j < n; ++j) {
+                const double p3 = p2;
+                p2 = p1;
+                p1 = ((2.0 * j + 1.0) * z * p2 - j * p3) / (j + 1.0);
+            }
+            pp = n * (z * p1 - p2) / (z * z - 1.0);
+            const double dz = p1 / pp;
+            z -= dz;
+            if (std::fabs(dz) < 1e-16) break;
+        }
+        x[n - 1 - i] = z;
+        w[n - 1 - i] = 2.0 / ((1.0 - z * z) * pp * pp);
+    }
+}
+
+void lagrange_tables(int n, const double* x, double* D, double* lm, double* lp) {
+    std::vector<double> c(n, 1.0);
+    for (int j = 0; j < n; ++j)
+        for (int m = 0; m < n; ++m)
+            if (m != j) c[j] *= (x[j] - x[m]);
+    for (int i = 0; i < n; ++i) {
+        double s = 0.0;
+        for (int j = 0; j < n; ++j)
+            if (i != j) {
+                D[i * n + j] = c[i] / (c[j] * (x[i] - x[j]));
+                s += D[i * n + j];
+            }
+        D[i * n + i] = -s;
+    }
+    for (int j = 0; j < n; ++j) {
+        double a = 1.0, b = 1.0;
+        for (int m = 0; m < n; ++m)
+            if (m != j) {
+                a *= (-1.0 - x[m]) / (x[j] - x[m]);
+                b *= (1.0 - x[m]) / (x[j] - x[m]);
+            }
+        lm[j] = a;
+        lp[j] = b;
+    }
+}
+
+// max |A - B| / max |B| for a provided column-major matrix against a canonical generator
+template <class F>
+double rel_mismatch(const HostMat& A, F canon) {
+    double err = 0.0, sc = 0.0;
+    for (int64_t j = 0; j < A.cols; ++j)
+        for (int64_t i = 0; i < A.rows; ++i) {
+            const double c = canon((int)i, (int)j);
+            err = std::max(err, std::fabs(A.at(i, j) - c));
+            sc = std::max(sc, std::fabs(c));
+        }
+    return err / std::max(sc, 1e-300);
+}
+
+template <int n>
+void fill_hex_params(esdg_ctx* ctx, HexParams& p) {
+    HexFast* h = ctx->hex;
+    const esdg_desc& d = ctx->d;
+    p.K = d.K;
+    p.e_begin = 0;
+    p.e_count = d.K;
+    p.q_stride = (long long)d.Nq * d.K;
+    p.t_stride = ctx->trace_stride;
+    p.Q = ctx->Q;
+    p.Qout = ctx->Q;
+    p.res = ctx->res;
+    p.rhs = ctx->rhs;
+    p.Lcur = h->logs[h->cons];
+    p.Lnext = h->logs[h->prod];
+    p.Tcur = h->trace[h->cons];
+    p.Tnext = h->trace[h->prod];
+    p.mapP = ctx->mapP;
+    p.geo = ctx->geo;
+    p.geo_stride = ctx->geo_stride;
+    p.gamma = d.gamma;
+    p.lf_scale = d.lf_scale;
+    p.rk_a = p.rk_b = p.dt = 0.0;
+    p.mode = 0;
+    p.want_rhstest = 0;
+    p.partial = ctx->partials;
+    p.bad = ctx->bad_flag;
+    std::memcpy(p.T, h->T, sizeof p.T);
+    std::memcpy(p.lm, h->lm, sizeof p.lm);
+    std::memcpy(p.lp, h->lp, sizeof p.lp);
+    std::memcpy(p.w, h->w, sizeof p.w);
+}
+
+template <int n>
+int set_attrs(esdg_ctx* ctx) {
+    using D = HexDims<n>;
+    HexFast* h = ctx->hex;
+    h->EB = D::EB;
+    h->threads = D::THREADS;
+    h->smem_stage = (size_t)D::SMEM_DOUBLES * sizeof(double);
+    h->smem_traces = (size_t)(D::EB * 5 * D::Nq + 2 * n) * sizeof(double);
+    CK(cudaFuncSetAttribute(k_hex_stage<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage));
+    CK(cudaFuncSetAttribute(k_hex_stage<n, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage));
+    CK(cudaFuncSetAttribute(k_hex_traces<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_traces));
+    return ESDG_OK;
+}
+
+template <int n>
+int launch_traces_n(esdg_ctx* ctx, const double* Q) {
+    HexFast* h = ctx->hex;
+    HexParams p;
+    fill_hex_params<n>(ctx, p);
+    p.Q = Q;
+    const int blocks = (int)((ctx->d.K + h->EB - 1) / h->EB);
+    tick(ctx, "hex_traces");
+    k_hex_traces<n><<<blocks, h->threads, h->smem_traces, ctx->stream>>>(p);
+    tock(ctx);
+    CK(cudaGetLastError());
+    return ESDG_OK;
+}
+
+template <int n>
+int launch_stage_n(esdg_ctx* ctx, const HexParams& p, int blocks) {
+    HexFast* h = ctx->hex;
+    tick(ctx, "hex_stage");
+    if (h->diag)
+        k_hex_stage<n, true><<<blocks, h->threads, h->smem_stage, ctx->stream>>>(p);
+    else
+        k_hex_stage<n, false><<<blocks, h->threads, h->smem_stage, ctx->stream>>>(p);
+    tock(ctx);
+    CK(cudaGetLastError());
+    return ESDG_OK;
+}
+
+int set_attrs_dispatch(esdg_ctx* ctx) {
+    switch (ctx->hex->n) {
+        case 2: return set_attrs<2>(ctx);
+        case 3: return set_attrs<3>(ctx);
+        case 4: return set_attrs<4>(ctx);
+        case 5: return set_attrs<5>(ctx);
+    }
+    return fail(ctx, ESDG_EINVAL, "hex path: unsupported degree");
+}
+
+}  // namespace
+
+int hexfast_try_create(esdg_ctx* ctx) {
+    const esdg_desc& d = ctx->d;
+    if (d.elem != ESDG_HEX || d.dim != 3 || !d.collocated) return ESDG_OK;
+    if (getenv("ESDG_FORCE_GENERIC")) return ESDG_OK;
+    int n = (int)std::lround(std::cbrt((double)d.Nq));
+    if (n * n * n != d.Nq || n < 2 || n > 5 || d.Nfaces != 6 || d.Nfq != 6 * n * n) return ESDG_OK;
+    const int Nq = d.Nq, nfp = n * n, Nfq = d.Nfq, Nh = Nq + Nfq;
+    double x[8], w[8], D[64], lm[8], lp[8];
+    gauss_legendre(n, x, w);
+    lagrange_tables(n, x, D, lm, lp);
+    const HostMat* Ef = find(ctx->ops, "Ef");
+    const HostMat* Ph = find(ctx->ops, "Ph");
+    const HostMat* Lf = find(ctx->ops, "Lf");
+    const HostMat* wq = find(ctx->ops, "wq");
+    const HostMat* Qm[3] = {find(ctx->ops, "Qrh"), find(ctx->ops, "Qsh"), find(ctx->ops, "Qth")};
+    if (!Ef || !Ph || !Lf || !wq || !Qm[0] || !Qm[1] || !Qm[2]) return ESDG_OK;
+    // canonical generators -------------------------------------------------------------
+    auto coords = [&](int i, int* c) { c[0] = i % n; c[1] = (i / n) % n; c[2] = i / (n * n); };
+    auto wq_c = [&](int i) { int c[3]; coords(i, c); return w[c[0]] * w[c[1]] * w[c[2]]; };
+    // face point k -> (direction, side, line base coords)
+    auto ef_c = [&](int k, int i) -> double {
+        const int face = k / nfp, m = k % nfp, dd = face / 2, side = face % 2;
+        const int ip = m % n, jp = m / n;
+        int c[3];
+        coords(i, c);
+        int o1, o2;   // the two on-face coordinates of node i in the face's (jp, ip) convention
+        if (dd == 0) { o1 = c[1]; o2 = c[2]; }
+        else if (dd == 1) { o1 = c[0]; o2 = c[2]; }
+        else { o1 = c[0]; o2 = c[1]; }
+        if (o1 != jp || o2 != ip) return 0.0;
+        return side ? lp[c[dd]] : lm[c[dd]];
+    };
+    auto wf_c = [&](int k) { const int m = k % nfp; return w[m % n] * w[m / n]; };
+    auto q_c = [&](int dd, int i, int j) -> double {
+        if (i < Nq && j < Nq) {
+            int a[3], b[3];
+            coords(i, a);
+            coords(j, b);
+            for (int q = 0; q < 3; ++q)
+                if (q != dd && a[q] != b[q]) return 0.0;
+            const int o1 = (dd + 1) % 3, o2 = (dd + 2) % 3;
+            const double ww = w[a[o1]] * w[a[o2]];
+            return ww * .5 * (w[a[dd]] * D[a[dd] * n + b[dd]] - w[b[dd]] * D[b[dd] * n + a[dd]]);
+        }
+        if (i < Nq && j >= Nq) {   // .5 * Ef' * B
+            const int k = j - Nq, face = k / nfp;
+            if (face / 2 != dd) return 0.0;
+            const double nr = (face % 2) ? 1.0 : -1.0;
+            return .5 * ef_c(k, i) * wf_c(k) * nr;
+        }
+        if (i >= Nq && j < Nq) {
+            const int k = i - Nq, face = k / nfp;
+            if (face / 2 != dd) return 0.0;
+            const double nr = (face % 2) ? 1.0 : -1.0;
+            return -.5 * ef_c(k, j) * wf_c(k) * nr;
+        }
+        return 0.0;
+    };
+    const double TOLM = 1e-10;
+    bool ok = rel_mismatch(*wq, [&](int i, int) { return wq_c(i); }) < TOLM;
+    ok = ok && rel_mismatch(*Ef, ef_c) < TOLM;
+    for (int dd = 0; dd < 3 && ok; ++dd) ok = rel_mismatch(*Qm[dd], [&](int i, int j) { return q_c(dd, i, j); }) < TOLM;
+    // volume_scale * Ph == 2 * diag(1/wq) [I; Ef]'
+    ok = ok && rel_mismatch(*Ph, [&](int i, int j) {
+             const double v = j < Nq ? (i == j ? 1.0 : 0.0) : ef_c(j - Nq, i);
+             return 2.0 * v / wq_c(i) / d.volume_scale;
+         }) < TOLM;
+    ok = ok && rel_mismatch(*Lf, [&](int i, int k) { return ef_c(k, i) * wf_c(k) / wq_c(i); }) < TOLM;
+    if (!ok) return ESDG_OK;   // e.g. the upstream s-fastest node ordering: generic kernels handle it
+
+    HexFast* h = new HexFast();
+    ctx->hex = h;
+    h->n = n;
+    for (int a = 0; a < n; ++a) {
+        h->lm[a] = lm[a];
+        h->lp[a] = lp[a];
+        h->w[a] = w[a];
+        for (int b = 0; b < n; ++b) h->T[a * n + b] = (w[a] * D[a * n + b] - w[b] * D[b * n + a]) / w[a];
+    }
+    (void)Nh;
+    int rc;
+    if ((rc = set_attrs_dispatch(ctx))) return rc;
+    for (int q = 0; q < 2; ++q) {
+        if ((rc = dev_alloc(ctx, &h->trace[q], (size_t)HEX_TP * ctx->trace_stride))) return rc;
+        if ((rc = dev_alloc(ctx, &h->logs[q], (size_t)2 * d.Nq * d.K))) return rc;
+        CK(cudaMemset(h->trace[q], 0, (size_t)HEX_TP * ctx->trace_stride * sizeof(double)));
+    }
+    return ESDG_OK;
+}
+
+void hexfast_destroy(esdg_ctx* ctx) {
+    delete ctx->hex;
+    ctx->hex = nullptr;
+}
+
+int hexfast_traces(esdg_ctx* ctx, const double* Q) {
+    HexFast* h = ctx->hex;
+    h->prod ^= 1;            // write a fresh buffer; consumers switch to it at their next stage
+    h->cons = h->prod ^ 1;
+    switch (h->n) {
+        case 2: return launch_traces_n<2>(ctx, Q);
+        case 3: return launch_traces_n<3>(ctx, Q);
+        case 4: return launch_traces_n<4>(ctx, Q);
+        case 5: return launch_traces_n<5>(ctx, Q);
+    }
+    return fail(ctx, ESDG_EINVAL, "hex path: unsupported degree");
+}
+
+int hexfast_stage(esdg_ctx* ctx, const double* Q, int mode, double a, double b, double dt, int want_rhstest, int part) {
+    HexFast* h = ctx->hex;
+    const esdg_desc& d = ctx->d;
+    if (part != ESDG_PART_INTERIOR) {   // first (or only) part of a stage: consume what was produced last
+        h->cons = h->prod;
+        if (mode == 1) h->prod = h->cons ^ 1;
+    }
+    long long begin[2] = {0, 0}, count[2] = {d.K, 0};
+    int nr = 1;
+    const long long lo = ctx->bnd_lo, hi = ctx->bnd_hi;
+    if (part == ESDG_PART_BOUNDARY) {
+        begin[0] = 0; count[0] = lo;
+        begin[1] = d.K - hi; count[1] = hi;
+        nr = 2;
+    } else if (part == ESDG_PART_INTERIOR) {
+        begin[0] = lo; count[0] = d.K - lo - hi;
+    }
+    int block_off = part == ESDG_PART_INTERIOR ? (int)((lo + h->EB - 1) / h->EB + (hi + h->EB - 1) / h->EB) : 0;
+    for (int r = 0; r < nr; ++r) {
+        if (count[r] <= 0) continue;
+        HexParams p;
+        switch (h->n) {
+            case 2: fill_hex_params<2>(ctx, p); break;
+            case 3: fill_hex_params<3>(ctx, p); break;
+            case 4: fill_hex_params<4>(ctx, p); break;
+            default: fill_hex_params<5>(ctx, p); break;
+        }
+        p.Q = Q;
+        p.e_begin = begin[r];
+        p.e_count = count[r];
+        p.mode = mode;
+        p.rk_a = a; p.rk_b = b; p.dt = dt;
+        p.want_rhstest = want_rhstest;
+        p.partial = ctx->partials + block_off;
+        const int blocks = (int)((count[r] + h->EB - 1) / h->EB);
+        block_off += blocks;
+        int rc;
+        switch (h->n) {
+            case 2: rc = launch_stage_n<2>(ctx, p, blocks); break;
+            case 3: rc = launch_stage_n<3>(ctx, p, blocks); break;
+            case 4: rc = launch_stage_n<4>(ctx, p, blocks); break;
+            default: rc = launch_stage_n<5>(ctx, p, blocks); break;
+        }
+        if (rc) return rc;
+    }
+    return ESDG_OK;
+}

@@ -1,0 +1,29 @@
+// Host side of the tensor-product hex path (kernels_hex.cuh).
+#pragma once
+#include "esdg_ctx.h"
+
+constexpr int ESDG_HEX_TRACE_PLANES = 7;   // == esdg::HEX_TP (kernels_hex.cuh)
+
+struct HexFast {
+    int n = 0;                 // N + 1
+    bool diag = false;         // axis-aligned elements: only rxJ, syJ, tzJ non-zero
+    double T[64], lm[8], lp[8], w[8];
+    double* trace[2] = {nullptr, nullptr};   // 7 planes x trace_stride each
+    double* logs[2] = {nullptr, nullptr};    // 2 planes x Nq*K each (log rho, log beta at volume nodes)
+    int prod = 0;              // buffer most recently produced (pack/unpack act on it)
+    int cons = 0;              // buffer the running stage consumes
+    size_t smem_stage = 0, smem_traces = 0;
+    int threads = 0, EB = 1;
+};
+
+enum { ESDG_PART_ALL = 0, ESDG_PART_BOUNDARY = 1, ESDG_PART_INTERIOR = 2 };
+
+// Decide whether the caller's operators are the Kronecker products the hex kernels assume;
+// on success ctx->hex is set (device buffers allocated).  Returns an esdg_status; a mismatch is
+// NOT an error (ctx->hex stays null and the generic kernels are used).
+int hexfast_try_create(esdg_ctx* ctx);
+void hexfast_destroy(esdg_ctx* ctx);
+// traces + log stash of state Q into a fresh buffer (becomes `prod`)
+int hexfast_traces(esdg_ctx* ctx, const double* Q);
+// one rhs evaluation (mode 0) or fused LSRK stage (mode 1) over a part of the elements
+int hexfast_stage(esdg_ctx* ctx, const double* Q, int mode, double a, double b, double dt, int want_rhstest, int part);

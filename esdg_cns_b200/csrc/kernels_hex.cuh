@@ -1,0 +1,517 @@
+// Tensor-product hex kernels (collocated Gauss nodes, affine elements) -- the product path
+// for BASELINE configs 4/5.  One launch per LSRK stage does everything the reference's
+// rhs() + stage update do (examples/dg3D_euler_hex.jl:167-222, dg2D_euler_quad.jl:198-207):
+//
+//   A  stage Q; (rho,u,beta,logs) at volume nodes; own face traces -> shared memory
+//   B  surface: exterior trace gather through mapP, EC flux . nJ, Lax-Friedrichs penalty   (:182-197)
+//   C  flux differencing along the r, s, t grid lines.  Every UNORDERED pair of the
+//      hybridized operator is evaluated once (the symmetric loop of
+//      CompressibleNS/dg2D_CNS_cavity_optimized.jl:326-347): each volume thread owns the
+//      pairs (x, x+k mod n) of its line plus its 2 face partners per direction, and hands
+//      the contracted flux to the partner through shared memory
+//   D  partner gather; per face node H = -nrJ*sum_a l[a]*F + flux*   (Ph / Lf applied as 1-D sweeps)
+//   E  rhs = -(...)/J ; rhstest ; res = a*res + dt*rhs ; Q += b*res                       (:205-206)
+//   F  entropy projection of the NEW state to the faces -> traces for the next stage      (:175-178)
+//
+// Operators never appear as matrices: the kernel holds the 1-D pair coefficients
+// T[a][a'] = (w_a D[a,a'] - w_a' D[a',a]) / w_a, the end-point interpolation vectors lm, lp and
+// the Gauss weights.  esdg_finalize proves (to 1e-10) that the caller's Qrh/Qsh/Qth, Ef, Ph, Lf
+// ARE the Kronecker products of these before selecting this path; otherwise the generic
+// table-driven kernels run.
+//
+// Trace format (7 planes): rho, u, v, w, beta, log(rho), log(beta) at every face point -- what
+// the neighbour's surface flux needs, so the exterior logs are not recomputed.
+#pragma once
+#include "physics.cuh"
+
+namespace esdg {
+
+constexpr int HEX_TP = 7;   // trace planes (== ESDG_HEX_TRACE_PLANES in hex_fast.h)
+
+struct HexParams {
+    long long K, e_begin, e_count;
+    long long q_stride;      // Nq*K
+    long long t_stride;      // Nfq*K + n_halo
+    const double* Q;
+    double* Qout;
+    double* res;
+    double* rhs;
+    const double* Lcur;      // stashed (log rho, log beta) of Q at volume nodes: 2 planes of q_stride
+    double* Lnext;
+    const double* Tcur;
+    double* Tnext;
+    const int* mapP;
+    const double* geo;
+    int geo_stride;
+    double gamma, lf_scale;
+    double rk_a, rk_b, dt;
+    int mode;                // 0: write rhs ; 1: fused LSRK stage + traces of the new state
+    int want_rhstest;
+    double* partial;
+    int* bad;
+    double T[64], lm[8], lp[8], w[8];
+};
+
+template <int n>
+struct HexDims {
+    static constexpr int Nq = n * n * n, nfp = n * n, Nfq = 6 * nfp, Nh = Nq + Nfq;
+    static constexpr int KH = n / 2;                         // owned offsets per line
+    static constexpr int EB = (128 / Nq) > 0 ? (128 / Nq) : 1;
+    static constexpr int THREADS = ((EB * Nq + 31) / 32) * 32;
+    static constexpr int XV = KH * 5 * Nq, XF = 2 * 5 * nfp * n;
+    static constexpr int XSZ = (XV + XF) > 5 * Nq ? (XV + XF) : 5 * Nq;
+    static constexpr int TAB = n * n + 5 * n;
+    static constexpr int SMEM_DOUBLES = EB * (7 * Nh + XSZ + 5 * Nfq) + TAB;
+};
+
+struct Node {
+    double rho, u[3], beta, lr, lb;
+};
+
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+
+__device__ __forceinline__ Node ld_node(const double* W, int Nh, int idx) {
+    Node a;
+    a.rho = W[idx];
+    a.u[0] = W[Nh + idx];
+    a.u[1] = W[2 * Nh + idx];
+    a.u[2] = W[3 * Nh + idx];
+    a.beta = W[4 * Nh + idx];
+    a.lr = W[5 * Nh + idx];
+    a.lb = W[6 * Nh + idx];
+    return a;
+}
+
+// Entropy-conservative flux (euler_fluxes.jl:51-89 with logmean.jl:14-28) contracted with a
+// direction vector g: F[f] = sum_d g[d]*F_d[f](A,B).  DIAG: only g[D] is non-zero.
+// One reciprocal serves the three quotients rholog = da/dlog, 1/betalog and pa = rhoavg/(bA+bB).
+template <bool DIAG, int D>
+__device__ __forceinline__ void pair_flux(const Node& A, const Node& B, const double* g, double c_igm, double* F) {
+    const double dar = B.rho - A.rho, hr = .5 * (A.rho + B.rho);
+    const double dab = B.beta - A.beta, sb = A.beta + B.beta, hb = .5 * sb;
+    const bool tr = fabs(dar) < 1e-4 * hr, tb = fabs(dab) < 1e-4 * hb;
+    const double X = tr ? hr : (B.lr - A.lr);
+    const double Y = tb ? hb : dab;
+    const double XY = X * Y;
+    const double R = fast_rcp(XY * sb);
+    const double iX = R * (Y * sb), iY = R * (X * sb), iZ = R * XY;
+    const double qr = dar * iX;   // f (Taylor branch) or the log mean itself
+    const double vr = qr * qr;
+    const double rholog = tr ? hr * (1.0 + vr * (-.2 - vr * (.0512 - vr * 0.026038857142857))) : qr;
+    const double fb = dab * iY, vb = fb * fb;
+    const double xb = vb * (-.2 - vb * (.0512 - vb * 0.026038857142857));
+    const double ibl = iY * (tb ? (1.0 - xb) : (B.lb - A.lb));   // 1/betalog
+    const double pa = hr * iZ;                                    // rhoavg/(betaL+betaR)
+    double uavg[3], unorm = 0.0, un;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        uavg[d] = .5 * (A.u[d] + B.u[d]);
+        unorm = fma(A.u[d], B.u[d], unorm);
+    }
+    if (DIAG) {
+        un = g[D] * uavg[D];
+    } else {
+        un = g[0] * uavg[0];
+        un = fma(g[1], uavg[1], un);
+        un = fma(g[2], uavg[2], un);
+    }
+    const double Ep = fma(rholog, fma(ibl, c_igm, .5 * unorm), pa);   // rholog/(2(g-1)betalog)+pa+.5 rholog unorm
+    const double m = rholog * un;
+    F[0] = m;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (DIAG)
+            F[1 + d] = (d == D) ? fma(m, uavg[d], pa * g[d]) : m * uavg[d];
+        else
+            F[1 + d] = fma(m, uavg[d], pa * g[d]);
+    }
+    F[4] = Ep * un;
+}
+
+// volume-node primitives from conservative state; logs supplied (stash) or computed
+__device__ __forceinline__ void vol_prim(const double* U, double gamma, Node& P, double& rhoe, bool& bad) {
+    const double ir = fast_rcp(U[0]);
+    double ke = 0.0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        P.u[d] = U[1 + d] * ir;
+        ke = fma(U[1 + d], P.u[d], ke);
+    }
+    rhoe = U[4] - .5 * ke;
+    bad = bad || !(U[0] > 0.0) || !(rhoe > 0.0);
+    P.rho = U[0];
+    P.beta = .5 * U[0] * fast_rcp((gamma - 1.0) * rhoe);
+}
+
+// v_ufun (euler_variables.jl:79-86) with s = log((g-1)rhoe/rho^g) = (1-g) log rho - log beta - log 2
+__device__ __forceinline__ void entropy_vars(const double* U, double rhoe, double lr, double lb, double gamma, double* V) {
+    const double s = (1.0 - gamma) * lr - lb - 0.6931471805599453094;
+    const double ire = fast_rcp(rhoe);
+    V[0] = fma(-U[4], ire, gamma + 1.0 - s);
+    V[1] = U[1] * ire;
+    V[2] = U[2] * ire;
+    V[3] = U[3] * ire;
+    V[4] = -U[0] * ire;
+}
+
+// u_vfun (euler_variables.jl:95-113) followed by betafun / velocity / logs, all from the projected
+// entropy variables: rhoeV = exp((log(g-1) - g log(-vE) - s)/(g-1)), rho = rhoeV(-vE),
+// u = vU/(-vE), beta = -vE/(2(g-1)) (identically rho/(2p)), log rho and log beta follow without
+// further transcendental calls.
+__device__ __forceinline__ void trace_from_entropy(const double* V, double gamma, double* Tv) {
+    const double nvE = -V[4];
+    const double inv = fast_rcp(nvE);
+    const double v2 = fma(V[1], V[1], fma(V[2], V[2], V[3] * V[3]));
+    const double s = gamma - V[0] - .5 * v2 * inv;
+    const double lv = log(nvE);
+    const double ig = 1.0 / (gamma - 1.0);
+    const double lrhoe = (log(gamma - 1.0) - gamma * lv - s) * ig;
+    const double rhoeV = exp(lrhoe);
+    Tv[0] = rhoeV * nvE;
+    Tv[1] = V[1] * inv;
+    Tv[2] = V[2] * inv;
+    Tv[3] = V[3] * inv;
+    Tv[4] = .5 * nvE * ig;
+    Tv[5] = lrhoe + lv;
+    Tv[6] = lv - log(2.0 * (gamma - 1.0));
+}
+
+// face point (face = 2*d + side, m) -> first volume node of its line and the line stride
+template <int n>
+__device__ __forceinline__ void face_line(int d, int m, int& base, int& stride) {
+    const int ip = m % n, jp = m / n;
+    if (d == 0) { base = n * jp + n * n * ip; stride = 1; }
+    else if (d == 1) { base = jp + n * n * ip; stride = n; }
+    else { base = jp + n * ip; stride = n * n; }
+}
+
+// Phase F: project entropy variables (shared V[5][Nq] per element) to the faces, write 7-plane traces
+template <int n>
+__device__ __forceinline__ void write_traces(const HexParams& p, const double* sV, const double* s_lm, const double* s_lp,
+                                             long long e0, int nb) {
+    using D = HexDims<n>;
+    for (int it = threadIdx.x; it < nb * D::Nfq; it += blockDim.x) {
+        const int eb = it / D::Nfq, k = it - eb * D::Nfq;
+        const int face = k / D::nfp, m = k - face * D::nfp;
+        int base, stride;
+        face_line<n>(face >> 1, m, base, stride);
+        const double* l = (face & 1) ? s_lp : s_lm;
+        const double* v = sV + eb * 5 * D::Nq + base;
+        double V[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+        for (int a = 0; a < n; ++a) {
+            const double la = l[a];
+#pragma unroll
+            for (int f = 0; f < 5; ++f) V[f] = fma(la, v[f * D::Nq + a * stride], V[f]);
+        }
+        double Tv[HEX_TP];
+        trace_from_entropy(V, p.gamma, Tv);
+        const long long g = (e0 + eb) * D::Nfq + k;
+#pragma unroll
+        for (int q = 0; q < HEX_TP; ++q) p.Tnext[q * p.t_stride + g] = Tv[q];
+    }
+}
+
+// Traces (+ log stash) of a given state: used once after upload and by the rhs-only entry point.
+template <int n>
+__global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_traces(const __grid_constant__ HexParams p) {
+    using D = HexDims<n>;
+    extern __shared__ double sm[];
+    double* sV = sm;                       // [EB][5][Nq]
+    double* s_lm = sm + D::EB * 5 * D::Nq;
+    double* s_lp = s_lm + n;
+    const int tid = threadIdx.x;
+    if (tid < n) { s_lm[tid] = p.lm[tid]; s_lp[tid] = p.lp[tid]; }
+    const long long e0 = p.e_begin + (long long)blockIdx.x * D::EB;
+    const int nb = (int)min((long long)D::EB, p.e_begin + p.e_count - e0);
+    bool bad = false;
+    if (tid < nb * D::Nq) {
+        const int eb = tid / D::Nq, i = tid - eb * D::Nq;
+        const long long g = (e0 + eb) * D::Nq + i;
+        double U[5], V[5], rhoe;
+#pragma unroll
+        for (int f = 0; f < 5; ++f) U[f] = p.Q[f * p.q_stride + g];
+        Node P;
+        vol_prim(U, p.gamma, P, rhoe, bad);
+        const double lr = log(P.rho), lb = log(P.beta);
+        p.Lnext[g] = lr;
+        p.Lnext[p.q_stride + g] = lb;
+        entropy_vars(U, rhoe, lr, lb, p.gamma, V);
+#pragma unroll
+        for (int f = 0; f < 5; ++f) sV[(eb * 5 + f) * D::Nq + i] = V[f];
+    }
+    __syncthreads();
+    write_traces<n>(p, sV, s_lm, s_lp, e0, nb);
+    if (bad) atomicOr(p.bad, 1);
+}
+
+template <int n, bool DIAG>
+__global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_constant__ HexParams p) {
+    using D = HexDims<n>;
+    constexpr int Nq = D::Nq, nfp = D::nfp, Nfq = D::Nfq, Nh = D::Nh, KH = D::KH;
+    extern __shared__ double sm[];
+    double* sW = sm;                              // [EB][7][Nh]
+    double* sX = sW + D::EB * 7 * Nh;             // [EB][XSZ]   (XV | XF), later V[5][Nq]
+    double* sFL = sX + D::EB * D::XSZ;            // [EB][5][Nfq]
+    double* s_T = sFL + D::EB * 5 * Nfq;          // [n][n]
+    double* s_lm = s_T + n * n;
+    double* s_lp = s_lm + n;
+    double* s_lmw = s_lp + n;                     // lm[a]/w[a]
+    double* s_lpw = s_lmw + n;
+    double* s_w = s_lpw + n;
+    const int tid = threadIdx.x;
+    if (tid < n * n) s_T[tid] = p.T[tid];
+    if (tid < n) {
+        s_lm[tid] = p.lm[tid];
+        s_lp[tid] = p.lp[tid];
+        s_lmw[tid] = p.lm[tid] / p.w[tid];
+        s_lpw[tid] = p.lp[tid] / p.w[tid];
+        s_w[tid] = p.w[tid];
+    }
+    const long long e0 = p.e_begin + (long long)blockIdx.x * D::EB;
+    const int nb = (int)min((long long)D::EB, p.e_begin + p.e_count - e0);
+    const bool vol = tid < nb * Nq;
+    const int eb = vol ? tid / Nq : 0;
+    const int i = tid - eb * Nq;
+    const int xa = i % n, xb = (i / n) % n, xc = i / (n * n);
+    const long long e = e0 + eb;
+    const long long gq = e * Nq + i;
+    const double c_igm = 1.0 / (2.0 * (p.gamma - 1.0));
+    bool bad = false;
+
+    // ---- A: volume nodes + own traces -> shared -----------------------------------------------
+    double U[5] = {1, 0, 0, 0, 1}, rhoe = 1.0;
+    Node Pi;
+    double* W = sW + eb * 7 * Nh;
+    if (vol) {
+#pragma unroll
+        for (int f = 0; f < 5; ++f) U[f] = p.Q[f * p.q_stride + gq];
+        vol_prim(U, p.gamma, Pi, rhoe, bad);
+        Pi.lr = p.Lcur[gq];
+        Pi.lb = p.Lcur[p.q_stride + gq];
+        W[i] = Pi.rho;
+        W[Nh + i] = Pi.u[0];
+        W[2 * Nh + i] = Pi.u[1];
+        W[3 * Nh + i] = Pi.u[2];
+        W[4 * Nh + i] = Pi.beta;
+        W[5 * Nh + i] = Pi.lr;
+        W[6 * Nh + i] = Pi.lb;
+    }
+    for (int q = 0; q < HEX_TP; ++q) {
+        const double* src = p.Tcur + q * p.t_stride + e0 * Nfq;
+        for (int it = tid; it < nb * Nfq; it += blockDim.x) {
+            const int b2 = it / Nfq, k = it - b2 * Nfq;
+            sW[(b2 * 7 + q) * Nh + Nq + k] = src[it];
+        }
+    }
+    __syncthreads();
+
+    // ---- B: surface flux at face points (dg3D_euler_hex.jl:182-197) ----------------------------
+    for (int it = tid; it < nb * Nfq; it += blockDim.x) {
+        const int b2 = it / Nfq, k = it - b2 * Nfq;
+        const long long ee = e0 + b2;
+        const int face = k / nfp;
+        const double* gf = p.geo + ee * p.geo_stride + 10 + face * 4;
+        const double nJ[3] = {gf[0], gf[1], gf[2]};
+        const double sJ = gf[3];
+        const int ip = p.mapP[ee * Nfq + k];
+        Node M = ld_node(sW + b2 * 7 * Nh, Nh, Nq + k), P;
+        P.rho = p.Tcur[ip];
+        P.u[0] = p.Tcur[p.t_stride + ip];
+        P.u[1] = p.Tcur[2 * p.t_stride + ip];
+        P.u[2] = p.Tcur[3 * p.t_stride + ip];
+        P.beta = p.Tcur[4 * p.t_stride + ip];
+        P.lr = p.Tcur[5 * p.t_stride + ip];
+        P.lb = p.Tcur[6 * p.t_stride + ip];
+        double F[5];
+        pair_flux<false, 0>(M, P, nJ, c_igm, F);
+        if (p.lf_scale != 0.0) {
+            // conservative states from the primitive traces: E = p/(g-1) + .5 rho |u|^2, p = rho/(2 beta)
+            const double isJ = fast_rcp(sJ);
+            const double g1 = p.gamma - 1.0;
+            double UM[5], UP[5], unM = 0.0, unP = 0.0, kM = 0.0, kP = 0.0;
+            UM[0] = M.rho;
+            UP[0] = P.rho;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                UM[1 + d] = M.rho * M.u[d];
+                UP[1 + d] = P.rho * P.u[d];
+                kM = fma(UM[1 + d], M.u[d], kM);
+                kP = fma(UP[1 + d], P.u[d], kP);
+                unM = fma(UM[1 + d], nJ[d], unM);
+                unP = fma(UP[1 + d], nJ[d], unP);
+            }
+            const double pM = .5 * M.rho * fast_rcp(M.beta), pP = .5 * P.rho * fast_rcp(P.beta);
+            UM[4] = fma(.5, kM, pM / g1);
+            UP[4] = fma(.5, kP, pP / g1);
+            const double lamM = wavespeed_1d(UM[0], unM * isJ, UM[4], p.gamma);
+            const double lamP = wavespeed_1d(UP[0], unP * isJ, UP[4], p.gamma);
+            const double LFc = p.lf_scale * fmax(lamM, lamP) * sJ;
+#pragma unroll
+            for (int f = 0; f < 5; ++f) F[f] = fma(-LFc, UP[f] - UM[f], F[f]);
+        }
+#pragma unroll
+        for (int f = 0; f < 5; ++f) sFL[(b2 * 5 + f) * Nfq + k] = F[f];
+    }
+
+    // ---- C/D: flux differencing, one reference direction at a time ------------------------------
+    double acc[5] = {0, 0, 0, 0, 0};
+    const double* G = p.geo + e * p.geo_stride;
+    double* XVb = sX + eb * D::XSZ;
+    double* XFb = XVb + D::XV;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int xd = d == 0 ? xa : (d == 1 ? xb : xc);
+        const int sd = d == 0 ? 1 : (d == 1 ? n : n * n);
+        const int m = d == 0 ? (xc + n * xb) : (d == 1 ? (xc + n * xa) : (xb + n * xa));   // on-face index of my line
+        if (vol) {
+            const double g[3] = {G[d], G[3 + d], G[6 + d]};   // (r_x, r_y, r_z) J  of direction d
+            // owned volume pairs (x, x+k mod n)
+#pragma unroll
+            for (int k = 1; k <= KH; ++k) {
+                const bool own = !((n % 2 == 0) && (k == n / 2) && (xd >= n / 2));
+                int ap = xd + k;
+                ap = ap >= n ? ap - n : ap;
+                if (own) {
+                    const Node Pj = ld_node(W, Nh, i + (ap - xd) * sd);
+                    double F[5];
+                    if (d == 0) pair_flux<DIAG, 0>(Pi, Pj, g, c_igm, F);
+                    else if (d == 1) pair_flux<DIAG, 1>(Pi, Pj, g, c_igm, F);
+                    else pair_flux<DIAG, 2>(Pi, Pj, g, c_igm, F);
+                    const double t = s_T[xd * n + ap];
+#pragma unroll
+                    for (int f = 0; f < 5; ++f) {
+                        acc[f] = fma(t, F[f], acc[f]);
+                        XVb[((k - 1) * 5 + f) * Nq + i] = F[f];
+                    }
+                }
+            }
+            // the two face partners of my line
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const Node Pf = ld_node(W, Nh, Nq + (2 * d + side) * nfp + m);
+                double F[5];
+                if (d == 0) pair_flux<DIAG, 0>(Pi, Pf, g, c_igm, F);
+                else if (d == 1) pair_flux<DIAG, 1>(Pi, Pf, g, c_igm, F);
+                else pair_flux<DIAG, 2>(Pi, Pf, g, c_igm, F);
+                const double t = side ? s_lpw[xd] : -s_lmw[xd];
+#pragma unroll
+                for (int f = 0; f < 5; ++f) {
+                    acc[f] = fma(t, F[f], acc[f]);
+                    XFb[((side * 5 + f) * nfp + m) * n + xd] = F[f];
+                }
+            }
+        }
+        __syncthreads();
+        if (vol) {
+#pragma unroll
+            for (int k = 1; k <= KH; ++k) {
+                int am = xd - k;
+                am = am < 0 ? am + n : am;
+                const bool has = !((n % 2 == 0) && (k == n / 2) && (am >= n / 2));
+                if (has) {
+                    const double t = s_T[xd * n + am];
+                    const int j = i + (am - xd) * sd;
+#pragma unroll
+                    for (int f = 0; f < 5; ++f) acc[f] = fma(t, XVb[((k - 1) * 5 + f) * Nq + j], acc[f]);
+                }
+            }
+        }
+        // face nodes of this direction: H = -nrJ * sum_a l[a] F(a) + flux*
+        for (int it = tid; it < nb * 2 * nfp; it += blockDim.x) {
+            const int b2 = it / (2 * nfp), r = it - b2 * 2 * nfp;
+            const int side = r / nfp, mm = r - side * nfp;
+            const double* xf = sX + b2 * D::XSZ + D::XV;
+            const double* l = side ? s_lp : s_lm;
+            const double sg = side ? -1.0 : 1.0;
+#pragma unroll
+            for (int f = 0; f < 5; ++f) {
+                double h = 0.0;
+#pragma unroll
+                for (int a = 0; a < n; ++a) h = fma(l[a], xf[((side * 5 + f) * nfp + mm) * n + a], h);
+                double* dst = sFL + (b2 * 5 + f) * Nfq + (2 * d + side) * nfp + mm;
+                *dst = fma(sg, h, *dst);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- E: lift, scale, rhstest, LSRK stage ----------------------------------------------------
+    double tsum = 0.0;
+    if (vol) {
+        const double* FL = sFL + eb * 5 * Nfq;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int xd = d == 0 ? xa : (d == 1 ? xb : xc);
+            const int m = d == 0 ? (xc + n * xb) : (d == 1 ? (xc + n * xa) : (xb + n * xa));
+            const double cm = s_lmw[xd], cp = s_lpw[xd];
+#pragma unroll
+            for (int f = 0; f < 5; ++f) {
+                acc[f] = fma(cm, FL[f * Nfq + (2 * d) * nfp + m], acc[f]);
+                acc[f] = fma(cp, FL[f * Nfq + (2 * d + 1) * nfp + m], acc[f]);
+            }
+        }
+        const double J = G[9];
+        const double mJ = -1.0 / J;
+        double r[5];
+#pragma unroll
+        for (int f = 0; f < 5; ++f) r[f] = acc[f] * mJ;
+        if (p.want_rhstest) {
+            double V[5];
+            entropy_vars(U, rhoe, Pi.lr, Pi.lb, p.gamma, V);
+            const double wJ = s_w[xa] * s_w[xb] * s_w[xc] * J;
+#pragma unroll
+            for (int f = 0; f < 5; ++f) tsum = fma(wJ * V[f], r[f], tsum);
+        }
+        if (p.mode == 0) {
+#pragma unroll
+            for (int f = 0; f < 5; ++f) p.rhs[f * p.q_stride + gq] = r[f];
+        } else {
+            double Un[5];
+#pragma unroll
+            for (int f = 0; f < 5; ++f) {
+                const double rs = fma(p.rk_a, p.res[f * p.q_stride + gq], p.dt * r[f]);
+                p.res[f * p.q_stride + gq] = rs;
+                Un[f] = fma(p.rk_b, rs, U[f]);
+                p.Qout[f * p.q_stride + gq] = Un[f];
+            }
+            // ---- F (volume part): entropy variables of the new state -> shared -------------------
+            Node Pn;
+            double rhoen, V[5];
+            vol_prim(Un, p.gamma, Pn, rhoen, bad);
+            const double lr = log(Pn.rho), lb = log(Pn.beta);
+            p.Lnext[gq] = lr;
+            p.Lnext[p.q_stride + gq] = lb;
+            entropy_vars(Un, rhoen, lr, lb, p.gamma, V);
+            double* sV = sX + eb * 5 * Nq;   // element-contiguous V blocks: index (eb*5+f)*Nq + i
+#pragma unroll
+            for (int f = 0; f < 5; ++f) sV[f * Nq + i] = V[f];
+        }
+    }
+    if (p.mode == 1) {
+        __syncthreads();
+        write_traces<n>(p, sX, s_lm, s_lp, e0, nb);
+    }
+    if (p.want_rhstest) {
+        __shared__ double red[32];
+        for (int o = 16; o > 0; o >>= 1) tsum += __shfl_down_sync(0xffffffffu, tsum, o);
+        if ((tid & 31) == 0) red[tid >> 5] = tsum;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int wv = 0; wv < (int)(blockDim.x + 31) / 32; ++wv) t += red[wv];
+            p.partial[blockIdx.x] = t;
+        }
+    }
+    if (bad) atomicOr(p.bad, 1);
+}
+
+}  // namespace esdg

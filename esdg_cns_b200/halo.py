@@ -27,6 +27,9 @@ class SlabHalo:
 
     def exchange(self):
         """self.send (filled by the caller) -> self.recv."""
+        return self.finish(self.start())
+
+    def start(self):
         dist = self.dist
         self._s_lo.copy_(self.send[:, :self.n_lo])
         self._s_up.copy_(self.send[:, self.n_lo:])
@@ -41,9 +44,11 @@ class SlabHalo:
             ops.append(dist.P2POp(dist.irecv, self._r_up, self.upper))
         if self.lower is not None:
             ops.append(dist.P2POp(dist.irecv, self._r_lo, self.lower))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    def finish(self, works):
+        for w in works:
+            w.wait()
         h = self.n_halo // 2
         self.recv[:, :h].copy_(self._r_lo)
         self.recv[:, h:].copy_(self._r_up)
@@ -51,17 +56,40 @@ class SlabHalo:
 
 
 class GpuSlabStepper:
-    """LSRK45 on a z-slab: traces -> pack -> exchange -> fused stage update, per stage."""
+    """LSRK45 on a z-slab.  Per stage: boundary-layer elements first, their new traces are packed and
+    the NCCL exchange starts while the interior elements are still being updated; the received halo
+    is unpacked before the next stage."""
 
-    def __init__(self, solver, md, nf, dist, torch, device):
+    def __init__(self, solver, md, dist, torch, device, overlap=True):
         self.s = solver
-        self.halo = SlabHalo(md, nf, dist, torch, device)
+        self.halo = SlabHalo(md, solver.trace_planes(), dist, torch, device)
         solver.set_send_list(self.halo.send_list)
+        self.overlap = overlap
+        self.fresh = True          # state uploaded, traces not yet computed / exchanged
+
+    def _exchange(self):
+        self.s.pack_send(self.halo.send.data_ptr())
+        self.halo.exchange()
+        self.s.unpack_halo(self.halo.recv.data_ptr())
+
+    def mark_fresh(self):
+        self.fresh = True
 
     def step(self, dt, want_rhstest=False):
+        s = self.s
+        if self.fresh:
+            s.compute_traces()
+            self._exchange()
+            self.fresh = False
         for k in range(5):
-            self.s.compute_traces()
-            self.s.pack_send(self.halo.send.data_ptr())
-            self.halo.exchange()
-            self.s.unpack_halo(self.halo.recv.data_ptr())
-            self.s.stage_update(k, dt, want_rhstest and k == 4)
+            want = want_rhstest and k == 4
+            if self.overlap:
+                s.stage_update(k, dt, want, s.PART_BOUNDARY)
+                s.pack_send(self.halo.send.data_ptr())
+                works = self.halo.start()
+                s.stage_update(k, dt, want, s.PART_INTERIOR)
+                self.halo.finish(works)
+                s.unpack_halo(self.halo.recv.data_ptr())
+            else:
+                s.stage_update(k, dt, want, s.PART_ALL)
+                self._exchange()

@@ -129,9 +129,17 @@ int esdg_pack_send(esdg_ctx* ctx, void* send_dev /* Nfields*n doubles, device */
 int esdg_halo_ptr(esdg_ctx* ctx, void** halo_dev, int64_t* field_stride);
 /* copy a received buffer of Nfields x n_halo doubles (device) into the halo tail */
 int esdg_unpack_halo(esdg_ctx* ctx, const void* recv_dev);
-/* One LSRK stage whose trace exchange is done by the caller between the two calls:
- *   esdg_compute_traces ; pack ; <exchange> ; esdg_stage_update(stage) */
-int esdg_stage_update(esdg_ctx* ctx, int stage /*0..4*/, double dt, int compute_rhstest);
+/* Distributed LSRK stepping, driven by the caller:
+ *   after upload:  esdg_compute_traces ; esdg_pack_send ; <exchange> ; esdg_unpack_halo
+ *   every stage :  esdg_stage_update(stage) ; esdg_pack_send ; <exchange> ; esdg_unpack_halo */
+/* part: 0 = all local elements; 1 = only the elements whose traces are in the send list (launch
+ * first, then pack + start the exchange); 2 = the remaining interior elements (overlaps the exchange).
+ * After the call(s) the traces of the NEW state are valid locally: pack / exchange / unpack them
+ * before the next stage. */
+int esdg_stage_update(esdg_ctx* ctx, int stage /*0..4*/, double dt, int compute_rhstest, int part);
+/* number of double planes per trace point in the pack/unpack buffers (5 = Uf of the generic path,
+ * 7 = rho,u,v,w,beta,log rho,log beta of the tensor-product hex path) */
+int esdg_trace_planes(esdg_ctx* ctx);
 int esdg_read_rhstest(esdg_ctx* ctx, double* rhstest);
 
 /* ---- introspection ---------------------------------------------------------- */

@@ -109,3 +109,81 @@ def test_domain_error_on_negative_density():
     Q = [np.full((8, 8), v) for v in (-1.0, .3, -.2, .1, 2.5)]
     with pytest.raises(_lib.DomainError):
         api.rhs(Q, pmd, pops)
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-product hex path (kernels_hex.cuh): fused stage kernel, symmetric pair evaluation,
+# traces produced in the epilogue.  The generic table-driven kernels are forced with
+# ESDG_FORCE_GENERIC=1 so both paths stay covered.
+@pytest.mark.parametrize("force_generic", [False, True])
+@pytest.mark.parametrize("N,K1D", [(1, 3), (2, 3), (3, 3), (4, 2)])
+def test_hex_lsrk_two_steps_match_oracle(N, K1D, force_generic, monkeypatch):
+    from oracle import solvers as SV
+    from esdg_cns_b200 import api, setup_dg as SD
+    if force_generic:
+        monkeypatch.setenv("ESDG_FORCE_GENERIC", "1")
+    rd, md, ops, Q = _hex_case(N, K1D, "tgv")
+    dt = 1e-3
+    Qo = [q.copy() for q in Q]
+    res = [np.zeros_like(q) for q in Q]
+    for _ in range(2):
+        Qo, res, rto = SV.lsrk45_step(Qo, res, dt, lambda q, t: SV.rhs_collocated(q, md, ops, rd, .25, t))
+    prd, pops = SD.reference_hex(N)
+    pmd = SD.uniform_hex_mesh_md(prd, (K1D,) * 3, domain=((-np.pi, np.pi),) * 3)   # exact-zero metric: DIAG kernel
+    s = api.Solver(pmd, pops)
+    s.upload(Q)
+    rtg = s.lsrk45(dt, 2, want_rhstest=True)
+    Qg = s.download()
+    err = max(np.abs(a - b).max() / max(1.0, np.abs(b).max()) for a, b in zip(Qg, Qo))
+    print(f"hex N={N} lsrk x2 generic={force_generic}: state relerr {err:.2e}, rhstest {rtg:.3e} vs {rto:.3e}")
+    assert err < 1e-12          # dt * (rhs error at the noise floor ~1e-10) stays far below 1e-12
+    assert abs(rtg - rto) < 1e-10 * max(1.0, abs(rto))
+    # a second call continues from the resident state / traces
+    Qo, res, _ = SV.lsrk45_step(Qo, res, dt, lambda q, t: SV.rhs_collocated(q, md, ops, rd, .25, t))
+    s.lsrk45(dt, 1)
+    Qg = s.download()
+    assert max(np.abs(a - b).max() / max(1.0, np.abs(b).max()) for a, b in zip(Qg, Qo)) < 1e-12
+
+
+def test_hex_general_affine_metric():
+    """Sheared (non axis-aligned) affine hexes: exercises the non-DIAG kernel + general normals."""
+    from oracle import solvers as SV, physics as P, setupdg as S, mesh as M
+    from esdg_cns_b200 import api
+    N, K1D = 2, 3
+    VX, VY, VZ, EToV = M.uniform_hex_mesh(K1D, K1D, K1D)
+    X = VX + .15 * VY + .1 * VZ          # constant-Jacobian shear keeps every element affine
+    Y = VY + .2 * VZ
+    Z = VZ
+    rd = S.init_reference_hex(N)
+    md = S.init_mesh((X, Y, Z), EToV, rd)
+    ops = SV.build_sbp_ops(rd)
+    SV.interp_geofacs(md, rd, ops)
+    # periodic in the sheared frame is not a straight box: keep mapP=mapM on the boundary (free boundary)
+    rng = np.random.default_rng(3)
+    rho = 1 + .2 * rng.random(md.xq.shape)
+    u, v, w = (.3 * rng.random(rho.shape) for _ in range(3))
+    p = 1 + .2 * rng.random(rho.shape)
+    Q = list(P.primitive_to_conservative(rho, (u, v, w), p))
+    ref, rt_ref = SV.rhs_collocated(Q, md, ops, rd, .25, True)
+    s = api.Solver(md, ops)
+    out, rt = s.rhs(Q, True)
+    err = _relerr(out, ref)
+    print(f"sheared hex: relerr {err:.2e}")
+    assert err < parity_tol(lambda: SV.rhs_collocated(Q, md, ops, rd, .25, False)[0], ref)
+    assert abs(rt - rt_ref) < 1e-11 * max(1.0, abs(rt_ref))
+
+
+def test_hex_path_is_selected():
+    """The tensor-product kernels (not the generic fallback) must be what the bench config runs."""
+    from esdg_cns_b200 import api, setup_dg as SD
+    prd, pops = SD.reference_hex(4)
+    pmd = SD.uniform_hex_mesh_md(prd, (2, 2, 2))
+    s = api.Solver(pmd, pops)
+    s.enable_timing(True)
+    Q = [np.full((125, 8), v) for v in (1.0, .3, -.2, .1, 2.5)]
+    s.upload(Q)
+    s.lsrk45(1e-3, 1)
+    s.sync()
+    assert s.kernel_time_ms("hex_stage")[1] == 5
+    assert s.kernel_time_ms("generic_rhs")[1] == 0
+    assert s.trace_planes() == 7
