@@ -61,7 +61,7 @@ struct HexDims {
     static constexpr int XV = KH * 5 * Nq, XF = 2 * 5 * nfp * n;
     static constexpr int XSZ = (XV + XF) > 5 * Nq ? (XV + XF) : 5 * Nq;
     static constexpr int TAB = n * n + 5 * n;
-    static constexpr int SMEM_DOUBLES = EB * (7 * Nh + XSZ + 5 * Nfq) + TAB;
+    static constexpr int SMEM_DOUBLES = EB * (7 * Nh + XSZ + 5 * Nfq + 7 * Nfq) + TAB;
 };
 
 struct Node {
@@ -77,6 +77,14 @@ __device__ __forceinline__ double fast_rcp(double x) {
     y = fma(y, e, y);
     return y;
 }
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* q) { asm volatile("prefetch.global.L2 [%0];" ::"l"(q)); }
 
 __device__ __forceinline__ Node ld_node(const double* W, int Nh, int idx) {
     Node a;
@@ -261,7 +269,8 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
     double* sW = sm;                              // [EB][7][Nh]
     double* sX = sW + D::EB * 7 * Nh;             // [EB][XSZ]   (XV | XF), later V[5][Nq]
     double* sFL = sX + D::EB * D::XSZ;            // [EB][5][Nfq]
-    double* s_T = sFL + D::EB * 5 * Nfq;          // [n][n]
+    double* sP = sFL + D::EB * 5 * Nfq;           // [EB][7][Nfq] exterior traces
+    double* s_T = sP + D::EB * 7 * Nfq;           // [n][n]
     double* s_lm = s_T + n * n;
     double* s_lp = s_lm + n;
     double* s_lmw = s_lp + n;                     // lm[a]/w[a]
@@ -287,16 +296,55 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
     const double c_igm = 1.0 / (2.0 * (p.gamma - 1.0));
     bool bad = false;
 
-    // ---- A: volume nodes + own traces -> shared -----------------------------------------------
+    // ---- prologue: every global read of this element batch is put in flight before any math ----
+    // (1) exterior-trace indices, (2) own traces -> sW face rows and (3) exterior traces -> sP with
+    // cp.async (no register staging), (4) L2 prefetch of the LSRK register read in phase E.
+    constexpr int MAXIT = (D::EB * Nfq + D::THREADS - 1) / D::THREADS;
+    int ipv[MAXIT];
+#pragma unroll
+    for (int r = 0; r < MAXIT; ++r) {
+        const int it = tid + r * D::THREADS;
+        ipv[r] = it < nb * Nfq ? p.mapP[e0 * Nfq + it] : -1;
+    }
     double U[5] = {1, 0, 0, 0, 1}, rhoe = 1.0;
     Node Pi;
-    double* W = sW + eb * 7 * Nh;
+    Pi.lr = Pi.lb = 0.0;
     if (vol) {
 #pragma unroll
         for (int f = 0; f < 5; ++f) U[f] = p.Q[f * p.q_stride + gq];
-        vol_prim(U, p.gamma, Pi, rhoe, bad);
         Pi.lr = p.Lcur[gq];
         Pi.lb = p.Lcur[p.q_stride + gq];
+        if (p.mode == 1) {
+#pragma unroll
+            for (int f = 0; f < 5; ++f) prefetch_l2(p.res + f * p.q_stride + gq);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < MAXIT; ++r) {
+        const int it = tid + r * D::THREADS;
+        if (it < nb * Nfq) {
+            const int b2 = it / Nfq, k = it - b2 * Nfq;
+#pragma unroll
+            for (int q = 0; q < HEX_TP; ++q)
+                cp_async8(sW + (b2 * 7 + q) * Nh + Nq + k, p.Tcur + q * p.t_stride + e0 * Nfq + it);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < MAXIT; ++r) {
+        const int it = tid + r * D::THREADS;
+        if (it < nb * Nfq) {
+            const int b2 = it / Nfq, k = it - b2 * Nfq;
+#pragma unroll
+            for (int q = 0; q < HEX_TP; ++q)
+                cp_async8(sP + (b2 * 7 + q) * Nfq + k, p.Tcur + q * p.t_stride + ipv[r]);
+        }
+    }
+    cp_async_commit();
+
+    // ---- A: volume nodes -> shared --------------------------------------------------------------
+    double* W = sW + eb * 7 * Nh;
+    if (vol) {
+        vol_prim(U, p.gamma, Pi, rhoe, bad);
         W[i] = Pi.rho;
         W[Nh + i] = Pi.u[0];
         W[2 * Nh + i] = Pi.u[1];
@@ -305,13 +353,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
         W[5 * Nh + i] = Pi.lr;
         W[6 * Nh + i] = Pi.lb;
     }
-    for (int q = 0; q < HEX_TP; ++q) {
-        const double* src = p.Tcur + q * p.t_stride + e0 * Nfq;
-        for (int it = tid; it < nb * Nfq; it += blockDim.x) {
-            const int b2 = it / Nfq, k = it - b2 * Nfq;
-            sW[(b2 * 7 + q) * Nh + Nq + k] = src[it];
-        }
-    }
+    cp_async_wait_all();
     __syncthreads();
 
     // ---- B: surface flux at face points (dg3D_euler_hex.jl:182-197) ----------------------------
@@ -322,15 +364,8 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
         const double* gf = p.geo + ee * p.geo_stride + 10 + face * 4;
         const double nJ[3] = {gf[0], gf[1], gf[2]};
         const double sJ = gf[3];
-        const int ip = p.mapP[ee * Nfq + k];
-        Node M = ld_node(sW + b2 * 7 * Nh, Nh, Nq + k), P;
-        P.rho = p.Tcur[ip];
-        P.u[0] = p.Tcur[p.t_stride + ip];
-        P.u[1] = p.Tcur[2 * p.t_stride + ip];
-        P.u[2] = p.Tcur[3 * p.t_stride + ip];
-        P.beta = p.Tcur[4 * p.t_stride + ip];
-        P.lr = p.Tcur[5 * p.t_stride + ip];
-        P.lb = p.Tcur[6 * p.t_stride + ip];
+        const Node M = ld_node(sW + b2 * 7 * Nh, Nh, Nq + k);
+        const Node P = ld_node(sP + b2 * 7 * Nfq, Nfq, k);
         double F[5];
         pair_flux<false, 0>(M, P, nJ, c_igm, F);
         if (p.lf_scale != 0.0) {
