@@ -92,6 +92,8 @@ void fill_hex_params(esdg_ctx* ctx, HexParams& p) {
     p.geo_stride = ctx->geo_stride;
     p.gamma = d.gamma;
     p.lf_scale = d.lf_scale;
+    p.lg1 = std::log(d.gamma - 1.0);
+    p.l2g1 = std::log(2.0 * (d.gamma - 1.0));
     p.rk_a = p.rk_b = p.dt = 0.0;
     p.mode = 0;
     p.want_rhstest = 0;

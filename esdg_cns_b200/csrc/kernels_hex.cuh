@@ -43,7 +43,7 @@ struct HexParams {
     const int* mapP;
     const double* geo;
     int geo_stride;
-    double gamma, lf_scale;
+    double gamma, lf_scale, lg1, l2g1;   // lg1 = log(gamma-1), l2g1 = log(2(gamma-1))
     double rk_a, rk_b, dt;
     int mode;                // 0: write rhs ; 1: fused LSRK stage + traces of the new state
     int want_rhstest;
@@ -61,7 +61,7 @@ struct HexDims {
     static constexpr int XV = KH * 5 * Nq, XF = 2 * 5 * nfp * n;
     static constexpr int XSZ = (XV + XF) > 5 * Nq ? (XV + XF) : 5 * Nq;
     static constexpr int TAB = n * n + 5 * n;
-    static constexpr int SMEM_DOUBLES = EB * (7 * Nh + XSZ + 5 * Nfq + 7 * Nfq) + TAB;
+    static constexpr int SMEM_DOUBLES = EB * (7 * Nh + XSZ + 5 * Nfq + 7 * Nfq + 5 * Nq) + TAB;
 };
 
 struct Node {
@@ -174,14 +174,14 @@ __device__ __forceinline__ void entropy_vars(const double* U, double rhoe, doubl
 // entropy variables: rhoeV = exp((log(g-1) - g log(-vE) - s)/(g-1)), rho = rhoeV(-vE),
 // u = vU/(-vE), beta = -vE/(2(g-1)) (identically rho/(2p)), log rho and log beta follow without
 // further transcendental calls.
-__device__ __forceinline__ void trace_from_entropy(const double* V, double gamma, double* Tv) {
+__device__ __forceinline__ void trace_from_entropy(const double* V, double gamma, double lg1, double l2g1, double* Tv) {
     const double nvE = -V[4];
     const double inv = fast_rcp(nvE);
     const double v2 = fma(V[1], V[1], fma(V[2], V[2], V[3] * V[3]));
     const double s = gamma - V[0] - .5 * v2 * inv;
     const double lv = log(nvE);
     const double ig = 1.0 / (gamma - 1.0);
-    const double lrhoe = (log(gamma - 1.0) - gamma * lv - s) * ig;
+    const double lrhoe = (lg1 - gamma * lv - s) * ig;   // lg1 = log(gamma-1), host-computed
     const double rhoeV = exp(lrhoe);
     Tv[0] = rhoeV * nvE;
     Tv[1] = V[1] * inv;
@@ -189,7 +189,7 @@ __device__ __forceinline__ void trace_from_entropy(const double* V, double gamma
     Tv[3] = V[3] * inv;
     Tv[4] = .5 * nvE * ig;
     Tv[5] = lrhoe + lv;
-    Tv[6] = lv - log(2.0 * (gamma - 1.0));
+    Tv[6] = lv - l2g1;                                   // l2g1 = log(2(gamma-1))
 }
 
 // face point (face = 2*d + side, m) -> first volume node of its line and the line stride
@@ -221,7 +221,7 @@ __device__ __forceinline__ void write_traces(const HexParams& p, const double* s
             for (int f = 0; f < 5; ++f) V[f] = fma(la, v[f * D::Nq + a * stride], V[f]);
         }
         double Tv[HEX_TP];
-        trace_from_entropy(V, p.gamma, Tv);
+        trace_from_entropy(V, p.gamma, p.lg1, p.l2g1, Tv);
         const long long g = (e0 + eb) * D::Nfq + k;
 #pragma unroll
         for (int q = 0; q < HEX_TP; ++q) p.Tnext[q * p.t_stride + g] = Tv[q];
@@ -270,7 +270,8 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
     double* sX = sW + D::EB * 7 * Nh;             // [EB][XSZ]   (XV | XF), later V[5][Nq]
     double* sFL = sX + D::EB * D::XSZ;            // [EB][5][Nfq]
     double* sP = sFL + D::EB * 5 * Nfq;           // [EB][7][Nfq] exterior traces
-    double* s_T = sP + D::EB * 7 * Nfq;           // [n][n]
+    double* sR = sP + D::EB * 7 * Nfq;            // [EB][5][Nq] LSRK register (mode 1)
+    double* s_T = sR + D::EB * 5 * Nq;            // [n][n]
     double* s_lm = s_T + n * n;
     double* s_lp = s_lm + n;
     double* s_lmw = s_lp + n;                     // lm[a]/w[a]
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
         Pi.lb = p.Lcur[p.q_stride + gq];
         if (p.mode == 1) {
 #pragma unroll
-            for (int f = 0; f < 5; ++f) prefetch_l2(p.res + f * p.q_stride + gq);
+            for (int f = 0; f < 5; ++f) cp_async8(sR + (eb * 5 + f) * Nq + i, p.res + f * p.q_stride + gq);
         }
     }
 #pragma unroll
@@ -513,7 +514,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
             double Un[5];
 #pragma unroll
             for (int f = 0; f < 5; ++f) {
-                const double rs = fma(p.rk_a, p.res[f * p.q_stride + gq], p.dt * r[f]);
+                const double rs = fma(p.rk_a, sR[(eb * 5 + f) * Nq + i], p.dt * r[f]);
                 p.res[f * p.q_stride + gq] = rs;
                 Un[f] = fma(p.rk_b, rs, U[f]);
                 p.Qout[f * p.q_stride + gq] = Un[f];
