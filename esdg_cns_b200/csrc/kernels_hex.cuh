@@ -204,9 +204,9 @@ __device__ __forceinline__ void face_line(int d, int m, int& base, int& stride) 
 // Phase F: project entropy variables (shared V[5][Nq] per element) to the faces, write 7-plane traces
 template <int n>
 __device__ __forceinline__ void write_traces(const HexParams& p, const double* sV, const double* s_lm, const double* s_lp,
-                                             long long e0, int nb) {
+                                             long long e0, int nb, int ftid) {
     using D = HexDims<n>;
-    for (int it = threadIdx.x; it < nb * D::Nfq; it += blockDim.x) {
+    for (int it = ftid; it < nb * D::Nfq; it += blockDim.x) {
         const int eb = it / D::Nfq, k = it - eb * D::Nfq;
         const int face = k / D::nfp, m = k - face * D::nfp;
         int base, stride;
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_traces(const __grid
         for (int f = 0; f < 5; ++f) sV[(eb * 5 + f) * D::Nq + i] = V[f];
     }
     __syncthreads();
-    write_traces<n>(p, sV, s_lm, s_lp, e0, nb);
+    write_traces<n>(p, sV, s_lm, s_lp, e0, nb, threadIdx.x);
     if (bad) atomicOr(p.bad, 1);
 }
 
@@ -278,6 +278,10 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
     double* s_lpw = s_lmw + n;
     double* s_w = s_lpw + n;
     const int tid = threadIdx.x;
+    // face-item loops use a thread id rotated by a whole number of warps per CTA: the leftover pass
+    // (Nfq is not a multiple of the block size) then lands on a different SM sub-partition for each
+    // co-resident CTA instead of always on warp 0
+    const int ftid = (tid + 32 * (int)(blockIdx.x % (D::THREADS / 32))) % D::THREADS;
     if (tid < n * n) s_T[tid] = p.T[tid];
     if (tid < n) {
         s_lm[tid] = p.lm[tid];
@@ -304,7 +308,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
     int ipv[MAXIT];
 #pragma unroll
     for (int r = 0; r < MAXIT; ++r) {
-        const int it = tid + r * D::THREADS;
+        const int it = ftid + r * D::THREADS;
         ipv[r] = it < nb * Nfq ? p.mapP[e0 * Nfq + it] : -1;
     }
     double U[5] = {1, 0, 0, 0, 1}, rhoe = 1.0;
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
     }
 #pragma unroll
     for (int r = 0; r < MAXIT; ++r) {
-        const int it = tid + r * D::THREADS;
+        const int it = ftid + r * D::THREADS;
         if (it < nb * Nfq) {
             const int b2 = it / Nfq, k = it - b2 * Nfq;
 #pragma unroll
@@ -332,7 +336,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
     }
 #pragma unroll
     for (int r = 0; r < MAXIT; ++r) {
-        const int it = tid + r * D::THREADS;
+        const int it = ftid + r * D::THREADS;
         if (it < nb * Nfq) {
             const int b2 = it / Nfq, k = it - b2 * Nfq;
 #pragma unroll
@@ -358,7 +362,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
     __syncthreads();
 
     // ---- B: surface flux at face points (dg3D_euler_hex.jl:182-197) ----------------------------
-    for (int it = tid; it < nb * Nfq; it += blockDim.x) {
+    for (int it = ftid; it < nb * Nfq; it += blockDim.x) {
         const int b2 = it / Nfq, k = it - b2 * Nfq;
         const long long ee = e0 + b2;
         const int face = k / nfp;
@@ -462,7 +466,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
             }
         }
         // face nodes of this direction: H = -nrJ * sum_a l[a] F(a) + flux*
-        for (int it = tid; it < nb * 2 * nfp; it += blockDim.x) {
+        for (int it = ftid; it < nb * 2 * nfp; it += blockDim.x) {
             const int b2 = it / (2 * nfp), r = it - b2 * 2 * nfp;
             const int side = r / nfp, mm = r - side * nfp;
             const double* xf = sX + b2 * D::XSZ + D::XV;
@@ -534,7 +538,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
     }
     if (p.mode == 1) {
         __syncthreads();
-        write_traces<n>(p, sX, s_lm, s_lp, e0, nb);
+        write_traces<n>(p, sX, s_lm, s_lp, e0, nb, ftid);
     }
     if (p.want_rhstest) {
         __shared__ double red[32];
