@@ -1,0 +1,30 @@
+"""Multi-GPU path: z-slab partition + NCCL halo exchange must reproduce the single-GPU result."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("overlap,generic,N", [(1, 0, 2), (0, 0, 3), (1, 0, 4), (1, 1, 2)])
+def test_two_gpu_slabs_match_single_gpu(overlap, generic, N):
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(29530 + 3 * N + overlap + 2 * generic),
+           os.path.join(ROOT, "tests", "dist_check.py"), "--overlap", str(overlap), "--generic", str(generic),
+           "--N", str(N), "--K", "4", "3", "6"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0
