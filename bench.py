@@ -47,6 +47,27 @@ def alg_bytes_per_element_stage(N, nf=5):
     return 8 * nf * (5 * Ns + 2 * Nfq)
 
 
+def alg_flops_per_element_stage(N):
+    """SURVEY 8(d) F_alg for collocated hexes (FMA = 2 flops; unordered pairs once; hand count +-15%)."""
+    n = N + 1
+    Ns, Nfq, Nh, d, nf = n ** 3, 6 * n * n, n ** 3 + 6 * n * n, 3, 5
+    P_sym = 3 * n * n * (n * (n - 1) // 2) + Nfq * n
+    nnz_Ef, nnz_Ph, nnz_L = Nfq * n, Ns * (1 + 2 * d), Ns * 2 * d
+    return (P_sym * 106 + Nfq * 114 + 2 * nf * (nnz_Ef + nnz_Ph + nnz_L) + Ns * (3 * d + 10) + Nfq * (3 * d + 14)
+            + Nh * (3 * d + 5) + 6 * Ns * nf)
+
+
+def measured_traffic(kernel, K):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            t = json.load(fh).get(kernel)
+        if t and t.get("elements") == K:
+            return t["dram_bytes_per_launch"]
+    return None
+
+
 def tgv_dt(N, K1D_global):
     CN = (N + 1) * (N + 2) * 3 / 2            # dg3D_euler_hex.jl:115-117
     return CFL * 2 / (CN * K1D_global)
@@ -258,8 +279,16 @@ def run_ours(args):
         dom_ms, dom_n = ktimes[dom_name]
         B_alg = alg_bytes_per_element_stage(N)
         share = {"hex_stage": 1.0, "generic_rhs": (4 * Ns + 6 * (N + 1) ** 2) / (5 * Ns + 12 * (N + 1) ** 2)}.get(dom_name, 1.0)
-        per_launch_s = dom_ms * 1e-3 / max(dom_n, 1)
+        # one "launch" of the roofline = the launches that cover all K local elements once (1 on a single GPU;
+        # boundary layers + interior when the stage is split for halo overlap)
+        per_launch_s = dom_ms * 1e-3 / (args.steps * 5)
         achieved = B_alg * share * K / per_launch_s / 1e9
+        from esdg_cns_b200 import _lib
+        import ctypes
+        pk = ctypes.c_double(0.0)
+        _lib.load().esdg_measure_fp64_peak(local_rank, ctypes.byref(pk))
+        F_alg = alg_flops_per_element_stage(N)
+        fp64_tf = F_alg * K / per_launch_s / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -269,13 +298,17 @@ def run_ours(args):
                        "l2_policy": f"state {dof * 8 * 2 / 1e9:.2f} GB/GPU streamed every stage (>> 126 MB L2), no flush needed",
                        "parallelism": f"z-slab x{world}", "finite": finite},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": dom_name, "kernel_ms_per_launch": per_launch_s * 1e3,
+                         "traffic": measured_traffic(dom_name, K), "kernel": dom_name, "kernel_ms_per_launch": per_launch_s * 1e3,
                          "kernel_launches_timed": dom_n, "kernel_share_of_step": dom_ms / ms,
                          "alg_bytes_per_element_stage": B_alg * share, "peak_source": peak_src,
                          "ns_per_element_stage": 1e9 * ms * 1e-3 / (args.steps * 5 * K)},
             "e2e": {"value": dof * world * 5 * e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": dof * 8, "d2h_bytes_per_step": dof * 8,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps},
+            "fp64": {"achieved_tflops": fp64_tf, "peak_tflops_measured_dfma": pk.value, "peak_tflops_nominal": 37.2,
+                     "frac_of_measured": fp64_tf / pk.value if pk.value else None,
+                     "alg_flops_per_element_stage": F_alg,
+                     "note": "the stage kernel is FP64-pipe/latency bound, not HBM bound (profiles/)"},
             "gpu_launches": launches, "clocks": clocks,
             "kernels_ms": {k: {"total_ms": v[0], "launches": v[1]} for k, v in ktimes.items() if v[1]},
         }

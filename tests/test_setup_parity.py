@@ -1,0 +1,58 @@
+"""esdg_cns_b200.setup_dg (tensor-product, analytic connectivity) must reproduce the oracle's literal
+restatement of SetupDG.jl / connect_mesh / build_node_maps / geometric_factors array by array."""
+import numpy as np
+import pytest
+
+from esdg_cns_b200 import setup_dg as SD
+from oracle import solvers as SV
+
+
+def _close(a, b, tol=1e-13):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.abs(a - b).max() <= tol * max(1.0, np.abs(b).max())
+
+
+@pytest.mark.parametrize("N,Kx,Ky", [(1, 3, 2), (3, 5, 4)])
+def test_quad_setup_matches_oracle(N, Kx, Ky):
+    rd, md, ops, _ = SV.setup_quad_vortex(N, Kx, Ky)
+    prd, pops = SD.reference_quad(N)
+    pmd = SD.uniform_quad_mesh_md(prd, Kx, Ky, domain=((0, 15), (-5, 5)))
+    for n in ("rq", "sq", "wq", "wf", "rf", "sf", "nrJ", "nsJ"):
+        assert _close(getattr(prd, n), getattr(rd, n)), n
+    assert _close(pops.Ef, ops.Ef) and _close(pops.Ph, ops.Ph) and _close(pops.Lf, ops.Lf)
+    for a, b in zip(pops.Qskew, ops.Qskew):
+        assert _close(a, b)
+    assert _close(pmd.xq, md.xq) and _close(pmd.yq, md.yq)
+    nfp = N + 1
+    for n in ("rxJ", "sxJ", "ryJ", "syJ", "J"):
+        assert _close(np.broadcast_to(getattr(pmd, n), getattr(md, n).shape), getattr(md, n)), n
+    for n in ("nxJ", "nyJ", "sJ"):
+        assert _close(np.repeat(getattr(pmd, n), nfp, axis=0), getattr(md, n)), n
+    assert np.array_equal(pmd.mapP, md.mapP)
+
+
+@pytest.mark.parametrize("N,K", [(1, (2, 3, 2)), (2, (3, 2, 4)), (3, (2, 2, 2))])
+def test_hex_setup_matches_oracle(N, K):
+    rd, md, ops = SV.setup_hex(N, K, scale=(1.0, 2.0, .5), shift=(.1, .2, .3))
+    prd, pops = SD.reference_hex(N)
+    pmd = SD.uniform_hex_mesh_md(prd, K, domain=((-.9, 1.1), (-1.8, 2.2), (-.2, .8)))
+    for n in ("rq", "sq", "tq", "wq", "wf", "rf", "sf", "tf", "nrJ", "nsJ", "ntJ"):
+        assert _close(getattr(prd, n), getattr(rd, n)), n
+    assert _close(pops.Ef, ops.Ef) and _close(pops.Ph, ops.Ph) and _close(pops.Lf, ops.Lf)
+    for a, b in zip(pops.Qskew, ops.Qskew):
+        assert _close(a, b)
+    x, y, z = SD.hex_node_coords(prd, pmd)
+    assert _close(x, md.xq) and _close(y, md.yq) and _close(z, md.zq)
+    for n in ("rxJ", "sxJ", "txJ", "ryJ", "syJ", "tyJ", "rzJ", "szJ", "tzJ", "J"):
+        assert _close(np.broadcast_to(getattr(pmd, n), getattr(md, n).shape), getattr(md, n)), n
+    nfp = (N + 1) ** 2
+    for n in ("nxJ", "nyJ", "nzJ", "sJ"):
+        assert _close(np.repeat(getattr(pmd, n), nfp, axis=0), getattr(md, n)), n
+    assert np.array_equal(pmd.mapP, md.mapP)
+
+
+def test_nonperiodic_boundary_maps_to_itself():
+    prd, _ = SD.reference_hex(1)
+    md = SD.uniform_hex_mesh_md(prd, (2, 2, 2), periodic=(False, True, True))
+    self_idx = np.arange(md.mapP.size).reshape(md.mapP.shape, order="F")
+    assert (md.mapP == self_idx).sum() == 2 * 4 * 4    # two x-boundaries, 4 faces each, 4 points per face
