@@ -403,30 +403,45 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
     }
 
     // ---- C/D: flux differencing, one reference direction at a time ------------------------------
+    // The direction loop is rolled (3x smaller code: the unrolled kernel overflowed the instruction
+    // cache); velocity components, momentum accumulators, line coordinates and strides are kept in
+    // a frame ROTATED with the direction so that "component 0" is always the line direction.
     double acc[5] = {0, 0, 0, 0, 0};
     const double* G = p.geo + e * p.geo_stride;
     double* XVb = sX + eb * D::XSZ;
     double* XFb = XVb + D::XV;
-#pragma unroll
+    int x0 = xa, x1 = xb, x2 = xc;                 // rotated line coordinates: x0 runs along direction d
+    int s0 = 1, s1 = n, s2 = n * n;                // matching node strides
+    int m0 = xc + n * xb, m1 = xc + n * xa, m2 = xb + n * xa;   // on-face index of my line per direction
+#pragma unroll 1
     for (int d = 0; d < 3; ++d) {
-        const int xd = d == 0 ? xa : (d == 1 ? xb : xc);
-        const int sd = d == 0 ? 1 : (d == 1 ? n : n * n);
-        const int m = d == 0 ? (xc + n * xb) : (d == 1 ? (xc + n * xa) : (xb + n * xa));   // on-face index of my line
+        const int c1 = d == 2 ? 0 : d + 1, c2 = c1 == 2 ? 0 : c1 + 1;   // physical components in rotated order d,c1,c2
+        const int pl0 = (1 + d) * Nh, pl1 = (1 + c1) * Nh, pl2 = (1 + c2) * Nh;
         if (vol) {
-            const double g[3] = {G[d], G[3 + d], G[6 + d]};   // (r_x, r_y, r_z) J  of direction d
+            // (r_x, r_y, r_z) J of direction d, rotated
+            const double g[3] = {G[3 * d + d], G[3 * c1 + d], G[3 * c2 + d]};
+            auto ldn = [&](int idx) {
+                Node q;
+                q.rho = W[idx];
+                q.u[0] = W[pl0 + idx];
+                q.u[1] = W[pl1 + idx];
+                q.u[2] = W[pl2 + idx];
+                q.beta = W[4 * Nh + idx];
+                q.lr = W[5 * Nh + idx];
+                q.lb = W[6 * Nh + idx];
+                return q;
+            };
             // owned volume pairs (x, x+k mod n)
 #pragma unroll
             for (int k = 1; k <= KH; ++k) {
-                const bool own = !((n % 2 == 0) && (k == n / 2) && (xd >= n / 2));
-                int ap = xd + k;
+                const bool own = !((n % 2 == 0) && (k == n / 2) && (x0 >= n / 2));
+                int ap = x0 + k;
                 ap = ap >= n ? ap - n : ap;
                 if (own) {
-                    const Node Pj = ld_node(W, Nh, i + (ap - xd) * sd);
+                    const Node Pj = ldn(i + (ap - x0) * s0);
                     double F[5];
-                    if (d == 0) pair_flux<DIAG, 0>(Pi, Pj, g, c_igm, F);
-                    else if (d == 1) pair_flux<DIAG, 1>(Pi, Pj, g, c_igm, F);
-                    else pair_flux<DIAG, 2>(Pi, Pj, g, c_igm, F);
-                    const double t = s_T[xd * n + ap];
+                    pair_flux<DIAG, 0>(Pi, Pj, g, c_igm, F);
+                    const double t = s_T[x0 * n + ap];
 #pragma unroll
                     for (int f = 0; f < 5; ++f) {
                         acc[f] = fma(t, F[f], acc[f]);
@@ -437,16 +452,14 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
             // the two face partners of my line
 #pragma unroll
             for (int side = 0; side < 2; ++side) {
-                const Node Pf = ld_node(W, Nh, Nq + (2 * d + side) * nfp + m);
+                const Node Pf = ldn(Nq + (2 * d + side) * nfp + m0);
                 double F[5];
-                if (d == 0) pair_flux<DIAG, 0>(Pi, Pf, g, c_igm, F);
-                else if (d == 1) pair_flux<DIAG, 1>(Pi, Pf, g, c_igm, F);
-                else pair_flux<DIAG, 2>(Pi, Pf, g, c_igm, F);
-                const double t = side ? s_lpw[xd] : -s_lmw[xd];
+                pair_flux<DIAG, 0>(Pi, Pf, g, c_igm, F);
+                const double t = side ? s_lpw[x0] : -s_lmw[x0];
 #pragma unroll
                 for (int f = 0; f < 5; ++f) {
                     acc[f] = fma(t, F[f], acc[f]);
-                    XFb[((side * 5 + f) * nfp + m) * n + xd] = F[f];
+                    XFb[((side * 5 + f) * nfp + m0) * n + x0] = F[f];
                 }
             }
         }
@@ -454,34 +467,41 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
         if (vol) {
 #pragma unroll
             for (int k = 1; k <= KH; ++k) {
-                int am = xd - k;
+                int am = x0 - k;
                 am = am < 0 ? am + n : am;
                 const bool has = !((n % 2 == 0) && (k == n / 2) && (am >= n / 2));
                 if (has) {
-                    const double t = s_T[xd * n + am];
-                    const int j = i + (am - xd) * sd;
+                    const double t = s_T[x0 * n + am];
+                    const int j = i + (am - x0) * s0;
 #pragma unroll
                     for (int f = 0; f < 5; ++f) acc[f] = fma(t, XVb[((k - 1) * 5 + f) * Nq + j], acc[f]);
                 }
             }
         }
-        // face nodes of this direction: H = -nrJ * sum_a l[a] F(a) + flux*
-        for (int it = ftid; it < nb * 2 * nfp; it += blockDim.x) {
-            const int b2 = it / (2 * nfp), r = it - b2 * 2 * nfp;
-            const int side = r / nfp, mm = r - side * nfp;
-            const double* xf = sX + b2 * D::XSZ + D::XV;
+        // face nodes of this direction: H = -nrJ * sum_a l[a] F(a) + flux*, one (face point, field)
+        // per work item so that all warps share the reduction
+        for (int it = ftid; it < nb * 2 * 5 * nfp; it += blockDim.x) {
+            const int b2 = it / (2 * 5 * nfp), r = it - b2 * 2 * 5 * nfp;
+            const int sf = r / nfp, mm = r - sf * nfp;      // sf = side*5 + f (rotated field index)
+            const int side = sf / 5, fr = sf - side * 5;
+            const double* xf = sX + b2 * D::XSZ + D::XV + (sf * nfp + mm) * n;
             const double* l = side ? s_lp : s_lm;
-            const double sg = side ? -1.0 : 1.0;
+            double h = 0.0;
 #pragma unroll
-            for (int f = 0; f < 5; ++f) {
-                double h = 0.0;
-#pragma unroll
-                for (int a = 0; a < n; ++a) h = fma(l[a], xf[((side * 5 + f) * nfp + mm) * n + a], h);
-                double* dst = sFL + (b2 * 5 + f) * Nfq + (2 * d + side) * nfp + mm;
-                *dst = fma(sg, h, *dst);
-            }
+            for (int a = 0; a < n; ++a) h = fma(l[a], xf[a], h);
+            const int ff = (fr == 0 || fr == 4) ? fr : 1 + (fr == 1 ? d : (fr == 2 ? c1 : c2));   // un-rotate
+            double* dst = sFL + (b2 * 5 + ff) * Nfq + (2 * d + side) * nfp + mm;
+            *dst = side ? *dst - h : *dst + h;
         }
         __syncthreads();
+        // rotate the frame: direction d+1 becomes component 0
+        {
+            const double t = Pi.u[0]; Pi.u[0] = Pi.u[1]; Pi.u[1] = Pi.u[2]; Pi.u[2] = t;
+            const double ta = acc[1]; acc[1] = acc[2]; acc[2] = acc[3]; acc[3] = ta;
+            const int tx = x0; x0 = x1; x1 = x2; x2 = tx;
+            const int ts = s0; s0 = s1; s1 = s2; s2 = ts;
+            const int tm = m0; m0 = m1; m1 = m2; m2 = tm;
+        }
     }
 
     // ---- E: lift, scale, rhstest, LSRK stage ----------------------------------------------------
