@@ -61,7 +61,10 @@ struct HexDims {
     static constexpr int XV = KH * 5 * Nq, XF = 2 * 5 * nfp * n;
     static constexpr int XSZ = (XV + XF) > 5 * Nq ? (XV + XF) : 5 * Nq;
     static constexpr int TAB = n * n + 5 * n;
-    static constexpr int SMEM_DOUBLES = EB * (7 * Nh + XSZ + 5 * Nfq + 7 * Nfq + 5 * Nq) + TAB;
+#ifndef ESDG_HEX_STAGE_RES
+#define ESDG_HEX_STAGE_RES 1   // 1: LSRK register staged in shared memory by cp.async; 0: read in phase E (smaller footprint)
+#endif
+    static constexpr int SMEM_DOUBLES = EB * (7 * Nh + XSZ + 7 * Nfq + (ESDG_HEX_STAGE_RES ? 5 * Nq : 0)) + TAB;
 };
 
 struct Node {
@@ -262,16 +265,19 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_traces(const __grid
 }
 
 template <int n, bool DIAG>
-__global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_constant__ HexParams p) {
+#ifndef ESDG_HEX_MIN_CTAS
+#define ESDG_HEX_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(HexDims<n>::THREADS, ESDG_HEX_MIN_CTAS) k_hex_stage(const __grid_constant__ HexParams p) {
     using D = HexDims<n>;
     constexpr int Nq = D::Nq, nfp = D::nfp, Nfq = D::Nfq, Nh = D::Nh, KH = D::KH;
     extern __shared__ double sm[];
     double* sW = sm;                              // [EB][7][Nh]
     double* sX = sW + D::EB * 7 * Nh;             // [EB][XSZ]   (XV | XF), later V[5][Nq]
-    double* sFL = sX + D::EB * D::XSZ;            // [EB][5][Nfq]
-    double* sP = sFL + D::EB * 5 * Nfq;           // [EB][7][Nfq] exterior traces
+    double* sP = sX + D::EB * D::XSZ;             // [EB][7][Nfq] exterior traces ...
+    double* sFL = sP;                             // ... overwritten in place by the surface flux (first 5 planes)
     double* sR = sP + D::EB * 7 * Nfq;            // [EB][5][Nq] LSRK register (mode 1)
-    double* s_T = sR + D::EB * 5 * Nq;            // [n][n]
+    double* s_T = sR + (ESDG_HEX_STAGE_RES ? D::EB * 5 * Nq : 0);   // [n][n]
     double* s_lm = s_T + n * n;
     double* s_lp = s_lm + n;
     double* s_lmw = s_lp + n;                     // lm[a]/w[a]
@@ -321,7 +327,10 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
         Pi.lb = p.Lcur[p.q_stride + gq];
         if (p.mode == 1) {
 #pragma unroll
-            for (int f = 0; f < 5; ++f) cp_async8(sR + (eb * 5 + f) * Nq + i, p.res + f * p.q_stride + gq);
+            for (int f = 0; f < 5; ++f) {
+                if (ESDG_HEX_STAGE_RES) cp_async8(sR + (eb * 5 + f) * Nq + i, p.res + f * p.q_stride + gq);
+                else prefetch_l2(p.res + f * p.q_stride + gq);
+            }
         }
     }
 #pragma unroll
@@ -399,7 +408,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
             for (int f = 0; f < 5; ++f) F[f] = fma(-LFc, UP[f] - UM[f], F[f]);
         }
 #pragma unroll
-        for (int f = 0; f < 5; ++f) sFL[(b2 * 5 + f) * Nfq + k] = F[f];
+        for (int f = 0; f < 5; ++f) sFL[(b2 * 7 + f) * Nfq + k] = F[f];
     }
 
     // ---- C/D: flux differencing, one reference direction at a time ------------------------------
@@ -490,7 +499,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
 #pragma unroll
             for (int a = 0; a < n; ++a) h = fma(l[a], xf[a], h);
             const int ff = (fr == 0 || fr == 4) ? fr : 1 + (fr == 1 ? d : (fr == 2 ? c1 : c2));   // un-rotate
-            double* dst = sFL + (b2 * 5 + ff) * Nfq + (2 * d + side) * nfp + mm;
+            double* dst = sFL + (b2 * 7 + ff) * Nfq + (2 * d + side) * nfp + mm;
             *dst = side ? *dst - h : *dst + h;
         }
         __syncthreads();
@@ -507,7 +516,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
     // ---- E: lift, scale, rhstest, LSRK stage ----------------------------------------------------
     double tsum = 0.0;
     if (vol) {
-        const double* FL = sFL + eb * 5 * Nfq;
+        const double* FL = sFL + eb * 7 * Nfq;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
             const int xd = d == 0 ? xa : (d == 1 ? xb : xc);
@@ -538,7 +547,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(const __grid_
             double Un[5];
 #pragma unroll
             for (int f = 0; f < 5; ++f) {
-                const double rs = fma(p.rk_a, sR[(eb * 5 + f) * Nq + i], p.dt * r[f]);
+                const double rs = fma(p.rk_a, ESDG_HEX_STAGE_RES ? sR[(eb * 5 + f) * Nq + i] : p.res[f * p.q_stride + gq], p.dt * r[f]);
                 p.res[f * p.q_stride + gq] = rs;
                 Un[f] = fma(p.rk_b, rs, U[f]);
                 p.Qout[f * p.q_stride + gq] = Un[f];
