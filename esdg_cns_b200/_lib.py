@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libesdg_b200.so")
+LIB_PATH = os.environ.get("ESDG_B200_LIB", os.path.join(_HERE, "libesdg_b200.so"))   # override: kernel-variant experiments only
 
 ESDG_OK, ESDG_EINVAL, ESDG_ECUDA, ESDG_ENCCL, ESDG_ENOMEM, ESDG_ESTATE = range(6)
 ESDG_TRI, ESDG_QUAD, ESDG_HEX = 0, 1, 2

@@ -265,10 +265,12 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_traces(const __grid
 }
 
 template <int n, bool DIAG>
-#ifndef ESDG_HEX_MIN_CTAS
-#define ESDG_HEX_MIN_CTAS 1
+#ifdef ESDG_HEX_MIN_CTAS   // occupancy experiments; by default ptxas picks ~122 registers (4 CTAs/SM), which measured fastest
+__global__ void __launch_bounds__(HexDims<n>::THREADS, ESDG_HEX_MIN_CTAS) k_hex_stage(
+#else
+__global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(
 #endif
-__global__ void __launch_bounds__(HexDims<n>::THREADS, ESDG_HEX_MIN_CTAS) k_hex_stage(const __grid_constant__ HexParams p) {
+    const __grid_constant__ HexParams p) {
     using D = HexDims<n>;
     constexpr int Nq = D::Nq, nfp = D::nfp, Nfq = D::Nfq, Nh = D::Nh, KH = D::KH;
     extern __shared__ double sm[];
