@@ -313,3 +313,28 @@ int hexfast_stage(esdg_ctx* ctx, const double* Q, int mode, double a, double b, 
     }
     return ESDG_OK;
 }
+
+// ---- diagnostic entry point: the kernels' own log / exp on caller-supplied arguments -------------
+namespace {
+__global__ void k_debug_log_exp(const double* x, long long n, double* lg, double* ex) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        lg[i] = x[i] > 0.0 ? log_pos(x[i]) : 0.0;
+        ex[i] = exp_mod(x[i]);
+    }
+}
+}  // namespace
+
+extern "C" int esdg_debug_log_exp(int device, const double* x, int64_t n, double* log_out, double* exp_out) {
+    if (!x || !log_out || !exp_out || n <= 0) return ESDG_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return ESDG_ECUDA;
+    double *dx = nullptr, *dl = nullptr, *de = nullptr;
+    if (cudaMalloc(&dx, n * 8) != cudaSuccess || cudaMalloc(&dl, n * 8) != cudaSuccess || cudaMalloc(&de, n * 8) != cudaSuccess)
+        return ESDG_ENOMEM;
+    cudaMemcpy(dx, x, n * 8, cudaMemcpyHostToDevice);
+    k_debug_log_exp<<<(unsigned)((n + 255) / 256), 256>>>(dx, n, dl, de);
+    cudaMemcpy(log_out, dl, n * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(exp_out, de, n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(dx); cudaFree(dl); cudaFree(de);
+    return cudaGetLastError() == cudaSuccess ? ESDG_OK : ESDG_ECUDA;
+}

@@ -19,7 +19,7 @@
 // ARE the Kronecker products of these before selecting this path; otherwise the generic
 // table-driven kernels run.
 //
-// Trace format (7 planes): rho, u, v, w, beta, log(rho), log(beta) at every face point -- what
+// Trace format (7 planes): rho, u/2, v/2, w/2, beta, log(rho), log(beta) at every face point -- what
 // the neighbour's surface flux needs, so the exterior logs are not recomputed.
 #pragma once
 #include "physics.cuh"
@@ -81,6 +81,47 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return y;
 }
 
+// log / exp for normal, positive, moderate arguments (densities, inverse temperatures, -v_E, log
+// of rho_e).  The classic fdlibm argument reductions and minimax polynomials (e_log.c / e_exp.c,
+// error < 1 ulp) with the division replaced by fast_rcp; coefficients live in constant memory so
+// that the DFMAs take them as constant-bank operands instead of materialising 64-bit immediates.
+// ~2.5x fewer instructions than the library calls, which also handle denormals/inf/nan.
+__constant__ double c_lg[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
+                               2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
+                               1.479819860511658591e-01};
+__constant__ double c_ex[5] = {1.66666666666666019037e-01, -2.77777777770155933842e-03, 6.61375632143793436117e-05,
+                               -1.65339022054652515390e-06, 4.13813679705723846039e-08};
+
+__device__ __forceinline__ double log_pos(double x) {
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int k = (hi >> 20) - 1023;
+    hi &= 0x000fffff;
+    const int i = (hi + 0x95f64) & 0x100000;   // mantissa in (sqrt(2)/2, sqrt(2)]
+    hi |= (i ^ 0x3ff00000);
+    k += (i >> 20);
+    const double f = __hiloint2double(hi, lo) - 1.0;
+    const double s = f * fast_rcp(2.0 + f);
+    const double dk = (double)k;
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, c_lg[5], c_lg[3]), c_lg[1]);
+    const double t2 = z * fma(w, fma(w, fma(w, c_lg[6], c_lg[4]), c_lg[2]), c_lg[0]);
+    const double R = t2 + t1;
+    const double hfsq = .5 * f * f;
+    return dk * 6.93147180369123816490e-01 - ((hfsq - fma(s, hfsq + R, dk * 1.90821492927058770002e-10)) - f);
+}
+
+__device__ __forceinline__ double exp_mod(double x) {
+    const double kd = rint(x * 1.44269504088896338700e+00);
+    const double hi = fma(kd, -6.93147180369123816490e-01, x);
+    const double lo = kd * 1.90821492927058770002e-10;
+    const double r = hi - lo;
+    const double t = r * r;
+    const double c = r - t * fma(t, fma(t, fma(t, fma(t, c_ex[4], c_ex[3]), c_ex[2]), c_ex[1]), c_ex[0]);
+    const double y = 1.0 - ((lo - (r * c) * fast_rcp(2.0 - c)) - hi);
+    return __hiloint2double(__double2hiint(y) + ((int)kd << 20), __double2loint(y));
+}
+
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
@@ -124,8 +165,8 @@ __device__ __forceinline__ void pair_flux(const Node& A, const Node& B, const do
     double uavg[3], unorm = 0.0, un;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        uavg[d] = .5 * (A.u[d] + B.u[d]);
-        unorm = fma(A.u[d], B.u[d], unorm);
+        uavg[d] = A.u[d] + B.u[d];                 // Node.u holds HALF velocities
+        unorm = fma(A.u[d], B.u[d], unorm);        // = uL.uR / 4
     }
     if (DIAG) {
         un = g[D] * uavg[D];
@@ -134,7 +175,7 @@ __device__ __forceinline__ void pair_flux(const Node& A, const Node& B, const do
         un = fma(g[1], uavg[1], un);
         un = fma(g[2], uavg[2], un);
     }
-    const double Ep = fma(rholog, fma(ibl, c_igm, .5 * unorm), pa);   // rholog/(2(g-1)betalog)+pa+.5 rholog unorm
+    const double Ep = fma(rholog, fma(unorm, 2.0, ibl * c_igm), pa);   // rholog/(2(g-1)betalog)+pa+.5 rholog uL.uR
     const double m = rholog * un;
     F[0] = m;
 #pragma unroll
@@ -149,14 +190,14 @@ __device__ __forceinline__ void pair_flux(const Node& A, const Node& B, const do
 
 // volume-node primitives from conservative state; logs supplied (stash) or computed
 __device__ __forceinline__ void vol_prim(const double* U, double gamma, Node& P, double& rhoe, bool& bad) {
-    const double ir = fast_rcp(U[0]);
+    const double hir = .5 * fast_rcp(U[0]);
     double ke = 0.0;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        P.u[d] = U[1 + d] * ir;
-        ke = fma(U[1 + d], P.u[d], ke);
+        P.u[d] = U[1 + d] * hir;                    // half velocity
+        ke = fma(U[1 + d], P.u[d], ke);            // = .5 |rhoU|^2 / rho
     }
-    rhoe = U[4] - .5 * ke;
+    rhoe = U[4] - ke;
     bad = bad || !(U[0] > 0.0) || !(rhoe > 0.0);
     P.rho = U[0];
     P.beta = .5 * U[0] * fast_rcp((gamma - 1.0) * rhoe);
@@ -182,14 +223,15 @@ __device__ __forceinline__ void trace_from_entropy(const double* V, double gamma
     const double inv = fast_rcp(nvE);
     const double v2 = fma(V[1], V[1], fma(V[2], V[2], V[3] * V[3]));
     const double s = gamma - V[0] - .5 * v2 * inv;
-    const double lv = log(nvE);
+    const double lv = log_pos(nvE);
     const double ig = 1.0 / (gamma - 1.0);
     const double lrhoe = (lg1 - gamma * lv - s) * ig;   // lg1 = log(gamma-1), host-computed
-    const double rhoeV = exp(lrhoe);
+    const double rhoeV = exp_mod(lrhoe);
     Tv[0] = rhoeV * nvE;
-    Tv[1] = V[1] * inv;
-    Tv[2] = V[2] * inv;
-    Tv[3] = V[3] * inv;
+    const double hinv = .5 * inv;                        // traces carry HALF velocities, like Node.u
+    Tv[1] = V[1] * hinv;
+    Tv[2] = V[2] * hinv;
+    Tv[3] = V[3] * hinv;
     Tv[4] = .5 * nvE * ig;
     Tv[5] = lrhoe + lv;
     Tv[6] = lv - l2g1;                                   // l2g1 = log(2(gamma-1))
@@ -252,7 +294,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_traces(const __grid
         for (int f = 0; f < 5; ++f) U[f] = p.Q[f * p.q_stride + g];
         Node P;
         vol_prim(U, p.gamma, P, rhoe, bad);
-        const double lr = log(P.rho), lb = log(P.beta);
+        const double lr = log_pos(P.rho), lb = log_pos(P.beta);
         p.Lnext[g] = lr;
         p.Lnext[p.q_stride + g] = lb;
         entropy_vars(U, rhoe, lr, lb, p.gamma, V);
@@ -393,10 +435,11 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(
             UP[0] = P.rho;
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-                UM[1 + d] = M.rho * M.u[d];
-                UP[1 + d] = P.rho * P.u[d];
-                kM = fma(UM[1 + d], M.u[d], kM);
-                kP = fma(UP[1 + d], P.u[d], kP);
+                const double uM = 2.0 * M.u[d], uP = 2.0 * P.u[d];
+                UM[1 + d] = M.rho * uM;
+                UP[1 + d] = P.rho * uP;
+                kM = fma(UM[1 + d], uM, kM);
+                kP = fma(UP[1 + d], uP, kP);
                 unM = fma(UM[1 + d], nJ[d], unM);
                 unP = fma(UP[1 + d], nJ[d], unP);
             }
@@ -424,6 +467,20 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(
     int x0 = xa, x1 = xb, x2 = xc;                 // rotated line coordinates: x0 runs along direction d
     int s0 = 1, s1 = n, s2 = n * n;                // matching node strides
     int m0 = xc + n * xb, m1 = xc + n * xa, m2 = xb + n * xa;   // on-face index of my line per direction
+    // work items of the per-direction face reduction (independent of the direction)
+    constexpr int MAXH = (D::EB * 10 * nfp + D::THREADS - 1) / D::THREADS;
+    int h_xoff[MAXH], h_dst[MAXH], h_fr[MAXH];
+    bool h_side[MAXH];
+#pragma unroll
+    for (int r = 0; r < MAXH; ++r) {
+        const int it = ftid + r * D::THREADS;
+        const int b2 = it / (10 * nfp), q = it - b2 * 10 * nfp;
+        const int sf = q / nfp, mm = q - sf * nfp;          // sf = side*5 + (rotated) field
+        h_side[r] = sf >= 5;
+        h_fr[r] = sf >= 5 ? sf - 5 : sf;
+        h_xoff[r] = it < nb * 10 * nfp ? b2 * D::XSZ + D::XV + (sf * nfp + mm) * n : -1;
+        h_dst[r] = b2 * 7 * Nfq + (sf >= 5 ? nfp : 0) + mm;
+    }
 #pragma unroll 1
     for (int d = 0; d < 3; ++d) {
         const int c1 = d == 2 ? 0 : d + 1, c2 = c1 == 2 ? 0 : c1 + 1;   // physical components in rotated order d,c1,c2
@@ -490,19 +547,20 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(
             }
         }
         // face nodes of this direction: H = -nrJ * sum_a l[a] F(a) + flux*, one (face point, field)
-        // per work item so that all warps share the reduction
-        for (int it = ftid; it < nb * 2 * 5 * nfp; it += blockDim.x) {
-            const int b2 = it / (2 * 5 * nfp), r = it - b2 * 2 * 5 * nfp;
-            const int sf = r / nfp, mm = r - sf * nfp;      // sf = side*5 + f (rotated field index)
-            const int side = sf / 5, fr = sf - side * 5;
-            const double* xf = sX + b2 * D::XSZ + D::XV + (sf * nfp + mm) * n;
-            const double* l = side ? s_lp : s_lm;
-            double h = 0.0;
+        // per work item so that all warps share the reduction (item decode hoisted out of the loop)
 #pragma unroll
-            for (int a = 0; a < n; ++a) h = fma(l[a], xf[a], h);
-            const int ff = (fr == 0 || fr == 4) ? fr : 1 + (fr == 1 ? d : (fr == 2 ? c1 : c2));   // un-rotate
-            double* dst = sFL + (b2 * 7 + ff) * Nfq + (2 * d + side) * nfp + mm;
-            *dst = side ? *dst - h : *dst + h;
+        for (int r = 0; r < MAXH; ++r) {
+            if (h_xoff[r] >= 0) {
+                const double* xf = sX + h_xoff[r];
+                const double* l = h_side[r] ? s_lp : s_lm;
+                double h = 0.0;
+#pragma unroll
+                for (int a = 0; a < n; ++a) h = fma(l[a], xf[a], h);
+                const int fr = h_fr[r];
+                const int ff = (fr == 0 || fr == 4) ? fr : 1 + (fr == 1 ? d : (fr == 2 ? c1 : c2));   // un-rotate
+                double* dst = sFL + h_dst[r] + ff * Nfq + 2 * d * nfp;
+                *dst = h_side[r] ? *dst - h : *dst + h;
+            }
         }
         __syncthreads();
         // rotate the frame: direction d+1 becomes component 0
@@ -558,7 +616,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(
             Node Pn;
             double rhoen, V[5];
             vol_prim(Un, p.gamma, Pn, rhoen, bad);
-            const double lr = log(Pn.rho), lb = log(Pn.beta);
+            const double lr = log_pos(Pn.rho), lb = log_pos(Pn.beta);
             p.Lnext[gq] = lr;
             p.Lnext[p.q_stride + gq] = lb;
             entropy_vars(Un, rhoen, lr, lb, p.gamma, V);

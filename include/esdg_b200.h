@@ -146,6 +146,8 @@ int esdg_read_rhstest(esdg_ctx* ctx, double* rhstest);
 int64_t esdg_kernel_launches(const esdg_ctx* ctx);          /* kernels launched so far      */
 int esdg_kernel_time_ms(esdg_ctx* ctx, const char* kernel, double* total_ms, int64_t* launches);
 int esdg_enable_timing(esdg_ctx* ctx, int on);              /* CUDA-event timing per kernel */
+/* diagnostic: the kernels' own log (x > 0, normal) and exp (|x| < 700) evaluated on n host values */
+int esdg_debug_log_exp(int device, const double* x, int64_t n, double* log_out, double* exp_out);
 /* DFMA micro-benchmark: non-tensor FP64 peak of the device in TFLOP/s (roofline denominator) */
 int esdg_measure_fp64_peak(int device, double* tflops);
 const char* esdg_version(void);

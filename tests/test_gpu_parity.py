@@ -187,3 +187,23 @@ def test_hex_path_is_selected():
     assert s.kernel_time_ms("hex_stage")[1] == 5
     assert s.kernel_time_ms("generic_rhs")[1] == 0
     assert s.trace_planes() == 7
+
+
+def test_kernel_log_exp_accuracy():
+    """The kernels' lean log/exp (fdlibm reductions, kernels_hex.cuh) stay within 2 ulp of libm."""
+    from esdg_cns_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    x = np.concatenate([10.0 ** rng.uniform(-6, 6, 20000), 1 + rng.uniform(-1e-3, 1e-3, 2000), [1.0, 2.0, .5, 1.4, 0.4]])
+    lg, ex = np.empty_like(x), np.empty_like(x)
+    assert lib.esdg_debug_log_exp(0, x.ctypes.data, x.size, lg.ctypes.data, ex.ctypes.data) == 0
+    ref = np.log(x)
+    ulp = np.abs(lg - ref) / np.spacing(np.maximum(np.abs(ref), 1e-300))
+    near1 = np.abs(x - 1) < 1e-2                       # log ~ 0: compare absolutely
+    assert ulp[~near1].max() <= 2.0, ulp[~near1].max()
+    assert np.abs(lg - ref)[near1].max() < 4e-19 + 2 * np.spacing(np.abs(ref[near1])).max()
+    y = rng.uniform(-40, 40, 20000)
+    lg2, ex2 = np.empty_like(y), np.empty_like(y)
+    assert lib.esdg_debug_log_exp(0, y.ctypes.data, y.size, lg2.ctypes.data, ex2.ctypes.data) == 0
+    refe = np.exp(y)
+    assert (np.abs(ex2 - refe) / np.spacing(refe)).max() <= 2.0
