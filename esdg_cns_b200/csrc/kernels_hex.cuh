@@ -188,6 +188,83 @@ __device__ __forceinline__ void pair_flux(const Node& A, const Node& B, const do
     F[4] = Ep * un;
 }
 
+// Two independent two-point fluxes against the same node A, written statement-interleaved so that the
+// scheduler sees two dependency chains (the FP64 pipe is latency-bound with 4 warps per scheduler).
+#define ESDG_Q2 for (int q = 0; q < 2; ++q)
+template <bool DIAG, int D>
+__device__ __forceinline__ void pair_flux2(const Node& A, const Node* B, const double* g, double c_igm, double (*F)[5]) {
+    double dar[2], hr[2], dab[2], sb[2], hb[2], X[2], Y[2], XY[2], R[2], iX[2], iY[2], iZ[2];
+    bool tr[2], tb[2];
+#pragma unroll
+    ESDG_Q2 { dar[q] = B[q].rho - A.rho; hr[q] = .5 * (A.rho + B[q].rho); }
+#pragma unroll
+    ESDG_Q2 { dab[q] = B[q].beta - A.beta; sb[q] = A.beta + B[q].beta; hb[q] = .5 * sb[q]; }
+#pragma unroll
+    ESDG_Q2 { tr[q] = fabs(dar[q]) < 1e-4 * hr[q]; tb[q] = fabs(dab[q]) < 1e-4 * hb[q]; }
+#pragma unroll
+    ESDG_Q2 { X[q] = tr[q] ? hr[q] : (B[q].lr - A.lr); Y[q] = tb[q] ? hb[q] : dab[q]; }
+#pragma unroll
+    ESDG_Q2 XY[q] = X[q] * Y[q];
+    {   // two reciprocals, Newton steps interleaved
+        double y[2], e[2], x[2];
+#pragma unroll
+        ESDG_Q2 { x[q] = XY[q] * sb[q]; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[q]) : "d"(x[q])); }
+#pragma unroll
+        ESDG_Q2 e[q] = fma(-x[q], y[q], 1.0);
+#pragma unroll
+        ESDG_Q2 y[q] = fma(y[q], e[q], y[q]);
+#pragma unroll
+        ESDG_Q2 e[q] = fma(-x[q], y[q], 1.0);
+#pragma unroll
+        ESDG_Q2 R[q] = fma(y[q], e[q], y[q]);
+    }
+#pragma unroll
+    ESDG_Q2 { iX[q] = R[q] * (Y[q] * sb[q]); iY[q] = R[q] * (X[q] * sb[q]); iZ[q] = R[q] * XY[q]; }
+    double qr[2], vr[2], rholog[2], fb[2], vb[2], xb[2], ibl[2], pa[2];
+#pragma unroll
+    ESDG_Q2 { qr[q] = dar[q] * iX[q]; fb[q] = dab[q] * iY[q]; }
+#pragma unroll
+    ESDG_Q2 { vr[q] = qr[q] * qr[q]; vb[q] = fb[q] * fb[q]; }
+#pragma unroll
+    ESDG_Q2 rholog[q] = tr[q] ? hr[q] * (1.0 + vr[q] * (-.2 - vr[q] * (.0512 - vr[q] * 0.026038857142857))) : qr[q];
+#pragma unroll
+    ESDG_Q2 xb[q] = vb[q] * (-.2 - vb[q] * (.0512 - vb[q] * 0.026038857142857));
+#pragma unroll
+    ESDG_Q2 { ibl[q] = iY[q] * (tb[q] ? (1.0 - xb[q]) : (B[q].lb - A.lb)); pa[q] = hr[q] * iZ[q]; }
+    double uavg[2][3], unorm[2] = {0.0, 0.0}, un[2];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        ESDG_Q2 { uavg[q][d] = A.u[d] + B[q].u[d]; unorm[q] = fma(A.u[d], B[q].u[d], unorm[q]); }
+    }
+#pragma unroll
+    ESDG_Q2 {
+        if (DIAG) {
+            un[q] = g[D] * uavg[q][D];
+        } else {
+            un[q] = g[0] * uavg[q][0];
+            un[q] = fma(g[1], uavg[q][1], un[q]);
+            un[q] = fma(g[2], uavg[q][2], un[q]);
+        }
+    }
+    double Ep[2], m[2];
+#pragma unroll
+    ESDG_Q2 { Ep[q] = fma(rholog[q], fma(unorm[q], 2.0, ibl[q] * c_igm), pa[q]); m[q] = rholog[q] * un[q]; }
+#pragma unroll
+    ESDG_Q2 {
+        F[q][0] = m[q];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (DIAG)
+                F[q][1 + d] = (d == D) ? fma(m[q], uavg[q][d], pa[q] * g[d]) : m[q] * uavg[q][d];
+            else
+                F[q][1 + d] = fma(m[q], uavg[q][d], pa[q] * g[d]);
+        }
+        F[q][4] = Ep[q] * un[q];
+    }
+}
+#undef ESDG_Q2
+
 // volume-node primitives from conservative state; logs supplied (stash) or computed
 __device__ __forceinline__ void vol_prim(const double* U, double gamma, Node& P, double& rhoe, bool& bad) {
     const double hir = .5 * fast_rcp(U[0]);
@@ -499,35 +576,55 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(
                 q.lb = W[6 * Nh + idx];
                 return q;
             };
-            // owned volume pairs (x, x+k mod n)
+            // partners of this direction: KH owned volume pairs (x, x+k mod n) and the two face nodes
+            // of my line, evaluated two at a time
+            constexpr int NP = KH + 2;
+            int pj[NP];
+            double pc[NP];
+            double* px[NP];          // exchange slot of field 0 (field stride pxs)
+            int pxs[NP];
+            bool pst[NP];
 #pragma unroll
             for (int k = 1; k <= KH; ++k) {
                 const bool own = !((n % 2 == 0) && (k == n / 2) && (x0 >= n / 2));
                 int ap = x0 + k;
                 ap = ap >= n ? ap - n : ap;
-                if (own) {
-                    const Node Pj = ldn(i + (ap - x0) * s0);
-                    double F[5];
-                    pair_flux<DIAG, 0>(Pi, Pj, g, c_igm, F);
-                    const double t = s_T[x0 * n + ap];
+                pj[k - 1] = i + (ap - x0) * s0;
+                pc[k - 1] = own ? s_T[x0 * n + ap] : 0.0;
+                px[k - 1] = XVb + (k - 1) * 5 * Nq + i;
+                pxs[k - 1] = Nq;
+                pst[k - 1] = own;
+            }
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                pj[KH + side] = Nq + (2 * d + side) * nfp + m0;
+                pc[KH + side] = side ? s_lpw[x0] : -s_lmw[x0];
+                px[KH + side] = XFb + (side * 5 * nfp + m0) * n + x0;
+                pxs[KH + side] = nfp * n;
+                pst[KH + side] = true;
+            }
+#pragma unroll
+            for (int pp = 0; pp + 1 < NP; pp += 2) {
+                const Node B2[2] = {ldn(pj[pp]), ldn(pj[pp + 1])};
+                double F2[2][5];
+                pair_flux2<DIAG, 0>(Pi, B2, g, c_igm, F2);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
 #pragma unroll
                     for (int f = 0; f < 5; ++f) {
-                        acc[f] = fma(t, F[f], acc[f]);
-                        XVb[((k - 1) * 5 + f) * Nq + i] = F[f];
+                        acc[f] = fma(pc[pp + q], F2[q][f], acc[f]);
+                        if (pst[pp + q]) px[pp + q][f * pxs[pp + q]] = F2[q][f];
                     }
                 }
             }
-            // the two face partners of my line
-#pragma unroll
-            for (int side = 0; side < 2; ++side) {
-                const Node Pf = ldn(Nq + (2 * d + side) * nfp + m0);
+            if (NP % 2 == 1) {
+                const Node Pj = ldn(pj[NP - 1]);
                 double F[5];
-                pair_flux<DIAG, 0>(Pi, Pf, g, c_igm, F);
-                const double t = side ? s_lpw[x0] : -s_lmw[x0];
+                pair_flux<DIAG, 0>(Pi, Pj, g, c_igm, F);
 #pragma unroll
                 for (int f = 0; f < 5; ++f) {
-                    acc[f] = fma(t, F[f], acc[f]);
-                    XFb[((side * 5 + f) * nfp + m0) * n + x0] = F[f];
+                    acc[f] = fma(pc[NP - 1], F[f], acc[f]);
+                    if (pst[NP - 1]) px[NP - 1][f * pxs[NP - 1]] = F[f];
                 }
             }
         }
