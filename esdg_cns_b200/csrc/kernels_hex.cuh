@@ -60,7 +60,7 @@ struct HexDims {
     static constexpr int THREADS = ((EB * Nq + 31) / 32) * 32;
     static constexpr int XV = KH * 5 * Nq, XF = 2 * 5 * nfp * n;
     static constexpr int XSZ = (XV + XF) > 5 * Nq ? (XV + XF) : 5 * Nq;
-    static constexpr int TAB = n * n + 5 * n;
+    static constexpr int TAB = n * n + 5 * n + EB * 34;   // 1-D tables + per-element geometry records
 #ifndef ESDG_HEX_STAGE_RES
 #define ESDG_HEX_STAGE_RES 1   // 1: LSRK register staged in shared memory by cp.async; 0: read in phase E (smaller footprint)
 #endif
@@ -404,6 +404,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(
     double* s_lmw = s_lp + n;                     // lm[a]/w[a]
     double* s_lpw = s_lmw + n;
     double* s_w = s_lpw + n;
+    double* sGeo = s_w + n;                       // [EB][34]: G[9], J, 6 x (nxJ,nyJ,nzJ,sJ)
     const int tid = threadIdx.x;
     // face-item loops use a thread id rotated by a whole number of warps per CTA: the leftover pass
     // (Nfq is not a multiple of the block size) then lands on a different SM sub-partition for each
@@ -432,6 +433,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(
     // (1) exterior-trace indices, (2) own traces -> sW face rows and (3) exterior traces -> sP with
     // cp.async (no register staging), (4) L2 prefetch of the LSRK register read in phase E.
     constexpr int MAXIT = (D::EB * Nfq + D::THREADS - 1) / D::THREADS;
+    constexpr int PF_DIST = 592;   // CTAs in flight on a B200 (148 SMs x 4): distance of the L2 warm-up
     int ipv[MAXIT];
 #pragma unroll
     for (int r = 0; r < MAXIT; ++r) {
@@ -474,7 +476,34 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(
                 cp_async8(sP + (b2 * 7 + q) * Nfq + k, p.Tcur + q * p.t_stride + ipv[r]);
         }
     }
+    for (int it = tid; it < nb * 34; it += D::THREADS) cp_async8(sGeo + it, p.geo + e0 * 34 + it);
     cp_async_commit();
+    // (5) warm L2 for the CTA that will run ~one grid-wave later (it starts when this one retires)
+    {
+        const long long e1 = e0 + (long long)PF_DIST * D::EB;
+        if (e1 + D::EB <= p.e_begin + p.e_count) {
+            if (tid < D::EB * Nq) {
+                const long long g1 = e1 * Nq + tid;
+#pragma unroll
+                for (int f = 0; f < 5; ++f) prefetch_l2(p.Q + f * p.q_stride + g1);
+                prefetch_l2(p.Lcur + g1);
+                prefetch_l2(p.Lcur + p.q_stride + g1);
+                if (p.mode == 1) {
+#pragma unroll
+                    for (int f = 0; f < 5; ++f) prefetch_l2(p.res + f * p.q_stride + g1);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < MAXIT; ++r) {
+                const int it = ftid + r * D::THREADS;
+                if (it < D::EB * Nfq) {
+                    prefetch_l2(p.mapP + e1 * Nfq + it);
+#pragma unroll
+                    for (int q = 0; q < HEX_TP; ++q) prefetch_l2(p.Tcur + q * p.t_stride + e1 * Nfq + it);
+                }
+            }
+        }
+    }
 
     // ---- A: volume nodes -> shared --------------------------------------------------------------
     double* W = sW + eb * 7 * Nh;
@@ -496,7 +525,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(
         const int b2 = it / Nfq, k = it - b2 * Nfq;
         const long long ee = e0 + b2;
         const int face = k / nfp;
-        const double* gf = p.geo + ee * p.geo_stride + 10 + face * 4;
+        const double* gf = sGeo + b2 * 34 + 10 + face * 4;
         const double nJ[3] = {gf[0], gf[1], gf[2]};
         const double sJ = gf[3];
         const Node M = ld_node(sW + b2 * 7 * Nh, Nh, Nq + k);
@@ -538,7 +567,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(
     // cache); velocity components, momentum accumulators, line coordinates and strides are kept in
     // a frame ROTATED with the direction so that "component 0" is always the line direction.
     double acc[5] = {0, 0, 0, 0, 0};
-    const double* G = p.geo + e * p.geo_stride;
+    const double* G = sGeo + eb * 34;
     double* XVb = sX + eb * D::XSZ;
     double* XFb = XVb + D::XV;
     int x0 = xa, x1 = xb, x2 = xc;                 // rotated line coordinates: x0 runs along direction d
@@ -546,17 +575,16 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(
     int m0 = xc + n * xb, m1 = xc + n * xa, m2 = xb + n * xa;   // on-face index of my line per direction
     // work items of the per-direction face reduction (independent of the direction)
     constexpr int MAXH = (D::EB * 10 * nfp + D::THREADS - 1) / D::THREADS;
-    int h_xoff[MAXH], h_dst[MAXH], h_fr[MAXH];
+    int h_xoff[MAXH], h_dst[MAXH];
     bool h_side[MAXH];
 #pragma unroll
     for (int r = 0; r < MAXH; ++r) {
         const int it = ftid + r * D::THREADS;
         const int b2 = it / (10 * nfp), q = it - b2 * 10 * nfp;
-        const int sf = q / nfp, mm = q - sf * nfp;          // sf = side*5 + (rotated) field
+        const int sf = q / nfp, mm = q - sf * nfp;          // sf = side*5 + field
         h_side[r] = sf >= 5;
-        h_fr[r] = sf >= 5 ? sf - 5 : sf;
         h_xoff[r] = it < nb * 10 * nfp ? b2 * D::XSZ + D::XV + (sf * nfp + mm) * n : -1;
-        h_dst[r] = b2 * 7 * Nfq + (sf >= 5 ? nfp : 0) + mm;
+        h_dst[r] = b2 * 7 * Nfq + (sf >= 5 ? nfp : 0) + mm + (sf >= 5 ? sf - 5 : sf) * Nfq;
     }
 #pragma unroll 1
     for (int d = 0; d < 3; ++d) {
@@ -613,7 +641,9 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(
 #pragma unroll
                     for (int f = 0; f < 5; ++f) {
                         acc[f] = fma(pc[pp + q], F2[q][f], acc[f]);
-                        if (pst[pp + q]) px[pp + q][f * pxs[pp + q]] = F2[q][f];
+                        // face slots are written in PHYSICAL field order (the face reduction is not rotated)
+                        const int fs = (pp + q >= KH) ? (f == 1 ? 1 + d : (f == 2 ? 1 + c1 : (f == 3 ? 1 + c2 : f))) : f;
+                        if (pst[pp + q]) px[pp + q][fs * pxs[pp + q]] = F2[q][f];
                     }
                 }
             }
@@ -624,7 +654,8 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(
 #pragma unroll
                 for (int f = 0; f < 5; ++f) {
                     acc[f] = fma(pc[NP - 1], F[f], acc[f]);
-                    if (pst[NP - 1]) px[NP - 1][f * pxs[NP - 1]] = F[f];
+                    const int fs = (f == 1 ? 1 + d : (f == 2 ? 1 + c1 : (f == 3 ? 1 + c2 : f)));   // last partner is a face
+                    if (pst[NP - 1]) px[NP - 1][fs * pxs[NP - 1]] = F[f];
                 }
             }
         }
@@ -653,9 +684,7 @@ __global__ void __launch_bounds__(HexDims<n>::THREADS) k_hex_stage(
                 double h = 0.0;
 #pragma unroll
                 for (int a = 0; a < n; ++a) h = fma(l[a], xf[a], h);
-                const int fr = h_fr[r];
-                const int ff = (fr == 0 || fr == 4) ? fr : 1 + (fr == 1 ? d : (fr == 2 ? c1 : c2));   // un-rotate
-                double* dst = sFL + h_dst[r] + ff * Nfq + 2 * d * nfp;
+                double* dst = sFL + h_dst[r] + 2 * d * nfp;
                 *dst = h_side[r] ? *dst - h : *dst + h;
             }
         }
