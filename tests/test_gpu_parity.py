@@ -207,3 +207,61 @@ def test_kernel_log_exp_accuracy():
     assert lib.esdg_debug_log_exp(0, y.ctypes.data, y.size, lg2.ctypes.data, ex2.ctypes.data) == 0
     refe = np.exp(y)
     assert (np.abs(ex2 - refe) / np.spacing(refe)).max() <= 2.0
+
+
+# ---------------------------------------------------------------------------------------------
+# modal triangles (BASELINE config 2 shape): Vq / VhP projection path, dense operators
+@pytest.mark.parametrize("N,Kx,Ky,lf", [(2, 4, 3, .25), (3, 4, 4, 0.0), (4, 6, 4, .25)])
+def test_tri_rhs_matches_oracle(N, Kx, Ky, lf):
+    from oracle import solvers as SV
+    from esdg_cns_b200 import api
+    rd, md, ops, Q = SV.setup_tri_vortex(N, Kx, Ky)
+    ops.lf_scale = lf
+    ref, rt_ref = SV.rhs_tri(Q, md, ops, rd, lf, True)
+    s = api.Solver(md, ops)
+    out, rt = s.rhs(Q, True)
+    err = _relerr(out, ref)
+    tol = parity_tol(lambda: SV.rhs_tri(Q, md, ops, rd, lf, False)[0], ref)
+    print(f"tri N={N} {Kx}x{Ky} lf={lf}: relerr {err:.2e} tol {tol:.2e} rhstest {rt:.3e} vs {rt_ref:.3e}")
+    assert err < tol
+    assert abs(rt - rt_ref) < 1e-11 * max(1.0, abs(rt_ref))
+    if lf == 0.0:
+        assert abs(rt) < 1e-11
+
+
+def test_tri_lsrk_step_and_freestream():
+    from oracle import solvers as SV
+    from esdg_cns_b200 import api
+    rd, md, ops, Q = SV.setup_tri_vortex(4, 4, 4)
+    dt = 2 * (2 / 4) / 15
+    Qo, _, rto = SV.lsrk45_step(Q, [np.zeros_like(q) for q in Q], dt, lambda q, t: SV.rhs_tri(q, md, ops, rd, .25, t))
+    Qg, rtg = api.lsrk45_steps(Q, md, ops, dt, 1, want_rhstest=True)
+    assert max(np.abs(a - b).max() for a, b in zip(Qg, Qo)) < 1e-12
+    assert abs(rtg - rto) < 1e-11
+    Qc = [np.full_like(Q[0], v) for v in (1.0, .3, -.2, 2.5)]
+    out, _ = api.rhs(Qc, md, ops)
+    assert max(np.abs(r).max() for r in out) < 1e-11
+
+
+def test_golden_fixtures_on_gpu():
+    """CUDA path against the committed fixtures (tests/golden/*.npz, generated by make_golden.py)."""
+    import os
+    from oracle import solvers as SV
+    from esdg_cns_b200 import api
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    for name, setup, lf in (("quad_N3_4x4_vortex", lambda: SV.setup_quad_vortex(3, 4, 4)[:3], .5),
+                            ("hex_N2_3x3x3_tgv", lambda: SV.setup_hex(2, 3, scale=(np.pi,) * 3), .25),
+                            ("tri_N3_3x2_vortex", lambda: SV.setup_tri_vortex(3, 3, 2)[:3], .25)):
+        d = np.load(os.path.join(gold, name + ".npz"))
+        rd, md, ops = setup()
+        ops.lf_scale = lf
+        s = api.Solver(md, ops)
+        out, rt = s.rhs(list(d["Q"]), True)
+        scale = np.abs(d["rhs"]).max()
+        assert np.abs(np.stack(out) - d["rhs"]).max() / scale < 2e-10, name     # TGV noise floor, see helpers.py
+        assert abs(rt - float(d["rhstest"])) < 1e-11
+        if "Q1" in d:
+            s.upload(list(d["Q"]))
+            s.lsrk45(float(d["dt"]), 1)
+            Q1 = np.stack(s.download())
+            assert np.abs(Q1 - d["Q1"]).max() / np.abs(d["Q1"]).max() < 1e-13, name
