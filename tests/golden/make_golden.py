@@ -13,7 +13,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from oracle import physics as P, solvers as SV  # noqa: E402
+from oracle import cns, physics as P, solvers as SV  # noqa: E402
 
 
 def quad_case():
@@ -53,7 +53,28 @@ def flux_kat():
                         F=np.array(F, dtype=float))
 
 
+def cns_state(md):
+    """Smooth non-trivial state on the cavity domain (walls at +-1) used by the CNS parity tests."""
+    x, y = md.x, md.y
+    rho = 1 + .1 * np.sin(np.pi * x) * np.cos(np.pi * y)
+    u = .2 * np.sin(np.pi * x) * np.sin(np.pi * y)
+    v = .1 * np.cos(.5 * np.pi * x) * np.cos(.5 * np.pi * y) * (1 - y ** 2)
+    p = 1 / (.09 * 1.4) * (1 + .05 * np.cos(np.pi * x))
+    return list(P.primitive_to_conservative(rho, (u, v), p))
+
+
+def cns_case():
+    """BASELINE config 3: CNS on quads N=3, lid-driven cavity BCs (adiabatic no-slip), both dissipations on."""
+    rd, md, ops, bc, _ = cns.setup_cavity("quad", 3, 4)
+    Q = cns_state(md)
+    par = cns.cavity_params()
+    rhs, rt, rtv = cns.rhsRK(Q, md, ops, bc, par)
+    np.savez_compressed(os.path.join(HERE, "cns_quad_N3_4x4_cavity.npz"), Q=np.stack(Q), rhs=np.stack(rhs), rhstest=rt,
+                        rhstest_visc=rtv)
+
+
 if __name__ == "__main__":
+    cns_case()
     quad_case()
     hex_case()
     tri_case()
