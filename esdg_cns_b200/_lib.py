@@ -48,6 +48,9 @@ _SIGNATURES = {
     "esdg_set_operator": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int64]),
     "esdg_set_geometry": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int64]),
     "esdg_set_maps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "esdg_set_viscosity": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]),
+    "esdg_set_wall_bc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]),
+    "esdg_set_boundary_nodes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "esdg_finalize": (C.c_int, [C.c_void_p]),
     "esdg_rhs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "esdg_upload_state": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -62,6 +65,7 @@ _SIGNATURES = {
     "esdg_stage_update": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int]),
     "esdg_trace_planes": (C.c_int, [C.c_void_p]),
     "esdg_read_rhstest": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "esdg_read_rhstest_visc": (C.c_int, [C.c_void_p, C.c_void_p]),
     "esdg_kernel_launches": (C.c_int64, [C.c_void_p]),
     "esdg_kernel_time_ms": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "esdg_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),

@@ -42,21 +42,26 @@ def euler_fluxes(*_a, **_k):
 class Solver:
     """One GPU context: operators, geometry and maps resident in HBM."""
 
-    def __init__(self, md, ops, device=0, n_halo=0, stream=None, map_index_base=0):
+    def __init__(self, md, ops, device=0, n_halo=0, stream=None, map_index_base=0, cns=None):
+        """``cns``: None (Euler) or a namespace with the CNS script globals ``Re, mu, lam, Pr, bctype,
+        inviscid_dissp, viscous_dissp`` (dg2D_CNS_cavity_optimized.jl:21-36) and the boundary node
+        sets ``wall, lid, vlid, mapB`` (0-based unless map_index_base=1; :139-147)."""
         lib = L.load()
         self._lib = lib
         self._ctx = C.c_void_p()
         dim = 3 if ops.elem == "hex" else 2
         nf = dim + 2
         self.nf = nf
-        collocated = 1 if ops.elem in ("quad", "hex") else 0
+        collocated = 1 if (ops.elem in ("quad", "hex") and not getattr(ops, "modal", False)) else 0
+        self.cns = cns
         Nq = int(np.asarray(ops.wq).size)
         Nfq = int(np.asarray(ops.Lf).shape[1])
         Ns = int(np.asarray(ops.Ph).shape[0])
         self.Ns, self.K = Ns, int(md.K)
         d = L.esdg_desc(dim=dim, elem=ELEM_CODE[ops.elem], N=int(ops.N), Nfields=nf, Ns=Ns, Nq=Nq, Nfq=Nfq,
                         Nfaces=int(ops.Nfaces), collocated=collocated, affine=1, K=int(md.K), n_halo=int(n_halo),
-                        gamma=1.4, lf_scale=float(ops.lf_scale), volume_scale=float(ops.volume_scale))
+                        gamma=1.4, volume_scale=float(ops.volume_scale),
+                        lf_scale=float(ops.lf_scale) if (cns is None or cns.inviscid_dissp) else 0.0)
         self.desc = d
         code = lib.esdg_create(C.byref(d), int(device), C.byref(self._ctx))
         if code != L.ESDG_OK:
@@ -87,6 +92,20 @@ class Solver:
             self._ck(lib.esdg_set_geometry(self._ctx, n.encode(), a.ctypes.data, a.shape[0], a.shape[1]))
         mapP = np.asfortranarray(np.asarray(md.mapP, dtype=np.int64) + (1 - map_index_base))
         self._ck(lib.esdg_set_maps(self._ctx, mapP.ctypes.data, mapP.size))
+        if cns is not None:
+            for n in ("Pq", "Vf", "Dr", "Ds"):
+                self._set_op(n, getattr(ops, n))
+            self._ck(lib.esdg_set_viscosity(self._ctx, float(cns.lam), float(cns.mu), float(cns.Pr), float(cns.Re),
+                                            int(bool(cns.viscous_dissp))))
+            shift = 1 - map_index_base
+            wall = np.ascontiguousarray(np.asarray(cns.wall, dtype=np.int64) + shift)
+            lid = np.ascontiguousarray(np.asarray(cns.lid, dtype=np.int64) + shift)
+            vlid = np.ascontiguousarray(np.asarray(cns.vlid, dtype=np.float64))
+            self._ck(lib.esdg_set_wall_bc(self._ctx, int(cns.bctype), wall.ctypes.data, wall.size, lid.ctypes.data,
+                                          vlid.ctypes.data, lid.size))
+            if getattr(cns, "mapB", None) is not None:
+                mb = np.ascontiguousarray(np.asarray(cns.mapB, dtype=np.int64) + shift)
+                self._ck(lib.esdg_set_boundary_nodes(self._ctx, mb.ctypes.data, mb.size))
         self._ck(lib.esdg_finalize(self._ctx))
 
     # -- helpers ---------------------------------------------------------------
@@ -114,6 +133,8 @@ class Solver:
             qin = self._host_fields(Q)
             qp = L.ptr_array(qin)
         self._ck(self._lib.esdg_rhs(self._ctx, qp, L.ptr_array(out), int(bool(compute_rhstest)), rt))
+        if self.cns is not None:
+            return out, float(rt[0]), float(rt[1])
         return out, float(rt[0])
 
     def upload(self, Q):
@@ -172,6 +193,11 @@ class Solver:
         self._ck(self._lib.esdg_read_rhstest(self._ctx, C.byref(rt)))
         return float(rt.value)
 
+    def read_rhstest_visc(self):
+        rt = C.c_double(0.0)
+        self._ck(self._lib.esdg_read_rhstest_visc(self._ctx, C.byref(rt)))
+        return float(rt.value)
+
     # -- introspection ---------------------------------------------------------------
     def kernel_launches(self):
         return int(self._lib.esdg_kernel_launches(self._ctx))
@@ -192,11 +218,11 @@ class Solver:
 _solver_cache = []   # [(md, ops, Solver)], most recent last; the functional API keeps 4 contexts alive
 
 
-def _cached_solver(md, ops):
+def _cached_solver(md, ops, cns=None):
     for ent in _solver_cache:
-        if ent[0] is md and ent[1] is ops:
+        if ent[0] is md and ent[1] is ops and (cns is None or ent[2].cns is cns):
             return ent[2]
-    ent = (md, ops, Solver(md, ops))
+    ent = (md, ops, Solver(md, ops, cns=cns))
     _solver_cache.append(ent)
     while len(_solver_cache) > 4:
         _solver_cache.pop(0)[2].close()
@@ -220,3 +246,22 @@ def lsrk45_steps(Q, md, ops, dt, nsteps=1, want_rhstest=False):
     s.upload(Q)
     rt = s.lsrk45(dt, nsteps, want_rhstest)
     return s.download(), rt
+
+
+def rhsRK(Q, rd, md, Re, BCTYPE, ops, flux_fun, inviscid_dissp, viscous_dissp, cns):
+    """``rhsQ, rhstest, rhstest_visc = rhsRK!(Q, rd, md, Re, BCTYPE, ops, flux, inviscid_dissp,
+    viscous_dissp, <work arrays>)`` of examples/CompressibleNS/dg2D_CNS_cavity_optimized.jl:955-972.
+
+    ``cns`` carries what the reference script keeps in globals / closures: ``mu, lam, Pr``
+    (:33-36, as passed to init_visc_fxn) and the wall node sets ``wall, lid, vlid, mapB`` (:139-147).
+    ``ops`` additionally holds rd's ``Pq, Vf, Dr, Ds`` (the reference unpacks them from ``rd``).
+    """
+    if flux_fun is not euler_fluxes:
+        raise NotImplementedError("only the entropy-conservative euler_fluxes is compiled into the kernels")
+    if (cns.Re, cns.bctype, bool(cns.inviscid_dissp), bool(cns.viscous_dissp)) != \
+            (Re, BCTYPE, bool(inviscid_dissp), bool(viscous_dissp)):
+        raise ValueError("rhsRK: Re/BCTYPE/dissipation flags disagree with the cns settings")
+    for n in ("Pq", "Vf", "Dr", "Ds"):
+        if not hasattr(ops, n):
+            setattr(ops, n, getattr(rd, n))
+    return _cached_solver(md, ops, cns).rhs(Q, True)

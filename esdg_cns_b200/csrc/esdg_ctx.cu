@@ -3,6 +3,7 @@
 #include "hex_fast.h"
 
 #include "kernels_generic.cuh"
+#include "kernels_cns.cuh"
 
 using namespace esdg;
 
@@ -81,6 +82,62 @@ int launch_rhs(esdg_ctx* ctx, const double* Qsrc, int mode, double a, double b, 
     return ESDG_OK;
 }
 
+// ---- compressible Navier-Stokes path (kernels_cns.cuh) -----------------------------------------
+void fill_cns(esdg_ctx* ctx, CnsParams& P, const double* Qsrc) {
+    fill_params(ctx, P.g);
+    P.g.Q = Qsrc;
+    const CnsState& c = ctx->cns;
+    P.Pq = c.Pq.view(); P.Vf = c.Vf.view(); P.Dr = c.Dr.view(); P.Ds = c.Ds.view();
+    P.bc = c.bc;
+    P.vlid = c.vlid_dev;
+    P.bctype = c.bctype;
+    P.viscous_dissp = c.viscous_dissp;
+    P.lam = -c.lambda;                                  // `let lambda=-lambda` (dg2D_CNS_cavity_optimized.jl:614)
+    P.mu = c.mu; P.Pr = c.Pr; P.Re = c.Re;
+    const double theta = 1.0 / 0.3 / 0.3 / 1.4 / 0.4;   // :189 (`1.0/0.3^2/1.4/0.4`, hard-coded in the reference)
+    P.inv_theta2 = 2.0 / theta;
+    P.sig = c.sig;
+    P.sig_stride = (long long)ctx->d.Ns * ctx->d.K;
+    P.sig_tr = c.sig_tr;
+    P.partial_visc = c.partial_visc;
+    P.partial_vrhs = c.partial_vrhs;
+}
+
+int cns_traces(esdg_ctx* ctx, const double* Qsrc) {
+    CnsParams P;
+    fill_cns(ctx, P, Qsrc);
+    tick(ctx, "cns_traces");
+    k_cns_traces<<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(P);
+    tock(ctx);
+    CK(cudaGetLastError());
+    return ESDG_OK;
+}
+
+// sigma pass + rhs pass (the V traces of Qsrc must be valid)
+int cns_stage(esdg_ctx* ctx, const double* Qsrc, int mode, double a, double b, double dt, int want) {
+    CnsParams P;
+    fill_cns(ctx, P, Qsrc);
+    P.g.mode = mode;
+    P.g.rk_a = a; P.g.rk_b = b; P.g.dt = dt;
+    P.g.want_rhstest = want;
+    tick(ctx, "cns_sigma");
+    k_cns_sigma<<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(P);
+    tock(ctx);
+    CK(cudaGetLastError());
+    tick(ctx, "cns_rhs");
+    k_cns_rhs<<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(P);
+    tock(ctx);
+    CK(cudaGetLastError());
+    if (want) {
+        tick(ctx, "reduce_partials");
+        k_reduce_partials_cns<<<1, 256, 0, ctx->stream>>>(ctx->partials, ctx->cns.partial_vrhs, ctx->cns.partial_visc,
+                                                         grid_blocks(ctx), ctx->rhstest_dev);
+        tock(ctx);
+        CK(cudaGetLastError());
+    }
+    return ESDG_OK;
+}
+
 // ---- path selection: tensor-product hex kernels when the operators allow, else generic ----
 int total_partials(const esdg_ctx* ctx) {
     if (!ctx->hex) return grid_blocks(ctx);
@@ -102,6 +159,7 @@ int reduce_rhstest(esdg_ctx* ctx, bool split) {
 
 // traces (and whatever else the next rhs needs) of state Q
 int do_traces(esdg_ctx* ctx, const double* Q) {
+    if (ctx->cns.on) return cns_traces(ctx, Q);
     if (ctx->hex) return hexfast_traces(ctx, Q);
     return launch_traces(ctx, Q);
 }
@@ -111,6 +169,12 @@ int do_traces(esdg_ctx* ctx, const double* Q) {
 // its trace kernel).
 int do_stage(esdg_ctx* ctx, const double* Q, int mode, double a, double b, double dt, int want, int part) {
     int rc;
+    if (ctx->cns.on) {
+        if (part == ESDG_PART_INTERIOR) return ESDG_OK;
+        if ((rc = cns_stage(ctx, Q, mode, a, b, dt, want))) return rc;
+        if (mode == 1) return cns_traces(ctx, ctx->Q);
+        return ESDG_OK;
+    }
     if (ctx->hex) {
         if ((rc = hexfast_stage(ctx, Q, mode, a, b, dt, want, part))) return rc;
         if (want && part != ESDG_PART_BOUNDARY) return reduce_rhstest(ctx, part == ESDG_PART_INTERIOR);
@@ -202,7 +266,7 @@ int esdg_set_stream(esdg_ctx* ctx, void* s) {
 
 int esdg_set_operator(esdg_ctx* ctx, const char* name, const double* a, int64_t rows, int64_t cols) {
     if (!ctx || !name || !a || rows <= 0 || cols <= 0) return fail(ctx, ESDG_EINVAL, "esdg_set_operator: bad argument");
-    static const char* known[] = {"Ef", "Vq", "VhP", "Ph", "Lf", "Qrh", "Qsh", "Qth", "wq"};
+    static const char* known[] = {"Ef", "Vq", "VhP", "Ph", "Lf", "Qrh", "Qsh", "Qth", "wq", "Pq", "Vf", "Dr", "Ds"};
     bool ok = false;
     for (const char* k : known) ok = ok || !strcmp(k, name);
     if (!ok) return fail(ctx, ESDG_EINVAL, std::string("esdg_set_operator: unknown operator ") + name);
@@ -235,6 +299,113 @@ int esdg_set_maps(esdg_ctx* ctx, const int64_t* mapP, int64_t n) {
     if (n != (int64_t)ctx->d.Nfq * ctx->d.K) return fail(ctx, ESDG_EINVAL, "esdg_set_maps: mapP must hold Nfq*K entries");
     ctx->mapP_host.assign(mapP, mapP + n);
     ctx->finalized = false;
+    return ESDG_OK;
+}
+
+int esdg_set_viscosity(esdg_ctx* ctx, double lambda, double mu, double Pr, double Re, int viscous_dissp) {
+    if (!ctx) return ESDG_EINVAL;
+    if (ctx->d.dim != 2 || ctx->d.collocated)
+        return fail(ctx, ESDG_EINVAL, "esdg_set_viscosity: the CNS path is 2D with the Vq/Pq projection (desc.dim = 2, collocated = 0)");
+    if (!(mu >= 0.0) || !(Pr > 0.0) || !(Re > 0.0)) return fail(ctx, ESDG_EINVAL, "esdg_set_viscosity: need mu >= 0, Pr > 0, Re > 0");
+    CnsState& c = ctx->cns;
+    c.on = true;
+    c.lambda = lambda; c.mu = mu; c.Pr = Pr; c.Re = Re;
+    c.viscous_dissp = viscous_dissp != 0;
+    ctx->finalized = false;
+    return ESDG_OK;
+}
+
+int esdg_set_wall_bc(esdg_ctx* ctx, int bctype, const int64_t* wall_idx, int64_t nwall, const int64_t* lid_idx,
+                     const double* vlid, int64_t nlid) {
+    if (!ctx) return ESDG_EINVAL;
+    if (bctype < 1 || bctype > 3) return fail(ctx, ESDG_EINVAL, "esdg_set_wall_bc: BCTYPE must be 1 (adiabatic), 2 (isothermal) or 3 (slip)");
+    if (nwall < 0 || nlid < 0 || (nwall > 0 && !wall_idx) || (nlid > 0 && (!lid_idx || !vlid)))
+        return fail(ctx, ESDG_EINVAL, "esdg_set_wall_bc: bad argument");
+    CnsState& c = ctx->cns;
+    c.bctype = bctype;
+    c.wall.assign(wall_idx, wall_idx + nwall);
+    c.lid.assign(lid_idx, lid_idx + nlid);
+    c.vlid.assign(vlid, vlid + nlid);
+    ctx->finalized = false;
+    return ESDG_OK;
+}
+
+int esdg_set_boundary_nodes(esdg_ctx* ctx, const int64_t* mapB, int64_t nB) {
+    if (!ctx || nB < 0 || (nB > 0 && !mapB)) return fail(ctx, ESDG_EINVAL, "esdg_set_boundary_nodes: bad argument");
+    ctx->cns.mapB.assign(mapB, mapB + nB);
+    ctx->cns.have_mapB = true;
+    ctx->finalized = false;
+    return ESDG_OK;
+}
+
+// CNS part of esdg_finalize: extra operators, BC tables, sigma storage, launch shape.
+static int finalize_cns(esdg_ctx* ctx) {
+    const esdg_desc& d = ctx->d;
+    CnsState& c = ctx->cns;
+    const int Nh = ctx->Nh;
+    if (d.n_halo != 0) return fail(ctx, ESDG_EINVAL, "esdg_finalize: the CNS path runs on one GPU per context (n_halo must be 0)");
+    struct { const char* n; int64_t r, cl; DevEll* out; } need[4] = {
+        {"Pq", d.Ns, d.Nq, &c.Pq}, {"Vf", d.Nfq, d.Ns, &c.Vf}, {"Dr", d.Ns, d.Ns, &c.Dr}, {"Ds", d.Ns, d.Ns, &c.Ds}};
+    int rc;
+    for (auto& q : need) {
+        const HostMat* m = find(ctx->ops, q.n);
+        if (!m || m->rows != q.r || m->cols != q.cl)
+            return fail(ctx, ESDG_EINVAL, std::string("esdg_finalize: CNS operator missing or mis-sized: ") + q.n);
+        if ((rc = build_ell(ctx, *m, 0.0, q.out))) return rc;
+    }
+    const int64_t ntr = (int64_t)d.Nfq * d.K;
+    std::vector<unsigned char> bc((size_t)ntr, 0);
+    std::vector<double> vl;
+    auto mark = [&](const std::vector<int64_t>& idx, unsigned char bits, bool exclusive) -> bool {
+        for (int64_t v1 : idx) {
+            const int64_t v = v1 - 1;
+            if (v < 0 || v >= ntr) return false;
+            if (exclusive && (bc[(size_t)v] & 3)) return false;
+            bc[(size_t)v] |= bits;
+        }
+        return true;
+    };
+    if (!mark(c.wall, 1, true) || !mark(c.lid, 2, true))
+        return fail(ctx, ESDG_EINVAL, "esdg_finalize: wall/lid index out of range or listed twice");
+    if (!c.lid.empty()) {
+        vl.assign((size_t)ntr, 0.0);
+        for (size_t i = 0; i < c.lid.size(); ++i) vl[(size_t)(c.lid[i] - 1)] = c.vlid[i];
+    }
+    if (c.have_mapB) {
+        if (!mark(c.mapB, 4, false)) return fail(ctx, ESDG_EINVAL, "esdg_finalize: mapB index out of range");
+    } else {
+        for (auto& b : bc) if (b & 3) b |= 4;           // default: md.mapB = wall + lid (cavity, :139-147)
+    }
+    // a wall/lid node must be a boundary node of the mesh: mapP == mapM there (SetupDG.jl:294-298)
+    for (int64_t i = 0; i < ntr; ++i)
+        if ((bc[(size_t)i] & 3) && ctx->mapP_host[(size_t)i] - 1 != i)
+            return fail(ctx, ESDG_EINVAL, "esdg_finalize: wall/lid node is not a boundary node (mapP != mapM)");
+    if ((rc = dev_upload(ctx, &c.bc, bc))) return rc;
+    if (!vl.empty() && (rc = dev_upload(ctx, &c.vlid_dev, vl))) return rc;
+    if ((rc = dev_alloc(ctx, &c.sig, (size_t)6 * d.Ns * d.K))) return rc;
+    if ((rc = dev_alloc(ctx, &c.sig_tr, (size_t)6 * ctx->trace_stride))) return rc;
+    // launch shape: generic modal block + CNS extras
+    int maxsm = 0;
+    CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    auto bytes = [&](int EB) {
+        return generic_smem_bytes(2, EB, d.Ns, d.Nq, d.Nfq, Nh, 0) + cns_extra_doubles(EB, d.Ns, d.Nq, d.Nfq) * sizeof(double);
+    };
+    int EB = std::min(16, std::max(1, ESDG_GENERIC_MAX_THREADS / Nh));
+    while (EB > 1 && bytes(EB) > (size_t)maxsm / 2) --EB;
+    if (bytes(EB) > (size_t)maxsm) return fail(ctx, ESDG_EINVAL, "esdg_finalize: element too large for shared memory (CNS)");
+    ctx->EB = EB;
+    ctx->smem_bytes = bytes(EB);
+    ctx->threads = std::min(ESDG_GENERIC_MAX_THREADS, ((EB * Nh + 31) / 32) * 32);
+    CK(cudaFuncSetAttribute(k_cns_traces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+    CK(cudaFuncSetAttribute(k_cns_sigma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+    CK(cudaFuncSetAttribute(k_cns_rhs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+    const size_t nb = (size_t)grid_blocks(ctx);
+    if ((rc = dev_alloc(ctx, &c.partial_visc, nb))) return rc;
+    if ((rc = dev_alloc(ctx, &c.partial_vrhs, nb))) return rc;
+    CK(cudaMemset(c.partial_visc, 0, nb * sizeof(double)));
+    CK(cudaMemset(c.partial_vrhs, 0, nb * sizeof(double)));
+    CK(cudaMemset(c.sig, 0, (size_t)6 * d.Ns * d.K * sizeof(double)));
+    CK(cudaMemset(c.sig_tr, 0, (size_t)6 * ctx->trace_stride * sizeof(double)));
     return ESDG_OK;
 }
 
@@ -404,7 +575,12 @@ int esdg_finalize(esdg_ctx* ctx) {
     CK(cudaMemset(ctx->res, 0, nstate * sizeof(double)));
     CK(cudaMemset(ctx->traces, 0, (size_t)NF * ctx->trace_stride * sizeof(double)));
     CK(cudaMemset(ctx->rhstest_dev, 0, 2 * sizeof(double)));
-    if ((rc = hexfast_try_create(ctx))) return rc;
+    if (ctx->cns.on) {
+        if ((rc = finalize_cns(ctx))) return rc;
+    } else if (!ctx->cns.wall.empty() || !ctx->cns.lid.empty()) {
+        return fail(ctx, ESDG_EINVAL, "esdg_finalize: wall BCs need the CNS path (call esdg_set_viscosity; mu = 0 gives Euler with walls)");
+    }
+    if (!ctx->cns.on && (rc = hexfast_try_create(ctx))) return rc;
     if (ctx->hex) {
         bool diag = true;
         for (int64_t e = 0; e < d.K && diag; ++e)
@@ -468,7 +644,10 @@ int esdg_rhs(esdg_ctx* ctx, const double* const* Q, double* const* rhs_out, int 
     double t[2] = {0, 0};
     if (compute_rhstest) CK(cudaMemcpyAsync(t, ctx->rhstest_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if ((rc = check_bad(ctx))) return rc;
-    if (rhstest) { rhstest[0] = t[0]; }
+    if (rhstest) {
+        rhstest[0] = t[0];
+        if (ctx->cns.on) rhstest[1] = t[1];              // rhstest_visc of rhsRK! (dg2D_CNS_cavity_optimized.jl:960-971)
+    }
     return ESDG_OK;
 }
 
@@ -587,6 +766,14 @@ int esdg_read_rhstest(esdg_ctx* ctx, double* rhstest) {
     int rc = require_ready(ctx, "esdg_read_rhstest");
     if (rc) return rc;
     CK(cudaMemcpyAsync(rhstest, ctx->rhstest_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return check_bad(ctx);
+}
+
+int esdg_read_rhstest_visc(esdg_ctx* ctx, double* rhstest_visc) {
+    int rc = require_ready(ctx, "esdg_read_rhstest_visc");
+    if (rc) return rc;
+    if (!ctx->cns.on) return fail(ctx, ESDG_EINVAL, "esdg_read_rhstest_visc: not a CNS context");
+    CK(cudaMemcpyAsync(rhstest_visc, ctx->rhstest_dev + 1, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     return check_bad(ctx);
 }
 

@@ -28,6 +28,21 @@ struct KernelTimer {
     cudaEvent_t a, b;
 };
 
+// Compressible Navier-Stokes extension (kernels_cns.cuh): settings given before esdg_finalize and
+// the device data built by it.
+struct CnsState {
+    bool on = false;                      // esdg_set_viscosity was called
+    double lambda = 0, mu = 0, Pr = 0, Re = 0;
+    int viscous_dissp = 0, bctype = 1;
+    std::vector<int64_t> wall, lid, mapB; // 1-based linear indices into Nfq x K (Julia)
+    std::vector<double> vlid;
+    bool have_mapB = false;
+    DevEll Pq, Vf, Dr, Ds;
+    unsigned char* bc = nullptr;
+    double* vlid_dev = nullptr;
+    double *sig = nullptr, *sig_tr = nullptr, *partial_visc = nullptr, *partial_vrhs = nullptr;
+};
+
 struct esdg_ctx {
     esdg_desc d{};
     int device = 0;
@@ -66,6 +81,7 @@ struct esdg_ctx {
 
     // specialised hex path (kernels_hex.cuh); null if the operators do not match
     struct HexFast* hex = nullptr;
+    CnsState cns;
     long long bnd_lo = 0, bnd_hi = 0;   // leading / trailing elements whose traces are sent to neighbours
     bool res_zero = true;
 

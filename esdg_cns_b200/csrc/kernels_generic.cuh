@@ -24,6 +24,7 @@ template <int DIM>
 struct GenericSmem {
     static constexpr int NF = DIM + 2;
     double *U, *V, *W, *Uf, *Fl, *QF, *VP, *R;
+    double* Vface = nullptr;              // optional [EB][NF][Nfq]: projected entropy variables at face points (CNS)
     __device__ GenericSmem(double* base, const GenericParams& p) {
         const int EB = p.EB;
         U = base;                         // [EB][NF][Ns]
@@ -105,6 +106,10 @@ __device__ __forceinline__ void project_batch(const GenericParams& p, GenericSme
                 // projected entropy variables at volume points are the rhstest weights (tri :180)
 #pragma unroll
                 for (int f = 0; f < NF; ++f) s.VP[(eb * NF + f) * p.Nq + r] = V[f];
+            }
+            if (s.Vface && r >= p.Nq) {
+#pragma unroll
+                for (int f = 0; f < NF; ++f) s.Vface[(eb * NF + f) * p.Nfq + (r - p.Nq)] = V[f];
             }
         }
         Prim<DIM> P;

@@ -147,6 +147,67 @@ def reference_hex(N, lf_scale=.25):
     return rd, ops
 
 
+def gll_1d(N):
+    """Gauss-Lobatto-Legendre points (the interpolation nodes of Basis2DQuad.nodes_2D, :77-81)."""
+    if N == 1:
+        return np.array([-1.0, 1.0])
+    inner = np.polynomial.legendre.Legendre.basis(N).deriv().roots()
+    return np.concatenate([[-1.0], np.sort(inner.real), [1.0]])
+
+
+def reference_quad_modal(N, lf_scale=.25):
+    """GLL-nodal quad element with Gauss quadrature and the Vq/Pq projection: ``init_reference_quad``
+    (src/SetupDG.jl:205-268) + the operator tuple of the CNS scripts
+    (dg2D_CNS_cavity_optimized.jl:61-89), built from 1D Lagrange pieces.  BASELINE config 3."""
+    n = N + 1
+    xg, wg = gauss_1d(N)
+    xl = gll_1d(N)
+    D1 = lagrange_deriv(xl)
+    Lq = lagrange_eval(xl, xg)                      # Gauss <- GLL
+    Lm, Lp = lagrange_eval(xl, -1.0)[0], lagrange_eval(xl, 1.0)[0]
+    I = np.eye(n)
+    # nodes k = a + n*b: r = xl[a] (fastest), s = xl[b]
+    r, s = np.tile(xl, n), np.repeat(xl, n)
+    Dr, Ds = np.kron(I, D1), np.kron(D1, I)
+    # volume quadrature q = i + n*j: s = xg[i] (fastest), r = xg[j]   (SetupDG.jl:244-246)
+    rq, sq = np.repeat(xg, n), np.tile(xg, n)
+    wq = np.repeat(wg, n) * np.tile(wg, n)
+
+    def interp(rr, ss):
+        A, B = lagrange_eval(xl, rr), lagrange_eval(xl, ss)     # [pt, a], [pt, b]
+        return (B[:, :, None] * A[:, None, :]).reshape(len(rr), n * n)   # column k = a + n*b
+
+    Vq = interp(rq, sq)
+    e, z = np.ones(n), np.zeros(n)
+    rf, sf = np.concatenate([xg, e, -xg, -e]), np.concatenate([-e, xg, e, -xg])   # CCW faces (:235-239)
+    wf = np.tile(wg, 4)
+    Vf = interp(rf, sf)
+    M = Vq.T @ (wq[:, None] * Vq)
+    Pq = np.linalg.solve(M, Vq.T * wq[None, :])
+    LIFT = np.linalg.solve(M, Vf.T * wf[None, :])
+    rd = SimpleNamespace(elem="quad", N=N, Nfaces=4, r=r, s=s, rq=rq, sq=sq, wq=wq, rf=rf, sf=sf, wf=wf,
+                         nrJ=np.concatenate([z, e, z, -e]), nsJ=np.concatenate([-e, z, e, z]),
+                         Dr=Dr, Ds=Ds, Vq=Vq, Pq=Pq, Vf=Vf, LIFT=LIFT, M=M)
+    Ef = Vf @ Pq
+    Qskew = _hybridize([Pq.T @ M @ Dr @ Pq, Pq.T @ M @ Ds @ Pq], Ef, wf, [rd.nrJ, rd.nsJ])
+    Vh = np.vstack([Vq, Vf])
+    ops = SimpleNamespace(elem="quad", N=N, Nfaces=4, wq=wq, Qskew=Qskew, Vh=Vh, Ph=np.linalg.solve(M, Vh.T),
+                          VhP=Vh @ Pq, Lf=LIFT, Vq=Vq, Pq=Pq, Vf=Vf, Dr=Dr, Ds=Ds, modal=True,
+                          volume_scale=2.0, lf_scale=lf_scale)
+    return rd, ops
+
+
+def cavity_bc_sets(md):
+    """``lid`` / ``wall`` node sets of the lid-driven cavity on [-1,1]^2
+    (dg2D_CNS_cavity_optimized.jl:139-147); 0-based linear indices into the Nfq x K face arrays."""
+    mp = md.mapP.reshape(-1, order="F")
+    mapB = np.nonzero(mp == np.arange(mp.size))[0]
+    yb = md.yf.reshape(-1, order="F")[mapB]
+    lid = mapB[np.abs(yb - 1) < 1e-12]
+    wall = mapB[np.abs(yb - 1) >= 1e-12]
+    return SimpleNamespace(lid=lid, wall=wall, vlid=np.ones(lid.size), mapB=mapB)
+
+
 # --------------------------------------------------------------------- meshes
 def uniform_quad_mesh_md(rd, Kx, Ky, domain=((-1.0, 1.0), (-1.0, 1.0)), periodic=(True, True)):
     """MeshData of a uniform Kx x Ky quad mesh (elements x-fastest, UniformQuadMesh.jl:37-44)."""
@@ -160,6 +221,11 @@ def uniform_quad_mesh_md(rd, Kx, Ky, domain=((-1.0, 1.0), (-1.0, 1.0)), periodic
     md = SimpleNamespace(K=K, dim=2)
     md.xq = (x0 + hx * ex)[None, :] + hx / 2 * (1 + rd.rq)[:, None]
     md.yq = (y0 + hy * ey)[None, :] + hy / 2 * (1 + rd.sq)[:, None]
+    md.xf = (x0 + hx * ex)[None, :] + hx / 2 * (1 + rd.rf)[:, None]
+    md.yf = (y0 + hy * ey)[None, :] + hy / 2 * (1 + rd.sf)[:, None]
+    if hasattr(rd, "r"):                     # interpolation nodes of a modal/nodal element
+        md.x = (x0 + hx * ex)[None, :] + hx / 2 * (1 + rd.r)[:, None]
+        md.y = (y0 + hy * ey)[None, :] + hy / 2 * (1 + rd.s)[:, None]
     one = np.ones((1, K))
     md.rxJ, md.sxJ, md.ryJ, md.syJ = hy / 2 * one, 0 * one, 0 * one, hx / 2 * one
     md.J = hx * hy / 4 * one

@@ -81,6 +81,8 @@ int esdg_set_stream(esdg_ctx* ctx, void* cuda_stream);
  *       "Lf"  (Ns x Nfq) quad/hex Lf (:78) or rd.LIFT (SetupDG.jl:192)
  *       "Qrh","Qsh","Qth" (Nh x Nh) skew hybridized SBP operators (:60-61)
  *       "wq"  (Nq x 1)   rd.wq  (only used for rhstest through wJq)
+ *       CNS path only (rd fields, src/SetupDG.jl:38-75): "Pq" (Ns x Nq), "Vf" (Nfq x Ns),
+ *       "Dr","Ds" (Ns x Ns); "Lf" is rd.LIFT
  * Sparse Julia matrices are passed densified (`Matrix(A)`); sparsity is re-detected
  * with the reference's drop tolerance 1e-12 (dg2D_euler_quad.jl:62-63). */
 int esdg_set_operator(esdg_ctx* ctx, const char* name, const double* colmajor, int64_t rows, int64_t cols);
@@ -95,6 +97,25 @@ int esdg_set_geometry(esdg_ctx* ctx, const char* name, const double* colmajor, i
 /* md.mapP (Nfq x K, 1-based linear index into an Nfq x (K [+halo]) array; SetupDG.jl:294-298). */
 int esdg_set_maps(esdg_ctx* ctx, const int64_t* mapP, int64_t n);
 
+/* ---- compressible Navier-Stokes (examples/CompressibleNS/dg2D_CNS_cavity_optimized.jl) ----------
+ * Calling esdg_set_viscosity before esdg_finalize turns the context into the CNS rhs
+ *     rhsQ, rhstest, rhstest_visc = rhsRK!(Q, rd, md, Re, BCTYPE, ops, flux, inviscid_dissp, viscous_dissp, ...)   (:955-972)
+ * = rhs_inviscid! (:447-528) + rhs_viscous! (BR1, :749-849).  2D, Vq/Pq projection (collocated = 0).
+ * lambda, mu, Pr are the arguments of init_visc_fxn (:613; lambda's sign is flipped inside exactly as
+ * the reference does, :614), Re scales the penalisation tau = -1/Re/v4 (:821), viscous_dissp is the
+ * script flag (:30).  inviscid_dissp (:29) maps to desc.lf_scale = .25 (on, :508) or 0 (off). */
+int esdg_set_viscosity(esdg_ctx* ctx, double lambda, double mu, double Pr, double Re, int viscous_dissp);
+/* Wall boundary conditions, init_BC_funs (:135-264).  bctype = BCTYPE (:27): 1 adiabatic no-slip,
+ * 2 isothermal, 3 slip/reflective.  wall_idx / lid_idx: 1-based linear indices into the Nfq x K face
+ * arrays (the `wall` and `lid` subsets of md.mapB, :139-140), vlid: lid speed per lid node (:147).
+ * The inviscid mirror state (:157-176), the entropy-variable BCs (:178-216) and the stress BCs
+ * (:218-262) are applied at these nodes. */
+int esdg_set_wall_bc(esdg_ctx* ctx, int bctype, const int64_t* wall_idx, int64_t nwall, const int64_t* lid_idx,
+                     const double* vlid, int64_t nlid);
+/* md.mapB (src/node_map_functions.jl:53): nodes where the penalisation switches to its wall form
+ * (:829-839).  Default when not called: wall + lid. */
+int esdg_set_boundary_nodes(esdg_ctx* ctx, const int64_t* mapB, int64_t nB);
+
 /* Validates that everything required by the descriptor was supplied, compresses the
  * operators and uploads them.  Must be called once before any hot call. */
 int esdg_finalize(esdg_ctx* ctx);
@@ -103,7 +124,8 @@ int esdg_finalize(esdg_ctx* ctx);
  * Q / rhs_out: arrays of Nfields HOST pointers, each Ns*K doubles (the Julia
  * Vector{Matrix{Float64}}).  Q == NULL evaluates the resident state.  Synchronous.
  * rhstest[0] receives sum_f sum(wJq .* VU[f] .* rhs[f]) when compute_rhstest != 0
- * (dg2D_euler_quad.jl:186-191). */
+ * (dg2D_euler_quad.jl:186-191).  CNS contexts: rhstest must hold 2 doubles, (rhstest, rhstest_visc)
+ * of rhsRK! (dg2D_CNS_cavity_optimized.jl:960-971). */
 int esdg_rhs(esdg_ctx* ctx, const double* const* Q, double* const* rhs_out, int compute_rhstest, double* rhstest);
 
 /* State residency (Q and the LSRK register resQ live in HBM between calls). */
@@ -141,6 +163,7 @@ int esdg_stage_update(esdg_ctx* ctx, int stage /*0..4*/, double dt, int compute_
  * 7 = rho,u,v,w,beta,log rho,log beta of the tensor-product hex path) */
 int esdg_trace_planes(esdg_ctx* ctx);
 int esdg_read_rhstest(esdg_ctx* ctx, double* rhstest);
+int esdg_read_rhstest_visc(esdg_ctx* ctx, double* rhstest_visc);   /* CNS contexts */
 
 /* ---- introspection ---------------------------------------------------------- */
 int64_t esdg_kernel_launches(const esdg_ctx* ctx);          /* kernels launched so far      */

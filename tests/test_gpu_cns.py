@@ -1,0 +1,138 @@
+"""GPU parity of the compressible Navier-Stokes path (kernels_cns.cuh, through the C ABI) against
+the oracle's restatement of dg2D_CNS_cavity_optimized.jl: rhsRK! = rhs_inviscid! + rhs_viscous!
+with the three wall-BC types, both dissipation switches, on triangles (the reference's own element)
+and on quads (BASELINE config 3).  Tolerance 1e-12 relative (north star) or 4x the oracle's own
+1-ulp-log noise floor where the reference formula is conditioned worse (helpers.parity_tol)."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from helpers import relerr, parity_tol
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _state(md):
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_golden import cns_state
+    return cns_state(md)
+
+
+def _cns_settings(par, bc, md):
+    return SimpleNamespace(Re=par.Re, mu=par.mu, lam=par.lam, Pr=par.Pr, bctype=par.bctype,
+                           inviscid_dissp=par.inviscid_dissp, viscous_dissp=par.viscous_dissp,
+                           wall=bc.wall, lid=bc.lid, vlid=bc.vlid, mapB=md.mapB)
+
+
+@pytest.mark.parametrize("elem,N,K1D", [("quad", 3, 4), ("tri", 3, 4), ("tri", 2, 3), ("quad", 2, 5)])
+@pytest.mark.parametrize("bctype", [1, 2, 3])
+@pytest.mark.parametrize("dissp", [(True, True), (False, False)])
+def test_cns_rhs_matches_oracle(elem, N, K1D, bctype, dissp):
+    from oracle import cns
+    from esdg_cns_b200 import api
+    rd, md, ops, bc, _ = cns.setup_cavity(elem, N, K1D)
+    Q = _state(md)
+    par = cns.cavity_params(bctype=bctype, inviscid_dissp=dissp[0], viscous_dissp=dissp[1])
+    ref, rt_ref, rtv_ref = cns.rhsRK(Q, md, ops, bc, par)
+    s = api.Solver(md, ops, cns=_cns_settings(par, bc, md))
+    out, rt, rtv = s.rhs(Q, True)
+    tol = parity_tol(lambda: cns.rhsRK(Q, md, ops, bc, par)[0], ref)
+    err = relerr(out, ref)
+    print(f"cns {elem} N={N} K1D={K1D} bc={bctype} dissp={dissp}: relerr {err:.2e} tol {tol:.2e} "
+          f"rhstest {rt:.6e}/{rt_ref:.6e} visc {rtv:.6e}/{rtv_ref:.6e}")
+    assert err < tol
+    assert abs(rt - rt_ref) < 1e-11 * max(1.0, abs(rt_ref))
+    assert abs(rtv - rtv_ref) < 1e-11 * max(1.0, abs(rtv_ref))
+    assert rtv <= 1e-12
+
+
+def test_cns_golden_fixture_and_reference_call_shape():
+    """Committed fixture through the reference-shaped entry point rhsRK(Q, rd, md, Re, BCTYPE, ops, ...)."""
+    from oracle import cns
+    from esdg_cns_b200 import api
+    g = np.load(os.path.join(GOLD, "cns_quad_N3_4x4_cavity.npz"))
+    rd, md, ops, bc, _ = cns.setup_cavity("quad", 3, 4)
+    par = cns.cavity_params()
+    st = _cns_settings(par, bc, md)
+    out, rt, rtv = api.rhsRK(list(g["Q"]), rd, md, par.Re, par.bctype, ops, api.euler_fluxes, True, True, st)
+    Q = list(g["Q"])
+    tol = parity_tol(lambda: cns.rhsRK(Q, md, ops, bc, par)[0], list(g["rhs"]))
+    assert relerr(out, list(g["rhs"])) < tol
+    assert abs(rt - float(g["rhstest"])) < 1e-12 and abs(rtv - float(g["rhstest_visc"])) < 1e-12
+
+
+def test_cns_cavity_at_rest_and_package_setup():
+    """Config 3 initial condition (fluid at rest, moving lid) with operators from esdg_cns_b200.setup_dg."""
+    from oracle import cns
+    from esdg_cns_b200 import api, setup_dg as SD
+    rd, md, ops, bc, Q = cns.setup_cavity("quad", 3, 6)
+    par = cns.cavity_params()
+    ref, rt_ref, rtv_ref = cns.rhsRK(Q, md, ops, bc, par)
+    prd, pops = SD.reference_quad_modal(3)
+    pmd = SD.uniform_quad_mesh_md(prd, 6, 6, periodic=(False, False))
+    pbc = SD.cavity_bc_sets(pmd)
+    st = SimpleNamespace(Re=par.Re, mu=par.mu, lam=par.lam, Pr=par.Pr, bctype=1, inviscid_dissp=True,
+                         viscous_dissp=True, wall=pbc.wall, lid=pbc.lid, vlid=pbc.vlid, mapB=pbc.mapB)
+    s = api.Solver(pmd, pops, cns=st)
+    out, rt, rtv = s.rhs(Q, True)
+    # a uniform state is all cancellation: the oracle's own residual in the lower half of the cavity is
+    # 1e-11 (tests/test_oracle_cns.py), so round-off differences of that size are the floor here
+    assert relerr(out, ref) < 1e-10
+    assert abs(rt - rt_ref) < 1e-12 and abs(rtv - rtv_ref) < 1e-12
+
+
+@pytest.mark.parametrize("elem", ["quad", "tri"])
+def test_cns_lsrk_steps_match_oracle(elem):
+    from oracle import cns, solvers as SV
+    from esdg_cns_b200 import api
+    N, K1D = 3, 4
+    rd, md, ops, bc, _ = cns.setup_cavity(elem, N, K1D)
+    Q = _state(md)
+    par = cns.cavity_params()
+    dt = .5 * (2 / K1D) / ((N + 1) * (N + 2) / 2)             # :39-42
+    Qo, res = [q.copy() for q in Q], [np.zeros_like(q) for q in Q]
+
+    def f(q, want):
+        r, rt, _ = cns.rhsRK(q, md, ops, bc, par)
+        return r, rt
+    for _ in range(2):
+        Qo, res, rto = SV.lsrk45_step(Qo, res, dt, f)
+    s = api.Solver(md, ops, cns=_cns_settings(par, bc, md))
+    s.upload(Q)
+    rtg = s.lsrk45(dt, 2, want_rhstest=True)
+    Qg = s.download()
+    err = relerr(Qg, Qo)
+    print(f"cns {elem} lsrk x2: state relerr {err:.2e}, rhstest {rtg:.6e} vs {rto:.6e}, visc {s.read_rhstest_visc():.3e}")
+    assert err < 1e-11           # rhs parity (<= 2e-10, see above) x dt x 10 stages, relative to the state
+    assert abs(rtg - rto) < 1e-11 * max(1.0, abs(rto))
+
+
+def test_cns_mu_zero_periodic_equals_euler_tri_path():
+    """No walls, mu = 0, no penalisation: the CNS kernels reproduce the Euler tri rhs (dg2D_euler_tri.jl)."""
+    from oracle import cns, solvers as SV
+    from esdg_cns_b200 import api
+    rd, md, ops_e, Q = SV.setup_tri_vortex(3, 4, 4)
+    ref, _ = SV.rhs_tri(Q, md, ops_e, rd, .25, False)
+    ops = cns.build_cns_ops(rd)
+    st = SimpleNamespace(Re=1000.0, mu=0.0, lam=0.0, Pr=.71, bctype=1, inviscid_dissp=True, viscous_dissp=False,
+                         wall=[], lid=[], vlid=[], mapB=[])
+    s = api.Solver(md, ops, cns=st)
+    out, rt, rtv = s.rhs(Q, True)
+    assert relerr(out, ref) < parity_tol(lambda: SV.rhs_tri(Q, md, ops_e, rd, .25, False)[0], ref)
+    assert rtv == 0.0
+
+
+def test_cns_bad_wall_node_is_rejected():
+    from oracle import cns
+    from esdg_cns_b200 import api, _lib
+    rd, md, ops, bc, Q = cns.setup_cavity("quad", 2, 3)
+    par = cns.cavity_params()
+    st = _cns_settings(par, bc, md)
+    interior = np.setdiff1d(np.arange(md.mapP.size), md.mapB)[:1]
+    st.wall = np.concatenate([bc.wall, interior])
+    with pytest.raises(_lib.EsdgError):
+        api.Solver(md, ops, cns=st)

@@ -56,3 +56,25 @@ def test_nonperiodic_boundary_maps_to_itself():
     md = SD.uniform_hex_mesh_md(prd, (2, 2, 2), periodic=(False, True, True))
     self_idx = np.arange(md.mapP.size).reshape(md.mapP.shape, order="F")
     assert (md.mapP == self_idx).sum() == 2 * 4 * 4    # two x-boundaries, 4 faces each, 4 points per face
+
+
+def test_modal_quad_and_cavity_sets_match_oracle():
+    """reference_quad_modal (tensor-product restatement of init_reference_quad + the CNS operator
+    tuple) and the cavity boundary sets against the oracle's literal SetupDG restatement."""
+    from oracle import cns
+    for N in (2, 3):
+        prd, pops = SD.reference_quad_modal(N)
+        rd, md, ops, bc, _ = cns.setup_cavity("quad", N, 3)
+        for n in ("r", "s", "rq", "sq", "wq", "rf", "sf", "wf", "Dr", "Ds", "Vq", "Pq", "Vf", "LIFT"):
+            assert np.abs(getattr(prd, n) - getattr(rd, n)).max() < 1e-12, n
+        for n in ("Ph", "VhP", "Lf"):
+            assert np.abs(getattr(pops, n) - getattr(ops, n)).max() < 1e-11, n
+        for a, b in zip(pops.Qskew, ops.Qskew):
+            assert np.abs(a - b).max() < 1e-13
+        pmd = SD.uniform_quad_mesh_md(prd, 3, 3, periodic=(False, False))
+        assert np.array_equal(pmd.mapP, md.mapP)
+        assert np.abs(pmd.x - md.x).max() < 1e-14 and np.abs(pmd.yf - md.yf).max() < 1e-14
+        pbc = SD.cavity_bc_sets(pmd)
+        assert np.array_equal(np.sort(pbc.lid), np.sort(bc.lid))
+        assert np.array_equal(np.sort(pbc.wall), np.sort(bc.wall))
+        assert np.array_equal(np.sort(pbc.mapB), np.sort(md.mapB))
