@@ -3,6 +3,7 @@
 
 #include "ctx_util.h"
 #include "kernels_hex.cuh"
+#include "kernels_hex_line.cuh"
 
 using namespace esdg;
 using namespace esdg_host;
@@ -103,18 +104,35 @@ void fill_hex_params(esdg_ctx* ctx, HexParams& p) {
     std::memcpy(p.lm, h->lm, sizeof p.lm);
     std::memcpy(p.lp, h->lp, sizeof p.lp);
     std::memcpy(p.w, h->w, sizeof p.w);
+    for (int a = 0; a < 8; ++a) {
+        p.lmw[a] = a < n ? h->lm[a] / h->w[a] : 0.0;
+        p.lpw[a] = a < n ? h->lp[a] / h->w[a] : 0.0;
+    }
 }
 
 template <int n>
 int set_attrs(esdg_ctx* ctx) {
     using D = HexDims<n>;
+    using LD = LineDims<n>;
     HexFast* h = ctx->hex;
-    h->EB = D::EB;
-    h->threads = D::THREADS;
-    h->smem_stage = (size_t)D::SMEM_DOUBLES * sizeof(double);
+    const char* kv = getenv("ESDG_HEX_KERNEL");          // "node": the node-per-thread kernel (comparison runs)
+    h->line = !(kv && !strcmp(kv, "node"));
+    h->EB_tr = D::EB;
+    h->threads_tr = D::THREADS;
     h->smem_traces = (size_t)(D::EB * 5 * D::Nq + 2 * n) * sizeof(double);
-    CK(cudaFuncSetAttribute(k_hex_stage<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage));
-    CK(cudaFuncSetAttribute(k_hex_stage<n, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage));
+    if (h->line) {
+        h->EB = LD::EB;
+        h->threads = LD::THREADS;
+        h->smem_stage = (size_t)LD::SMEM_DOUBLES * sizeof(double);
+        CK(cudaFuncSetAttribute(k_hex_stage_line<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage));
+        CK(cudaFuncSetAttribute(k_hex_stage_line<n, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage));
+    } else {
+        h->EB = D::EB;
+        h->threads = D::THREADS;
+        h->smem_stage = (size_t)D::SMEM_DOUBLES * sizeof(double);
+        CK(cudaFuncSetAttribute(k_hex_stage<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage));
+        CK(cudaFuncSetAttribute(k_hex_stage<n, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage));
+    }
     CK(cudaFuncSetAttribute(k_hex_traces<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_traces));
     return ESDG_OK;
 }
@@ -125,9 +143,9 @@ int launch_traces_n(esdg_ctx* ctx, const double* Q) {
     HexParams p;
     fill_hex_params<n>(ctx, p);
     p.Q = Q;
-    const int blocks = (int)((ctx->d.K + h->EB - 1) / h->EB);
+    const int blocks = (int)((ctx->d.K + h->EB_tr - 1) / h->EB_tr);
     tick(ctx, "hex_traces");
-    k_hex_traces<n><<<blocks, h->threads, h->smem_traces, ctx->stream>>>(p);
+    k_hex_traces<n><<<blocks, h->threads_tr, h->smem_traces, ctx->stream>>>(p);
     tock(ctx);
     CK(cudaGetLastError());
     return ESDG_OK;
@@ -137,7 +155,12 @@ template <int n>
 int launch_stage_n(esdg_ctx* ctx, const HexParams& p, int blocks) {
     HexFast* h = ctx->hex;
     tick(ctx, "hex_stage");
-    if (h->diag)
+    if (h->line) {
+        if (h->diag)
+            k_hex_stage_line<n, true><<<blocks, h->threads, h->smem_stage, ctx->stream>>>(p);
+        else
+            k_hex_stage_line<n, false><<<blocks, h->threads, h->smem_stage, ctx->stream>>>(p);
+    } else if (h->diag)
         k_hex_stage<n, true><<<blocks, h->threads, h->smem_stage, ctx->stream>>>(p);
     else
         k_hex_stage<n, false><<<blocks, h->threads, h->smem_stage, ctx->stream>>>(p);
@@ -338,3 +361,13 @@ extern "C" int esdg_debug_log_exp(int device, const double* x, int64_t n, double
     cudaFree(dx); cudaFree(dl); cudaFree(de);
     return cudaGetLastError() == cudaSuccess ? ESDG_OK : ESDG_ECUDA;
 }
+
+#ifdef ESDG_PHASE_TIMING
+// debug build: read and clear the per-phase cycle counters of k_hex_stage_line
+extern "C" int esdg_debug_phase_cycles(unsigned long long* out16) {
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyFromSymbol(out16, g_phase_cycles, sizeof z) != cudaSuccess) return ESDG_ECUDA;
+    cudaMemcpyToSymbol(g_phase_cycles, z, sizeof z);
+    return ESDG_OK;
+}
+#endif

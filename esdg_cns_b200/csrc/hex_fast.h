@@ -13,7 +13,9 @@ struct HexFast {
     int prod = 0;              // buffer most recently produced (pack/unpack act on it)
     int cons = 0;              // buffer the running stage consumes
     size_t smem_stage = 0, smem_traces = 0;
-    int threads = 0, EB = 1;
+    int threads = 0, EB = 1;           // stage kernel launch shape
+    int threads_tr = 0, EB_tr = 1;     // k_hex_traces launch shape
+    bool line = true;                  // line-per-thread stage kernel (kernels_hex_line.cuh); false: node-per-thread
 };
 
 enum { ESDG_PART_ALL = 0, ESDG_PART_BOUNDARY = 1, ESDG_PART_INTERIOR = 2 };

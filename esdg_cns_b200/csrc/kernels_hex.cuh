@@ -50,6 +50,7 @@ struct HexParams {
     double* partial;
     int* bad;
     double T[64], lm[8], lp[8], w[8];
+    double lmw[8], lpw[8];   // lm[a]/w[a], lp[a]/w[a]
 };
 
 template <int n>

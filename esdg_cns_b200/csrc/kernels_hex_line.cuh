@@ -1,0 +1,730 @@
+// Tensor-product hex stage kernel, LINE-PER-THREAD flux differencing.
+//
+// Same fused stage as k_hex_stage (kernels_hex.cuh: surface + volume + lift + LSRK + next traces,
+// examples/dg3D_euler_hex.jl:167-222 + dg2D_euler_quad.jl:198-207) with a different work
+// decomposition of the dominant phase.  The hybridized SBP operator of a Gauss-collocated hex
+// couples a volume node only to the nodes of its three grid lines and to the two face points
+// each line ends in, so the Hadamard sum  sum_j Q_ij o F(u_i,u_j)  (dg3D_euler_hex.jl:122-164)
+// splits into 3*n^2 independent LINE problems per element:
+//     n volume nodes + 2 face nodes  ->  n(n-1)/2 + 2n unordered pairs.
+// One thread owns one line: it loads the n+2 nodes ONCE into registers, evaluates every unordered
+// pair exactly once (the symmetric loop of CompressibleNS/dg2D_CNS_cavity_optimized.jl:326-347),
+// keeps all n*5 + 2*5 accumulators in registers and writes each result once.  Compared with the
+// node-per-thread kernel this removes the shared-memory exchange of pair fluxes, all per-pair
+// index arithmetic (the pair table is compile-time; T[a][b] are constant-bank operands of the
+// DFMAs) and 4 of the 9 block barriers.  Every phase processes TWO independent items per thread
+// statement-interleaved (vecmath.cuh), because occupancy is 2.5 warps per scheduler and the FP64
+// pipe must be fed from instruction-level parallelism.
+//
+// Phases per CTA (EB elements):
+//   0  cp.async: Q, LSRK register, log stash, own traces, exterior traces (mapP gather), geometry
+//   A  volume primitives (rho, u/2, beta) -> shared
+//   B  surface flux F_EC(M,P).nJ - LFc (U+ - U)                       dg3D_euler_hex.jl:182-197
+//   C  line problems; face rows get  flux* -/+ sum_a l[a] F(a,face)   (Ph / Lf as 1-D sweeps)
+//   E  rhs = -(sum_d acc_d + lift)/J ; rhstest ; res = a res + dt rhs ; Q += b res
+//   F  entropy projection of the new state -> traces + log stash for the next stage   (:175-178)
+#pragma once
+#include "kernels_hex.cuh"
+#include "vecmath.cuh"
+
+namespace esdg {
+
+#ifdef ESDG_PHASE_TIMING   // debug build only: per-phase cycle counts summed over CTAs (thread 0 of each CTA)
+__device__ unsigned long long g_phase_cycles[16];
+#define PHASE_MARK(k)                                                                      \
+    do {                                                                                   \
+        if (threadIdx.x == 0) {                                                            \
+            const long long t_ = clock64();                                                \
+            atomicAdd(&g_phase_cycles[k], (unsigned long long)(t_ - t_phase));             \
+            t_phase = t_;                                                                  \
+        }                                                                                  \
+    } while (0)
+#else
+#define PHASE_MARK(k)
+#endif
+
+// ---- TMA bulk copy (cp.async.bulk, completion on an mbarrier): one instruction moves a whole plane ----
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(double* smem_dst, const double* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
+template <int n>
+struct LineDims {
+    static constexpr int Nq = n * n * n, nfp = n * n, Nfq = 6 * nfp, Nh = Nq + Nfq, NL = 3 * nfp;
+#ifndef ESDG_LINE_EB5
+#define ESDG_LINE_EB5 2
+#endif
+    static constexpr int EB = n == 5 ? ESDG_LINE_EB5 : (n == 4 ? 2 : (n == 3 ? 4 : 8));
+    static constexpr int THREADS = ((EB * NL + 31) / 32) * 32;
+    static constexpr int MINB = (n == 5 && ESDG_LINE_EB5 == 2) ? 2 : 4;   // CTAs per SM the register budget is sized for
+    static constexpr int EN = EB * Nq, EF = EB * Nfq;
+    static constexpr int TAB = 5 * n + EB * 34;
+    // WV[7][EN] WF[7][EF] P[7][EF] A[15][EN] Q[5][EN] R[5][EN]
+    static constexpr int SMEM_DOUBLES = 7 * EN + 14 * EF + 15 * EN + 10 * EN + TAB;
+};
+
+// unordered pairs (a,b), a < b, of one line in a fixed order
+template <int n>
+struct PairTab {
+    static constexpr int NP = n * (n - 1) / 2;
+    int a[NP > 0 ? NP : 1], b[NP > 0 ? NP : 1];
+    constexpr PairTab() : a(), b() {
+        int k = 0;
+        for (int i = 0; i < n; ++i)
+            for (int j = i + 1; j < n; ++j) { a[k] = i; b[k] = j; ++k; }
+    }
+};
+
+template <int W>
+struct NodeV {
+    VD<W> rho, u[3], beta, lr, lb;
+};
+
+template <int W>
+__device__ __forceinline__ void set_lane(NodeV<W>& d, int q, const Node& s) {
+    d.rho[q] = s.rho; d.u[0][q] = s.u[0]; d.u[1][q] = s.u[1]; d.u[2][q] = s.u[2];
+    d.beta[q] = s.beta; d.lr[q] = s.lr; d.lb[q] = s.lb;
+}
+
+// pair_flux (kernels_hex.cuh) on W independent pairs: EC flux (euler_fluxes.jl:51-89, logmean.jl:14-28)
+// contracted with g; one reciprocal per pair serves rholog, 1/betalog and pa.
+template <int W, bool DIAG>
+__device__ __forceinline__ void pair_flux_v(const NodeV<W>& A, const NodeV<W>& B, const VD<W>* g, double c_igm, VD<W>* F) {
+    const VD<W> dar = B.rho - A.rho, hr = .5 * (A.rho + B.rho);
+    const VD<W> dab = B.beta - A.beta, sb = A.beta + B.beta, hb = .5 * sb;
+    const VB<W> tr = vlt(vabs(dar), 1e-4 * hr), tb = vlt(vabs(dab), 1e-4 * hb);
+    const VD<W> X = vsel(tr, hr, B.lr - A.lr);
+    const VD<W> Y = vsel(tb, hb, dab);
+    const VD<W> XY = X * Y;
+    const VD<W> R = vrcp(XY * sb);
+    const VD<W> iX = R * (Y * sb), iY = R * (X * sb), iZ = R * XY;
+    const VD<W> qr = dar * iX;                     // f (Taylor branch) or the log mean itself
+    const VD<W> fb = dab * iY;
+    const VD<W> vr = qr * qr, vb = fb * fb;
+    const VD<W> rholog = vsel(tr, hr * vfma(vr, vfma(vr, vfma(vr, 0.026038857142857, -.0512), -.2), 1.0), qr);
+    const VD<W> xb = vb * vfma(vb, vfma(vb, 0.026038857142857, -.0512), -.2);
+    const VD<W> ibl = iY * vsel(tb, 1.0 - xb, B.lb - A.lb);   // 1/betalog
+    const VD<W> pa = hr * iZ;                                  // rhoavg/(betaL+betaR)
+    VD<W> uavg[3], unorm, un;
+    uavg[0] = A.u[0] + B.u[0];                                 // Node.u holds HALF velocities
+    uavg[1] = A.u[1] + B.u[1];
+    uavg[2] = A.u[2] + B.u[2];
+    unorm = A.u[0] * B.u[0];
+    unorm = vfma(A.u[1], B.u[1], unorm);
+    unorm = vfma(A.u[2], B.u[2], unorm);                       // = uL.uR / 4
+    un = g[0] * uavg[0];
+    if (!DIAG) {
+        un = vfma(g[1], uavg[1], un);
+        un = vfma(g[2], uavg[2], un);
+    }
+    const VD<W> Ep = vfma(rholog, vfma(unorm, 2.0, ibl * c_igm), pa);   // rholog/(2(g-1)betalog)+pa+.5 rholog uL.uR
+    const VD<W> m = rholog * un;
+    F[0] = m;
+    F[1] = vfma(m, uavg[0], pa * g[0]);
+    if (DIAG) {
+        F[2] = m * uavg[1];
+        F[3] = m * uavg[2];
+    } else {
+        F[2] = vfma(m, uavg[1], pa * g[1]);
+        F[3] = vfma(m, uavg[2], pa * g[2]);
+    }
+    F[4] = Ep * un;
+}
+
+// log_pos / exp_mod of kernels_hex.cuh on W lanes
+template <int W>
+__device__ __forceinline__ VD<W> vlog_pos(const VD<W>& x) {
+    VD<W> f, dk;
+    VFOR {
+        int hi = __double2hiint(x.v[q_]);
+        const int lo = __double2loint(x.v[q_]);
+        int k = (hi >> 20) - 1023;
+        hi &= 0x000fffff;
+        const int i = (hi + 0x95f64) & 0x100000;
+        hi |= (i ^ 0x3ff00000);
+        k += (i >> 20);
+        f.v[q_] = __hiloint2double(hi, lo) - 1.0;
+        dk.v[q_] = (double)k;
+    }
+    const VD<W> s = f * vrcp(f + 2.0);
+    const VD<W> z = s * s, w = z * z;
+    const VD<W> t1 = w * vfma(w, vfma(w, c_lg[5], c_lg[3]), c_lg[1]);
+    const VD<W> t2 = z * vfma(w, vfma(w, vfma(w, c_lg[6], c_lg[4]), c_lg[2]), c_lg[0]);
+    const VD<W> R = t2 + t1;
+    const VD<W> hfsq = .5 * f * f;
+    return dk * 6.93147180369123816490e-01 - ((hfsq - vfma(s, hfsq + R, dk * 1.90821492927058770002e-10)) - f);
+}
+
+template <int W>
+__device__ __forceinline__ VD<W> vexp_mod(const VD<W>& x) {
+    VD<W> kd;
+    VFOR kd.v[q_] = rint(x.v[q_] * 1.44269504088896338700e+00);
+    const VD<W> hi = vfma(kd, -6.93147180369123816490e-01, x);
+    const VD<W> lo = kd * 1.90821492927058770002e-10;
+    const VD<W> r = hi - lo;
+    const VD<W> t = r * r;
+    const VD<W> c = r - t * vfma(t, vfma(t, vfma(t, vfma(t, c_ex[4], c_ex[3]), c_ex[2]), c_ex[1]), c_ex[0]);
+    const VD<W> y = 1.0 - ((lo - (r * c) * vrcp(2.0 - c)) - hi);
+    VD<W> out;
+    VFOR out.v[q_] = __hiloint2double(__double2hiint(y.v[q_]) + ((int)kd.v[q_] << 20), __double2loint(y.v[q_]));
+    return out;
+}
+
+// vol_prim / entropy_vars / trace_from_entropy of kernels_hex.cuh on W lanes
+template <int W>
+__device__ __forceinline__ void vol_prim_v(const VD<W>* U, double gamma, VD<W>& rho, VD<W>* hu, VD<W>& beta, VD<W>& rhoe) {
+    const VD<W> hir = .5 * vrcp(U[0]);
+    hu[0] = U[1] * hir;
+    hu[1] = U[2] * hir;
+    hu[2] = U[3] * hir;
+    VD<W> ke = U[1] * hu[0];
+    ke = vfma(U[2], hu[1], ke);
+    ke = vfma(U[3], hu[2], ke);                 // = .5 |rhoU|^2 / rho
+    rhoe = U[4] - ke;
+    rho = U[0];
+    beta = .5 * U[0] * vrcp((gamma - 1.0) * rhoe);
+}
+
+template <int W>
+__device__ __forceinline__ void entropy_vars_v(const VD<W>* U, const VD<W>& rhoe, const VD<W>& lr, const VD<W>& lb, double gamma, VD<W>* V) {
+    const VD<W> s = vfma(lr, 1.0 - gamma, -lb) - 0.6931471805599453094;
+    const VD<W> ire = vrcp(rhoe);
+    V[0] = vfma(-U[4], ire, (gamma + 1.0) - s);
+    V[1] = U[1] * ire;
+    V[2] = U[2] * ire;
+    V[3] = U[3] * ire;
+    V[4] = -(U[0] * ire);
+}
+
+template <int W>
+__device__ __forceinline__ void trace_from_entropy_v(const VD<W>* V, double gamma, double lg1, double l2g1, VD<W>* Tv) {
+    const VD<W> nvE = -V[4];
+    const VD<W> inv = vrcp(nvE);
+    const VD<W> v2 = vfma(V[1], V[1], vfma(V[2], V[2], V[3] * V[3]));
+    const VD<W> s = (gamma - V[0]) - .5 * v2 * inv;
+    const VD<W> lv = vlog_pos(nvE);
+    const double ig = 1.0 / (gamma - 1.0);
+    const VD<W> lrhoe = ((lg1 - gamma * lv) - s) * ig;
+    const VD<W> rhoeV = vexp_mod(lrhoe);
+    Tv[0] = rhoeV * nvE;
+    const VD<W> hinv = .5 * inv;
+    Tv[1] = V[1] * hinv;
+    Tv[2] = V[2] * hinv;
+    Tv[3] = V[3] * hinv;
+    Tv[4] = (.5 * ig) * nvE;
+    Tv[5] = lrhoe + lv;
+    Tv[6] = lv - l2g1;
+}
+
+// |wavespeed(rho, rhoU_n, E)|, euler_variables.jl:7-10 (sic: sqrt of |u_n|), ir = 1/rho
+template <int W>
+__device__ __forceinline__ VD<W> wavespeed_v(const VD<W>& ir, const VD<W>& rhoun, const VD<W>& E, double gamma) {
+    const VD<W> pg = (gamma * (gamma - 1.0)) * (E - .5 * rhoun * rhoun * ir);
+    return vabs(vsqrt(vabs(rhoun * ir)) + vsqrt(pg * ir));
+}
+
+template <int n, bool DIAG>
+__global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex_stage_line(
+    const __grid_constant__ HexParams p) {
+    using D = LineDims<n>;
+    constexpr int Nq = D::Nq, nfp = D::nfp, Nfq = D::Nfq, NL = D::NL, EB = D::EB, NT = D::THREADS;
+    constexpr int EN = D::EN, EF = D::EF;
+    constexpr int W = 2;
+    extern __shared__ __align__(16) double sm[];
+    __shared__ unsigned long long mbar;
+    double* sWV = sm;                   // [7][EN]  rho, u/2, v/2, w/2, beta, log rho, log beta at volume nodes
+    double* sWF = sWV + 7 * EN;         // [7][EF]  the same at the face points (own traces)
+    double* sP = sWF + 7 * EF;          // [7][EF]  exterior traces, overwritten by the surface flux (5 planes)
+    double* sA = sP + 7 * EF;           // [3][5][EN] per-direction volume accumulators; later V[5][EN]
+    double* sQ = sA + 15 * EN;          // [5][EN]
+    double* sR = sQ + 5 * EN;           // [5][EN]  LSRK register (mode 1)
+    double* s_lm = sR + 5 * EN;
+    double* s_lp = s_lm + n;
+    double* s_lmw = s_lp + n;
+    double* s_lpw = s_lmw + n;
+    double* s_w = s_lpw + n;
+    double* sGeo = s_w + n;             // [EB][34]: G[9], J, 6 x (nxJ,nyJ,nzJ,sJ)
+    const int tid = threadIdx.x;
+#ifdef ESDG_PHASE_TIMING
+    long long t_phase = clock64();
+#endif
+    const long long e0 = p.e_begin + (long long)blockIdx.x * EB;
+    const int nb = (int)min((long long)EB, p.e_begin + p.e_count - e0);
+    constexpr int MAXF = (EF + NT - 1) / NT, MAXV = (EN + NT - 1) / NT;
+    constexpr int GF = (MAXF + W - 1) / W, GV = (MAXV + W - 1) / W;   // item groups of W per thread
+    const long long gq0 = e0 * Nq, gf0 = e0 * Nfq;
+    // exterior-trace indices first: their (L2) latency overlaps everything up to the gather below
+    int ipv[MAXF];
+#pragma unroll
+    for (int r = 0; r < MAXF; ++r) {
+        const int it = tid + r * NT;
+        ipv[r] = it < nb * Nfq ? p.mapP[gf0 + it] : -1;
+    }
+    PHASE_MARK(12);
+    if (tid == 0) mbar_init(&mbar, 1);
+    PHASE_MARK(13);
+    if (tid < n) {
+        s_lm[tid] = p.lm[tid];
+        s_lp[tid] = p.lp[tid];
+        s_lmw[tid] = p.lmw[tid];
+        s_lpw[tid] = p.lpw[tid];
+        s_w[tid] = p.w[tid];
+    }
+    __syncthreads();   // mbarrier initialised before any warp issues a bulk copy on it
+    PHASE_MARK(14);
+    const double c_igm = 1.0 / (2.0 * (p.gamma - 1.0));
+    bool bad = false;
+
+    // ---- 0: every global read of this batch goes in flight -----------------------------------------
+    // Contiguous planes (Q, LSRK register, log stash, own traces: 19 runs of 2 - 2.4 KB) move as TMA bulk
+    // copies issued by one thread; only the exterior-trace gather through mapP needs per-point cp.async.
+    // 16-byte alignment of every run (uniform per CTA); otherwise the 8-byte cp.async path
+    const bool bulk = (((p.q_stride | gq0 | (long long)(nb * Nq) | p.t_stride | gf0 | (long long)(nb * Nfq)) & 1) == 0) &&
+                      ((((size_t)p.Q | (size_t)p.res | (size_t)p.Lcur | (size_t)p.Tcur) & 15) == 0);
+    if (bulk) {
+        // 19 (mode 1) / 14 runs, one per lane-0 of the warps in turn: TMA issue costs ~90 cycles per copy when
+        // one thread issues them back to back
+        const unsigned bq = (unsigned)(nb * Nq * 8), bf = (unsigned)(nb * Nfq * 8);
+        if (tid == 0) mbar_expect_tx(&mbar, (p.mode == 1 ? 12u : 7u) * bq + 7u * bf);
+        if ((tid & 31) == 0) {
+            const int wv = tid >> 5;
+            constexpr int NW = NT / 32;
+            for (int c = wv; c < 19; c += NW) {
+                if (c < 5) bulk_g2s(sQ + c * EN, p.Q + c * p.q_stride + gq0, bq, &mbar);
+                else if (c < 7) bulk_g2s(sWV + c * EN, p.Lcur + (c - 5) * p.q_stride + gq0, bq, &mbar);
+                else if (c < 14) bulk_g2s(sWF + (c - 7) * EF, p.Tcur + (c - 7) * p.t_stride + gf0, bf, &mbar);
+                else if (p.mode == 1) bulk_g2s(sR + (c - 14) * EN, p.res + (c - 14) * p.q_stride + gq0, bq, &mbar);
+            }
+        }
+    } else {
+        for (int it = tid; it < nb * Nq; it += NT) {
+            const long long g = gq0 + it;
+#pragma unroll
+            for (int f = 0; f < 5; ++f) cp_async8(sQ + f * EN + it, p.Q + f * p.q_stride + g);
+            cp_async8(sWV + 5 * EN + it, p.Lcur + g);
+            cp_async8(sWV + 6 * EN + it, p.Lcur + p.q_stride + g);
+            if (p.mode == 1) {
+#pragma unroll
+                for (int f = 0; f < 5; ++f) cp_async8(sR + f * EN + it, p.res + f * p.q_stride + g);
+            }
+        }
+        for (int it = tid; it < nb * Nfq; it += NT) {
+#pragma unroll
+            for (int q = 0; q < HEX_TP; ++q) cp_async8(sWF + q * EF + it, p.Tcur + q * p.t_stride + gf0 + it);
+        }
+    }
+    PHASE_MARK(10);
+#pragma unroll
+    for (int r = 0; r < MAXF; ++r) {
+        const int it = tid + r * NT;
+        if (it < nb * Nfq) {
+#pragma unroll
+            for (int q = 0; q < HEX_TP; ++q) cp_async8(sP + q * EF + it, p.Tcur + q * p.t_stride + ipv[r]);
+        }
+    }
+    for (int it = tid; it < nb * 34; it += NT) cp_async8(sGeo + it, p.geo + e0 * 34 + it);
+    cp_async_commit();
+    PHASE_MARK(11);
+    // warm L2 for the CTA that starts when this one retires (one grid wave ahead)
+    {
+        constexpr int PF_DIST = 148 * D::MINB;
+        const long long e1 = e0 + (long long)PF_DIST * EB;
+        if (e1 + EB <= p.e_begin + p.e_count) {
+            for (int it = tid * 16; it < EN; it += NT * 16) {   // one 128-byte line per 16 doubles
+                const long long g1 = e1 * Nq + it;
+#pragma unroll
+                for (int f = 0; f < 5; ++f) prefetch_l2(p.Q + f * p.q_stride + g1);
+                prefetch_l2(p.Lcur + g1);
+                prefetch_l2(p.Lcur + p.q_stride + g1);
+                if (p.mode == 1) {
+#pragma unroll
+                    for (int f = 0; f < 5; ++f) prefetch_l2(p.res + f * p.q_stride + g1);
+                }
+            }
+            for (int it = tid * 16; it < EF; it += NT * 16) {
+                prefetch_l2(p.mapP + e1 * Nfq + it);
+#pragma unroll
+                for (int q = 0; q < HEX_TP; ++q) prefetch_l2(p.Tcur + q * p.t_stride + e1 * Nfq + it);
+            }
+        }
+    }
+    PHASE_MARK(0);
+    cp_async_wait_all();
+    __syncthreads();
+    if (bulk) mbar_wait(&mbar, 0);
+    PHASE_MARK(1);
+
+    // ---- A: volume primitives -> shared (W nodes per thread, interleaved) -------------------------
+#pragma unroll
+    for (int r = 0; r < GV; ++r) {
+        int it[W];
+        bool act[W];
+        VD<W> U[5], rho, hu[3], beta, rhoe;
+        VFOR {
+            it[q_] = tid + (r * W + q_) * NT;
+            act[q_] = it[q_] < nb * Nq;
+            it[q_] = act[q_] ? it[q_] : 0;
+        }
+#pragma unroll
+        for (int f = 0; f < 5; ++f) VFOR U[f].v[q_] = sQ[f * EN + it[q_]];
+        vol_prim_v<W>(U, p.gamma, rho, hu, beta, rhoe);
+        VFOR {
+            if (act[q_]) {
+                bad = bad || !(U[0].v[q_] > 0.0) || !(rhoe.v[q_] > 0.0);
+                sWV[it[q_]] = rho.v[q_];
+                sWV[EN + it[q_]] = hu[0].v[q_];
+                sWV[2 * EN + it[q_]] = hu[1].v[q_];
+                sWV[3 * EN + it[q_]] = hu[2].v[q_];
+                sWV[4 * EN + it[q_]] = beta.v[q_];
+            }
+        }
+    }
+
+    PHASE_MARK(2);
+    // ---- B: surface flux at face points (dg3D_euler_hex.jl:182-197), W points per thread ----------
+#pragma unroll
+    for (int r = 0; r < GF; ++r) {
+        int it[W];
+        bool act[W];
+        NodeV<W> M, P;
+        VD<W> nJ[3], sJ;
+        VFOR {
+            it[q_] = tid + (r * W + q_) * NT;
+            act[q_] = it[q_] < nb * Nfq;
+            it[q_] = act[q_] ? it[q_] : 0;
+            const int b2 = it[q_] / Nfq, k = it[q_] - b2 * Nfq;
+            const double* gf = sGeo + b2 * 34 + 10 + (k / nfp) * 4;
+            nJ[0].v[q_] = gf[0]; nJ[1].v[q_] = gf[1]; nJ[2].v[q_] = gf[2]; sJ.v[q_] = gf[3];
+            set_lane(M, q_, ld_node(sWF, EF, it[q_]));
+            set_lane(P, q_, ld_node(sP, EF, it[q_]));
+        }
+        VD<W> F[5];
+        pair_flux_v<W, false>(M, P, nJ, c_igm, F);
+        if (p.lf_scale != 0.0) {
+            // conservative states from the primitive traces: E = p/(g-1) + .5 rho |u|^2, p = rho/(2 beta)
+            const double ig1 = 1.0 / (p.gamma - 1.0);
+            const VD<W> isJ = vrcp(sJ);
+            const VD<W> irM = vrcp(M.rho), irP = vrcp(P.rho);
+            VD<W> UM[5], UP[5], unM, unP, kM, kP;
+            UM[0] = M.rho;
+            UP[0] = P.rho;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const VD<W> uM = 2.0 * M.u[d], uP = 2.0 * P.u[d];
+                UM[1 + d] = M.rho * uM;
+                UP[1 + d] = P.rho * uP;
+                if (d == 0) {
+                    kM = UM[1] * uM; kP = UP[1] * uP;
+                    unM = UM[1] * nJ[0]; unP = UP[1] * nJ[0];
+                } else {
+                    kM = vfma(UM[1 + d], uM, kM);
+                    kP = vfma(UP[1 + d], uP, kP);
+                    unM = vfma(UM[1 + d], nJ[d], unM);
+                    unP = vfma(UP[1 + d], nJ[d], unP);
+                }
+            }
+            const VD<W> pM = .5 * M.rho * vrcp(M.beta), pP = .5 * P.rho * vrcp(P.beta);
+            UM[4] = vfma(kM, .5, pM * ig1);
+            UP[4] = vfma(kP, .5, pP * ig1);
+            const VD<W> lamM = wavespeed_v<W>(irM, unM * isJ, UM[4], p.gamma);
+            const VD<W> lamP = wavespeed_v<W>(irP, unP * isJ, UP[4], p.gamma);
+            const VD<W> LFc = p.lf_scale * vmax(lamM, lamP) * sJ;
+#pragma unroll
+            for (int f = 0; f < 5; ++f) F[f] = vfma(-LFc, UP[f] - UM[f], F[f]);
+        }
+        VFOR {
+            if (act[q_]) {
+#pragma unroll
+                for (int f = 0; f < 5; ++f) sP[f * EF + it[q_]] = F[f].v[q_];
+            }
+        }
+    }
+    PHASE_MARK(3);
+    __syncthreads();
+    PHASE_MARK(4);
+
+    // ---- C: one line per thread, two pairs at a time -----------------------------------------------
+    if (tid < nb * NL) {
+        constexpr PairTab<n> PT{};
+        constexpr int NP = PairTab<n>::NP;
+        const int eb = tid / NL, l = tid - eb * NL;
+        const int d = l / nfp, m = l - d * nfp;
+        int base, stride;
+        face_line<n>(d, m, base, stride);
+        base += eb * Nq;
+        const int c1 = d == 2 ? 0 : d + 1, c2 = c1 == 2 ? 0 : c1 + 1;   // physical components in rotated order d,c1,c2
+        const int pl0 = 1 + d, pl1 = 1 + c1, pl2 = 1 + c2;
+        const double* G = sGeo + eb * 34;
+        const double g0 = G[3 * d + d], g1 = G[3 * c1 + d], g2 = G[3 * c2 + d];   // (r_x, r_y, r_z) J of direction d, rotated
+        const VD<2> g_2[3] = {vset<2>(g0), vset<2>(g1), vset<2>(g2)};
+        const VD<1> g_1[3] = {vset<1>(g0), vset<1>(g1), vset<1>(g2)};
+        Node nd[n];
+#pragma unroll
+        for (int a = 0; a < n; ++a) {
+            const int idx = base + a * stride;
+            nd[a].rho = sWV[idx];
+            nd[a].u[0] = sWV[pl0 * EN + idx];
+            nd[a].u[1] = sWV[pl1 * EN + idx];
+            nd[a].u[2] = sWV[pl2 * EN + idx];
+            nd[a].beta = sWV[4 * EN + idx];
+            nd[a].lr = sWV[5 * EN + idx];
+            nd[a].lb = sWV[6 * EN + idx];
+        }
+        double acc[n][5];
+#pragma unroll
+        for (int a = 0; a < n; ++a)
+#pragma unroll
+            for (int f = 0; f < 5; ++f) acc[a][f] = 0.0;
+        // volume-volume pairs: acc_a += T[a][b] F(a,b), acc_b += T[b][a] F(a,b)
+#pragma unroll
+        for (int k = 0; k + 1 < NP; k += 2) {
+            NodeV<2> A, B;
+            set_lane(A, 0, nd[PT.a[k]]);     set_lane(B, 0, nd[PT.b[k]]);
+            set_lane(A, 1, nd[PT.a[k + 1]]); set_lane(B, 1, nd[PT.b[k + 1]]);
+            VD<2> F[5];
+            pair_flux_v<2, DIAG>(A, B, g_2, c_igm, F);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int a = PT.a[k + q], b = PT.b[k + q];
+#pragma unroll
+                for (int f = 0; f < 5; ++f) {
+                    acc[a][f] = fma(p.T[a * n + b], F[f].v[q], acc[a][f]);
+                    acc[b][f] = fma(p.T[b * n + a], F[f].v[q], acc[b][f]);
+                }
+            }
+        }
+        if (NP % 2 == 1) {
+            constexpr int k = NP > 0 ? NP - 1 : 0;
+            const int a = PT.a[k], b = PT.b[k];
+            NodeV<1> A, B;
+            set_lane(A, 0, nd[a]);
+            set_lane(B, 0, nd[b]);
+            VD<1> F[5];
+            pair_flux_v<1, DIAG>(A, B, g_1, c_igm, F);
+#pragma unroll
+            for (int f = 0; f < 5; ++f) {
+                acc[a][f] = fma(p.T[a * n + b], F[f].v[0], acc[a][f]);
+                acc[b][f] = fma(p.T[b * n + a], F[f].v[0], acc[b][f]);
+            }
+        }
+        // volume-face pairs: node a against the two face points its line ends in (lane = side)
+        Node fn[2];
+        int fidx[2];
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            fidx[side] = eb * Nfq + (2 * d + side) * nfp + m;
+            fn[side].rho = sWF[fidx[side]];
+            fn[side].u[0] = sWF[pl0 * EF + fidx[side]];
+            fn[side].u[1] = sWF[pl1 * EF + fidx[side]];
+            fn[side].u[2] = sWF[pl2 * EF + fidx[side]];
+            fn[side].beta = sWF[4 * EF + fidx[side]];
+            fn[side].lr = sWF[5 * EF + fidx[side]];
+            fn[side].lb = sWF[6 * EF + fidx[side]];
+        }
+        NodeV<2> FB;
+        set_lane(FB, 0, fn[0]);
+        set_lane(FB, 1, fn[1]);
+        double h[2][5];
+#pragma unroll
+        for (int f = 0; f < 5; ++f) h[0][f] = h[1][f] = 0.0;
+#pragma unroll
+        for (int a = 0; a < n; ++a) {
+            NodeV<2> A;
+            set_lane(A, 0, nd[a]);
+            set_lane(A, 1, nd[a]);
+            VD<2> F[5];
+            pair_flux_v<2, DIAG>(A, FB, g_2, c_igm, F);
+#pragma unroll
+            for (int f = 0; f < 5; ++f) {
+                acc[a][f] = fma(-p.lmw[a], F[f].v[0], acc[a][f]);
+                acc[a][f] = fma(p.lpw[a], F[f].v[1], acc[a][f]);
+                h[0][f] = fma(p.lm[a], F[f].v[0], h[0][f]);
+                h[1][f] = fma(p.lp[a], F[f].v[1], h[1][f]);
+            }
+        }
+        // face rows: H = flux* -/+ sum_a l[a] F(a) (physical field order in shared memory); only the nodes
+        // of THIS line lift from these two face points, so the lift (Lf as a 1-D sweep) is applied here
+        {
+            const double* fl = sP + fidx[0];
+            const double Hm[5] = {fl[0] + h[0][0], fl[pl0 * EF] + h[0][1], fl[pl1 * EF] + h[0][2], fl[pl2 * EF] + h[0][3],
+                                  fl[4 * EF] + h[0][4]};
+            fl = sP + fidx[1];
+            const double Hp[5] = {fl[0] - h[1][0], fl[pl0 * EF] - h[1][1], fl[pl1 * EF] - h[1][2], fl[pl2 * EF] - h[1][3],
+                                  fl[4 * EF] - h[1][4]};
+#pragma unroll
+            for (int a = 0; a < n; ++a)
+#pragma unroll
+                for (int f = 0; f < 5; ++f) acc[a][f] = fma(p.lpw[a], Hp[f], fma(p.lmw[a], Hm[f], acc[a][f]));
+        }
+        double* A = sA + d * 5 * EN;
+#pragma unroll
+        for (int a = 0; a < n; ++a) {
+            const int idx = base + a * stride;
+            A[idx] = acc[a][0];
+            A[pl0 * EN + idx] = acc[a][1];
+            A[pl1 * EN + idx] = acc[a][2];
+            A[pl2 * EN + idx] = acc[a][3];
+            A[4 * EN + idx] = acc[a][4];
+        }
+    }
+    PHASE_MARK(5);
+    __syncthreads();
+    PHASE_MARK(6);
+
+    // ---- E: lift, scale, rhstest, LSRK stage; F (volume part): entropy variables of the new state ----
+    double tsum = 0.0;
+#pragma unroll
+    for (int r = 0; r < GV; ++r) {
+        int it[W];
+        bool act[W];
+        VD<W> acc[5], U[5], J, wJ;
+        VFOR {
+            it[q_] = tid + (r * W + q_) * NT;
+            act[q_] = it[q_] < nb * Nq;
+            it[q_] = act[q_] ? it[q_] : 0;
+        }
+#pragma unroll
+        for (int f = 0; f < 5; ++f)
+            VFOR acc[f].v[q_] = (sA[f * EN + it[q_]] + sA[(5 + f) * EN + it[q_]]) + sA[(10 + f) * EN + it[q_]];
+        VFOR {
+            const int eb = it[q_] / Nq, i = it[q_] - eb * Nq;
+            J.v[q_] = sGeo[eb * 34 + 9];
+            if (p.want_rhstest) {
+                const int xa = i % n, xb = (i / n) % n, xc = i / (n * n);
+                wJ.v[q_] = s_w[xa] * s_w[xb] * s_w[xc] * J.v[q_];
+            }
+        }
+        const VD<W> mJ = -vrcp(J);
+        VD<W> rr[5];
+#pragma unroll
+        for (int f = 0; f < 5; ++f) {
+            rr[f] = acc[f] * mJ;
+            VFOR U[f].v[q_] = sQ[f * EN + it[q_]];
+        }
+        if (p.want_rhstest) {
+            VD<W> V[5], lr, lb;
+            VFOR { lr.v[q_] = sWV[5 * EN + it[q_]]; lb.v[q_] = sWV[6 * EN + it[q_]]; }
+            const VD<W> hir = .5 * vrcp(U[0]);
+            const VD<W> ke = hir * vfma(U[1], U[1], vfma(U[2], U[2], U[3] * U[3]));
+            entropy_vars_v<W>(U, U[4] - ke, lr, lb, p.gamma, V);
+            VFOR {
+                if (act[q_]) {
+#pragma unroll
+                    for (int f = 0; f < 5; ++f) tsum = fma(wJ.v[q_] * V[f].v[q_], rr[f].v[q_], tsum);
+                }
+            }
+        }
+        if (p.mode == 0) {
+            VFOR {
+                if (act[q_]) {
+#pragma unroll
+                    for (int f = 0; f < 5; ++f) p.rhs[f * p.q_stride + e0 * Nq + it[q_]] = rr[f].v[q_];
+                }
+            }
+        } else {
+            VD<W> Un[5], rs[5];
+#pragma unroll
+            for (int f = 0; f < 5; ++f) {
+                VFOR rs[f].v[q_] = fma(p.rk_a, sR[f * EN + it[q_]], p.dt * rr[f].v[q_]);
+                Un[f] = vfma(p.rk_b, rs[f], U[f]);
+            }
+            VFOR {
+                if (act[q_]) {
+#pragma unroll
+                    for (int f = 0; f < 5; ++f) {
+                        p.res[f * p.q_stride + e0 * Nq + it[q_]] = rs[f].v[q_];
+                        p.Qout[f * p.q_stride + e0 * Nq + it[q_]] = Un[f].v[q_];
+                    }
+                }
+            }
+            VD<W> rho, hu[3], beta, rhoen, V[5];
+            vol_prim_v<W>(Un, p.gamma, rho, hu, beta, rhoen);
+            const VD<W> lr = vlog_pos<W>(rho), lb = vlog_pos<W>(beta);
+            entropy_vars_v<W>(Un, rhoen, lr, lb, p.gamma, V);
+            VFOR {
+                if (act[q_]) {
+                    bad = bad || !(Un[0].v[q_] > 0.0) || !(rhoen.v[q_] > 0.0);
+                    p.Lnext[e0 * Nq + it[q_]] = lr.v[q_];
+                    p.Lnext[p.q_stride + e0 * Nq + it[q_]] = lb.v[q_];
+                    // V[5][EN] aliases the d = 0 accumulator block: this thread is the only reader of those slots
+#pragma unroll
+                    for (int f = 0; f < 5; ++f) sA[f * EN + it[q_]] = V[f].v[q_];
+                }
+            }
+        }
+    }
+    PHASE_MARK(7);
+    if (p.mode == 1) {
+        __syncthreads();
+        PHASE_MARK(8);
+        // ---- F: project to the faces, 7-plane traces of the new state ----------------------------
+#pragma unroll
+        for (int r = 0; r < GF; ++r) {
+            int it[W];
+            bool act[W];
+            VD<W> V[5];
+            VFOR {
+                it[q_] = tid + (r * W + q_) * NT;
+                act[q_] = it[q_] < nb * Nfq;
+                it[q_] = act[q_] ? it[q_] : 0;
+                const int eb = it[q_] / Nfq, k = it[q_] - eb * Nfq;
+                const int face = k / nfp, m = k - face * nfp;
+                int base, stride;
+                face_line<n>(face >> 1, m, base, stride);
+                const double* l = (face & 1) ? s_lp : s_lm;
+                const double* v = sA + eb * Nq + base;
+#pragma unroll
+                for (int f = 0; f < 5; ++f) V[f].v[q_] = 0.0;
+#pragma unroll
+                for (int a = 0; a < n; ++a) {
+                    const double la = l[a];
+#pragma unroll
+                    for (int f = 0; f < 5; ++f) V[f].v[q_] = fma(la, v[f * EN + a * stride], V[f].v[q_]);
+                }
+            }
+            VD<W> Tv[HEX_TP];
+            trace_from_entropy_v<W>(V, p.gamma, p.lg1, p.l2g1, Tv);
+            VFOR {
+                if (act[q_]) {
+#pragma unroll
+                    for (int q = 0; q < HEX_TP; ++q) p.Tnext[q * p.t_stride + e0 * Nfq + it[q_]] = Tv[q].v[q_];
+                }
+            }
+        }
+    }
+    PHASE_MARK(9);
+    if (p.want_rhstest) {
+        __shared__ double red[32];
+        for (int o = 16; o > 0; o >>= 1) tsum += __shfl_down_sync(0xffffffffu, tsum, o);
+        if ((tid & 31) == 0) red[tid >> 5] = tsum;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int wv = 0; wv < NT / 32; ++wv) t += red[wv];
+            p.partial[blockIdx.x] = t;
+        }
+    }
+    if (bad) atomicOr(p.bad, 1);
+}
+
+}  // namespace esdg

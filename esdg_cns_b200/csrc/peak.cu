@@ -5,13 +5,19 @@
 #include "../../include/esdg_b200.h"
 
 namespace {
-__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
-    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
-    for (int i = 0; i < iters; ++i) {
-        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+// 4 independent chains, 8x unrolled, multiplier/addend as constant operands: the configuration that reached
+// 0.495 warp-DFMA per cycle per SM sub-partition in profiles/microbench (register operands top out at 0.46)
+__global__ void __launch_bounds__(128) k_dfma_peak(double* out, int iters) {
+    double x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = threadIdx.x + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] = fma(x[i], 1.0000001, 1e-9);
     }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (x[0] + x[1]) + (x[2] + x[3]);
 }
 }  // namespace
 
@@ -20,7 +26,7 @@ extern "C" int esdg_measure_fp64_peak(int device, double* tflops) {
     if (cudaSetDevice(device) != cudaSuccess) return ESDG_ECUDA;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ESDG_ECUDA;
-    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+    const int blocks = prop.multiProcessorCount * 16, threads = 128, iters = 1 << 12;
     double* out = nullptr;
     if (cudaMalloc(&out, sizeof(double) * blocks * threads) != cudaSuccess) return ESDG_ENOMEM;
     cudaEvent_t e0, e1;
@@ -29,12 +35,12 @@ extern "C" int esdg_measure_fp64_peak(int device, double* tflops) {
     double best = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
         cudaEventRecord(e0);
-        k_dfma_peak<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);
+        k_dfma_peak<<<blocks, threads>>>(out, iters);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
-        const double fl = 2.0 * 8.0 * iters * (double)blocks * threads;
+        const double fl = 2.0 * 32.0 * iters * (double)blocks * threads;
         if (rep > 0 && ms > 0) best = fl / (ms * 1e-3) / 1e12 > best ? fl / (ms * 1e-3) / 1e12 : best;
     }
     cudaEventDestroy(e0);

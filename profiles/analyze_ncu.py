@@ -1,11 +1,11 @@
 #!/usr/bin/env python
-"""Summarise an .ncu-rep: headline metrics, stall reasons, and stall samples per source line.
-usage: python profiles/analyze_ncu.py gpurun_out/prof.ncu-rep [source-file] [top]"""
-import collections, csv, io, subprocess, sys
+"""Summarise an .ncu-rep: headline metrics, stall reasons, opcode mix and stall samples per source
+line (all source files of the kernel).
+usage: python profiles/analyze_ncu.py gpurun_out/prof.ncu-rep [top]"""
+import collections, csv, io, os, subprocess, sys
 
 rep = sys.argv[1]
-srcfile = sys.argv[2] if len(sys.argv) > 2 else "esdg_cns_b200/csrc/kernels_hex.cuh"
-top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
+top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
@@ -30,41 +30,55 @@ for i, h in enumerate(hdr):
             print(f"  {h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''):24s} {v:.3f}")
 cs = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(cs)))
-hi = [i for i, r in enumerate(rows) if r and r[0] == "Line No"]
-if hi:
-    hdr = rows[hi[0]]
-    ci = {h: i for i, h in enumerate(hdr)}
-    nh = len(hdr)
-    end = hi[1] if len(hi) > 1 else len(rows)
-    samples, inst, stall = collections.Counter(), collections.Counter(), collections.defaultdict(collections.Counter)
-    names = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-    cur, tot = None, 0.0
-    for r in rows[hi[0] + 1:end]:
-        if not r:
+samples, inst, stall, ops = collections.Counter(), collections.Counter(), collections.defaultdict(collections.Counter), collections.Counter()
+fpath, hdrs, cur = None, None, None
+for r in rows:
+    if not r:
+        continue
+    if r[0] == "File Path":
+        fpath = r[1]
+        continue
+    if r[0] == "Line No":
+        hdrs = r
+        ci = {h: i for i, h in enumerate(hdrs)}
+        names = [h for h in hdrs if h.startswith("stall_") and "Not Issued" not in h]
+        continue
+    if hdrs is None:
+        continue
+    if r[0].strip().isdigit():
+        cur = (fpath, int(r[0]))
+        continue
+    if len(r) >= 4 and r[2].startswith("0x"):
+        off = len(r) - len(hdrs)
+        try:
+            n = float(r[ci["# Samples"] + off])
+            ni = float(r[ci["Instructions Executed"] + off])
+        except ValueError:
             continue
-        if r[0].strip().isdigit():
-            cur = int(r[0])
-            continue
-        if len(r) >= 4 and r[2].startswith("0x"):
-            off = len(r) - nh
-
-            def g(nm):
-                try:
-                    return float(r[ci[nm] + off])
-                except ValueError:
-                    return 0.0
-            s = g("# Samples")
-            samples[cur] += s
-            tot += s
-            inst[cur] += g("Instructions Executed")
-            for sn in names:
-                stall[cur][sn] += g(sn)
-    try:
-        src = open(srcfile).read().split("\n")
-    except OSError:
-        src = []
-    print(f"stall samples per source line of {srcfile} (total {int(tot)}):")
-    for ln, s in samples.most_common(top):
-        t3 = ", ".join(f"{k.replace('stall_', '')}:{int(v)}" for k, v in stall[ln].most_common(3))
-        text = src[ln - 1].strip()[:90] if 0 < ln <= len(src) else ""
-        print(f"  {ln:4d} {100 * s / tot:5.1f}% inst={inst[ln] / 1e6:7.1f}M [{t3}] {text}")
+        samples[cur] += n
+        inst[cur] += ni
+        t = r[3].strip().split()
+        op = (t[1] if t and t[0].startswith("@") else (t[0] if t else "")).split(".")[0]
+        ops[op] += ni
+        for h in names:
+            try:
+                stall[cur][h[6:]] += float(r[ci[h] + off])
+            except ValueError:
+                pass
+tot, toti = sum(samples.values()), sum(inst.values())
+print(f"total warp instructions {toti/1e6:.1f} M; opcode mix (%):", [(k, round(100 * v / toti, 1)) for k, v in ops.most_common(20)])
+byfile = collections.Counter()
+for (f, l), n in samples.items():
+    byfile[f] += n
+print("stall samples by file:", [(os.path.basename(f or "?"), int(n)) for f, n in byfile.most_common()])
+srcs = {}
+print(f"stall samples per source line (total {int(tot)}):")
+for (f, ln), n in samples.most_common(top):
+    if f not in srcs:
+        try:
+            srcs[f] = open(f).read().split("\n")
+        except OSError:
+            srcs[f] = []
+    text = srcs[f][ln - 1].strip()[:84] if 0 < ln <= len(srcs[f]) else ""
+    st = ", ".join(f"{k}:{int(v)}" for k, v in stall[(f, ln)].most_common(3))
+    print(f"  {os.path.basename(f or '?')[:18]:18s}{ln:4d} {100*n/tot:5.1f}% inst={inst[(f, ln)]/1e6:7.1f}M [{st}] {text}")
