@@ -93,7 +93,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
@@ -227,13 +227,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()          # started before the warm-up: the first nvidia-smi call on a fresh box takes ~1 s
     for _ in range(max(args.warmup, 3)):
         step()
     s.sync()
-    # ---- device-resident timing ---------------------------------------------------------
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
-        sampler.start()
+        sampler.rows.clear()     # keep only samples taken under the timed load
+    # ---- device-resident timing ---------------------------------------------------------
     s.enable_timing(True)
     l0 = s.kernel_launches()
     barrier()

@@ -249,7 +249,10 @@ __global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex
     using D = LineDims<n>;
     constexpr int Nq = D::Nq, nfp = D::nfp, Nfq = D::Nfq, NL = D::NL, EB = D::EB, NT = D::THREADS;
     constexpr int EN = D::EN, EF = D::EF;
-    constexpr int W = 2;
+#ifndef ESDG_LINE_WI
+#define ESDG_LINE_WI 1
+#endif
+    constexpr int W = ESDG_LINE_WI;   // items per thread interleaved in the per-node / per-face-point phases (2 measured no faster)
     extern __shared__ __align__(16) double sm[];
     __shared__ unsigned long long mbar;
     double* sWV = sm;                   // [7][EN]  rho, u/2, v/2, w/2, beta, log rho, log beta at volume nodes
@@ -375,7 +378,7 @@ __global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex
     PHASE_MARK(1);
 
     // ---- A: volume primitives -> shared (W nodes per thread, interleaved) -------------------------
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < GV; ++r) {
         int it[W];
         bool act[W];
@@ -402,7 +405,7 @@ __global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex
 
     PHASE_MARK(2);
     // ---- B: surface flux at face points (dg3D_euler_hex.jl:182-197), W points per thread ----------
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < GF; ++r) {
         int it[W];
         bool act[W];
@@ -593,7 +596,7 @@ __global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex
 
     // ---- E: lift, scale, rhstest, LSRK stage; F (volume part): entropy variables of the new state ----
     double tsum = 0.0;
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < GV; ++r) {
         int it[W];
         bool act[W];
@@ -678,7 +681,7 @@ __global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex
         __syncthreads();
         PHASE_MARK(8);
         // ---- F: project to the faces, 7-plane traces of the new state ----------------------------
-#pragma unroll
+#pragma unroll 1
         for (int r = 0; r < GF; ++r) {
             int it[W];
             bool act[W];

@@ -136,3 +136,31 @@ def test_cns_bad_wall_node_is_rejected():
     st.wall = np.concatenate([bc.wall, interior])
     with pytest.raises(_lib.EsdgError):
         api.Solver(md, ops, cns=st)
+
+
+def test_cns_cavity_20_steps_track_oracle():
+    """Config 3 (lid-driven cavity from rest, quad N=3) over 20 LSRK45 steps at the script's fixed CFL dt (:39-42)."""
+    from oracle import cns, solvers as SV
+    from esdg_cns_b200 import api
+    N, K1D = 3, 6
+    rd, md, ops, bc, Q = cns.setup_cavity("quad", N, K1D)
+    par = cns.cavity_params()
+    dt = .5 * (2 / K1D) / ((N + 1) * (N + 2) / 2)
+    Qo, res = [q.copy() for q in Q], [np.zeros_like(q) for q in Q]
+
+    def f(q, want):
+        r, rt, _ = cns.rhsRK(q, md, ops, bc, par)
+        return r, rt
+    for _ in range(20):
+        Qo, res, rto = SV.lsrk45_step(Qo, res, dt, f)
+    s = api.Solver(md, ops, cns=_cns_settings(par, bc, md))
+    s.upload(Q)
+    rtg = s.lsrk45(dt, 20, want_rhstest=True)
+    Qg = s.download()
+    assert all(np.isfinite(q).all() for q in Qg)
+    err = relerr(Qg, Qo)
+    umax = np.abs(Qg[1] / Qg[0]).max()
+    print(f"cavity 20 steps: state relerr {err:.2e}, max|u| {umax:.3f}, rhstest {rtg:.4e} vs {rto:.4e}")
+    assert err < 1e-10
+    assert umax > 1e-2               # the lid has set the fluid in motion
+    assert abs(rtg - rto) < 1e-9 * max(1.0, abs(rto))
