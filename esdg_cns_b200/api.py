@@ -157,6 +157,23 @@ class Solver:
         self._ck(self._lib.esdg_lsrk45_step(self._ctx, float(dt), int(nsteps), None))
         return None
 
+    def dopri45(self, T, dt, err_tol=1e-5, max_attempts=10 ** 9):
+        """The adaptive time loop of dg2D_CNS_cavity_optimized.jl:974-1053 on the resident state:
+        ``while t < T`` DOPRI45 steps with FSAL and the PI controller.  Returns the histories the
+        script keeps (``thist, dthist, errhist, rhstesthist, vischist``) as a dict."""
+        self._ck(self._lib.esdg_dopri45_init(self._ctx))
+        t, h, dt0 = C.c_double(0.0), C.c_double(float(dt)), float(dt)
+        ok, err, rt = C.c_int(0), C.c_double(0.0), (C.c_double * 2)(0.0, 0.0)
+        hist = {"t": [0.0], "dt": [float(dt)], "err": [0.0], "rhstest": [0.0], "rhstest_visc": [0.0], "accepted": []}
+        n = 0
+        while t.value < T and n < max_attempts:
+            self._ck(self._lib.esdg_dopri45_step(self._ctx, C.byref(t), C.byref(h), dt0, float(err_tol), C.byref(ok),
+                                                 C.byref(err), rt))
+            n += 1
+            hist["t"].append(t.value); hist["dt"].append(h.value); hist["err"].append(err.value)
+            hist["rhstest"].append(rt[0]); hist["rhstest_visc"].append(rt[1]); hist["accepted"].append(bool(ok.value))
+        return hist
+
     def sync(self):
         self._ck(self._lib.esdg_sync(self._ctx))
 

@@ -33,7 +33,7 @@ void fill_params(esdg_ctx* ctx, GenericParams& p) {
     p.Q = ctx->Q;
     p.q_stride = (long long)d.Ns * d.K;
     p.traces = ctx->traces;
-    p.rhs = ctx->rhs;
+    p.rhs = ctx->rhs_target ? ctx->rhs_target : ctx->rhs;
     p.Qout = ctx->Q;
     p.res = ctx->res;
     p.rk_a = 0; p.rk_b = 0; p.dt = 0;
@@ -609,6 +609,7 @@ int esdg_upload_state(esdg_ctx* ctx, const double* const* Q) {
         CK(cudaMemcpyAsync(ctx->Q + f * n, Q[f], n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->res, 0, ctx->NF * n * sizeof(double), ctx->stream));
     ctx->traces_valid = false;
+    ctx->dopri.ready = false;
     return ESDG_OK;
 }
 
@@ -767,6 +768,139 @@ int esdg_read_rhstest(esdg_ctx* ctx, double* rhstest) {
     if (rc) return rc;
     CK(cudaMemcpyAsync(rhstest, ctx->rhstest_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     return check_bad(ctx);
+}
+
+// ---- DOPRI45 adaptive driver (dg2D_CNS_cavity_optimized.jl:919-934, :974-1053) --------------------
+namespace {
+const double DP_A[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {0.2, 0, 0, 0, 0, 0},
+    {3.0 / 40.0, 9.0 / 40.0, 0, 0, 0, 0},
+    {44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0, 0, 0, 0},
+    {19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0, 0, 0},
+    {9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0, 0},
+    {35.0 / 384.0, 0.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0}};          // :920-927
+const double DP_E[7] = {71.0 / 57600.0, 0.0, -71.0 / 16695.0, 71.0 / 1920.0, -17253.0 / 339200.0,
+                        22.0 / 525.0, -1.0 / 40.0};                                              // :931
+
+struct DopriArgs {
+    const double* K[7];
+    double c[7];
+    int ns;
+};
+
+// Qtmp = Q + dt * sum_s a[s] K_s   (k accumulated in the reference's order s = 1..INTRK-1, :1005-1010)
+__global__ void k_dopri_combine(const double* __restrict__ Q, double* __restrict__ Qtmp, DopriArgs a, double dt, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double k = 0.0;
+    for (int s = 0; s < a.ns; ++s) k = k + a.c[s] * a.K[s][i];
+    Qtmp[i] = Q[i] + dt * k;
+}
+
+// partial sums of (|sum_s E[s] K_s| / (errTol (1 + |Q|)))^2   (:1015-1023), one partial per CTA, fixed order
+__global__ void k_dopri_err(const double* __restrict__ Q, DopriArgs a, double err_tol, long long n, double* __restrict__ partial) {
+    __shared__ double sh[256];
+    double t = 0.0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        double e = 0.0;
+        for (int s = 0; s < 7; ++s) e = e + a.c[s] * a.K[s][i];
+        const double sc = fabs(e) / (err_tol * (1.0 + fabs(Q[i])));
+        t += sc * sc;
+    }
+    sh[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+int dopri_rhs(esdg_ctx* ctx, const double* src, double* out, int want) {
+    int rc;
+    ctx->rhs_target = out;
+    rc = do_traces(ctx, src);
+    if (!rc) rc = do_stage(ctx, src, 0, 0, 0, 0, want, ESDG_PART_ALL);
+    ctx->rhs_target = nullptr;
+    ctx->traces_valid = false;
+    return rc;
+}
+}  // namespace
+
+int esdg_dopri45_init(esdg_ctx* ctx) {
+    int rc = require_ready(ctx, "esdg_dopri45_init");
+    if (rc) return rc;
+    if (ctx->d.n_halo != 0) return fail(ctx, ESDG_EINVAL, "esdg_dopri45_init: single-GPU contexts only");
+    DopriState& D = ctx->dopri;
+    const size_t n = (size_t)ctx->NF * ctx->d.Ns * ctx->d.K;
+    if (!D.K[0]) {
+        for (int s = 0; s < 7; ++s)
+            if ((rc = dev_alloc(ctx, &D.K[s], n))) return rc;
+        if ((rc = dev_alloc(ctx, &D.Qtmp, n))) return rc;
+        D.n_err_blocks = (int)std::min<size_t>(1024, (n + 255) / 256);
+        if ((rc = dev_alloc(ctx, &D.err_partial, (size_t)D.n_err_blocks))) return rc;
+        if ((rc = dev_alloc(ctx, &D.err_dev, 2))) return rc;
+    }
+    D.prev_err = 0.0;
+    D.attempts = 0;
+    if ((rc = dopri_rhs(ctx, ctx->Q, D.K[0], 0))) return rc;       // FSAL start (:996-997)
+    D.ready = true;
+    return check_bad(ctx);
+}
+
+int esdg_dopri45_step(esdg_ctx* ctx, double* t, double* dt, double dt0, double err_tol, int* accepted, double* err_est,
+                      double* rhstest) {
+    int rc = require_ready(ctx, "esdg_dopri45_step");
+    if (rc) return rc;
+    DopriState& D = ctx->dopri;
+    if (!D.ready) return fail(ctx, ESDG_EINVAL, "esdg_dopri45_step: call esdg_dopri45_init after uploading the state");
+    if (!t || !dt || !(*dt > 0.0) || !(err_tol > 0.0)) return fail(ctx, ESDG_EINVAL, "esdg_dopri45_step: bad argument");
+    const long long n = (long long)ctx->NF * ctx->d.Ns * ctx->d.K;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    for (int k = 1; k < 7; ++k) {                                    // INTRK = 2:7 (:1004-1013)
+        DopriArgs a;
+        a.ns = k;
+        for (int s = 0; s < 7; ++s) { a.K[s] = D.K[s]; a.c[s] = s < k ? DP_A[k][s] : 0.0; }
+        tick(ctx, "dopri_combine");
+        k_dopri_combine<<<blocks, 256, 0, ctx->stream>>>(ctx->Q, D.Qtmp, a, *dt, n);
+        tock(ctx);
+        CK(cudaGetLastError());
+        if ((rc = dopri_rhs(ctx, D.Qtmp, D.K[k], k == 6))) return rc;
+    }
+    DopriArgs e;
+    e.ns = 7;
+    for (int s = 0; s < 7; ++s) { e.K[s] = D.K[s]; e.c[s] = DP_E[s]; }
+    tick(ctx, "dopri_err");
+    k_dopri_err<<<D.n_err_blocks, 256, 0, ctx->stream>>>(ctx->Q, e, err_tol, n, D.err_partial);
+    tock(ctx);
+    CK(cudaGetLastError());
+    tick(ctx, "reduce_partials");
+    k_reduce_partials<<<1, 256, 0, ctx->stream>>>(D.err_partial, D.n_err_blocks, D.err_dev);
+    tock(ctx);
+    CK(cudaGetLastError());
+    double h[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(h, D.err_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h + 1, ctx->rhstest_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = check_bad(ctx))) return rc;
+    const double err = std::sqrt(h[0] / (double)n);                  // length(Q[1])*4 = all entries (:1024)
+    const int ok = err < 1.0;
+    if (ok) {                                                        // :1025-1029
+        CK(cudaMemcpyAsync(ctx->Q, D.Qtmp, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        *t += *dt;
+        std::swap(D.K[0], D.K[6]);                                   // FSAL
+        ctx->traces_valid = false;
+    }
+    const double order = 5.0;
+    double dtnew = .8 * *dt * std::pow(.9 / err, .4 / (order + 1));  // P controller (:1031)
+    if (D.attempts > 0) dtnew *= std::pow(D.prev_err / std::max(1e-14, err), .3 / (order + 1));   // PI (:1032-1034)
+    *dt = std::max(std::min(10 * dt0, dtnew), 1e-9);                 // :1035
+    D.prev_err = err;
+    D.attempts += 1;
+    if (accepted) *accepted = ok;
+    if (err_est) *err_est = err;
+    if (rhstest) { rhstest[0] = h[1]; rhstest[1] = ctx->cns.on ? h[2] : 0.0; }
+    return ESDG_OK;
 }
 
 int esdg_read_rhstest_visc(esdg_ctx* ctx, double* rhstest_visc) {

@@ -43,6 +43,17 @@ struct CnsState {
     double *sig = nullptr, *sig_tr = nullptr, *partial_visc = nullptr, *partial_vrhs = nullptr;
 };
 
+// DOPRI45 driver state (dg2D_CNS_cavity_optimized.jl:919-934, :974-1053)
+struct DopriState {
+    bool ready = false;
+    double* K[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // rhsQrk[1..7]
+    double* Qtmp = nullptr;
+    double *err_partial = nullptr, *err_dev = nullptr;
+    int n_err_blocks = 0;
+    double prev_err = 0.0;
+    long long attempts = 0;    // `i` of the script: total steps attempted
+};
+
 struct esdg_ctx {
     esdg_desc d{};
     int device = 0;
@@ -82,6 +93,8 @@ struct esdg_ctx {
     // specialised hex path (kernels_hex.cuh); null if the operators do not match
     struct HexFast* hex = nullptr;
     CnsState cns;
+    DopriState dopri;
+    double* rhs_target = nullptr;   // where mode-0 rhs evaluations write (default: rhs)
     long long bnd_lo = 0, bnd_hi = 0;   // leading / trailing elements whose traces are sent to neighbours
     bool res_zero = true;
 

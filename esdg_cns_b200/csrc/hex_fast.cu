@@ -83,7 +83,7 @@ void fill_hex_params(esdg_ctx* ctx, HexParams& p) {
     p.Q = ctx->Q;
     p.Qout = ctx->Q;
     p.res = ctx->res;
-    p.rhs = ctx->rhs;
+    p.rhs = ctx->rhs_target ? ctx->rhs_target : ctx->rhs;
     p.Lcur = h->logs[h->cons];
     p.Lnext = h->logs[h->prod];
     p.Tcur = h->trace[h->cons];

@@ -137,6 +137,17 @@ int esdg_download_state(esdg_ctx* ctx, double* const* Q);
  * unless rhstest_last != NULL (then rhstest of the final stage is returned). */
 int esdg_lsrk45_step(esdg_ctx* ctx, double dt, int nsteps, double* rhstest_last);
 
+/* DOPRI45 adaptive driver of the CNS scripts (dg2D_CNS_cavity_optimized.jl:919-934 coefficients,
+ * :974-1053 loop): FSAL, Hairer error semi-norm with tolerance err_tol (the script's errTol = 1e-5,
+ * :1017), step accepted iff errEst < 1, P / PI step-size controller clipped to [1e-9, 10*dt0].
+ * esdg_dopri45_init evaluates the first stage of the resident state (:996-997); each
+ * esdg_dopri45_step is ONE iteration of the `while t < T` loop: it attempts a step of *dt, updates
+ * *t (if accepted) and *dt (always, to the controller's next value) and reports errEst; rhstest[2]
+ * receives (rhstest, rhstest_visc) of the last stage (:1039-1042).  Works on Euler contexts too. */
+int esdg_dopri45_init(esdg_ctx* ctx);
+int esdg_dopri45_step(esdg_ctx* ctx, double* t, double* dt, double dt0, double err_tol, int* accepted, double* err_est,
+                      double* rhstest);
+
 int esdg_sync(esdg_ctx* ctx);   /* waits; reports ESDG_ESTATE if the rhs met rho<=0 or p<=0 */
 
 /* ---- multi-GPU plumbing (one context per GPU; the host exchanges halos) ---------

@@ -302,3 +302,58 @@ def setup_cavity(elem="tri", N=3, K1D=4):
     rho = np.ones_like(md.x)
     Q = list(P.primitive_to_conservative(rho, (np.zeros_like(rho), np.zeros_like(rho)), (1 / (Ma ** 2 * GAMMA)) * np.ones_like(rho)))
     return rd, md, ops, bc, Q
+
+
+def dopri45_coeffs():  # :919-934
+    a = np.zeros((7, 7))
+    a[1, 0] = .2
+    a[2, :2] = [3.0 / 40.0, 9.0 / 40.0]
+    a[3, :3] = [44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0]
+    a[4, :4] = [19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0]
+    a[5, :5] = [9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0]
+    a[6, :6] = [35.0 / 384.0, 0.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0]
+    c = np.array([0.0, .2, .3, .8, 8.0 / 9.0, 1.0, 1.0])
+    E = np.array([71.0 / 57600.0, 0.0, -71.0 / 16695.0, 71.0 / 1920.0, -17253.0 / 339200.0, 22.0 / 525.0, -1.0 / 40.0])
+    return a, E, c
+
+
+def dopri45(Q, rhs_fun, T, dt, err_tol=1e-5, max_attempts=10 ** 9):
+    """The adaptive loop of dg2D_CNS_cavity_optimized.jl:974-1053 (FSAL, Hairer semi-norm, P/PI controller).
+    ``rhs_fun(Q) -> (rhsQ, rhstest, rhstest_visc)``.  Quirks kept: the error estimate is NOT scaled by dt
+    (:1014-1017), the loop does not clip the last step to T (:1001)."""
+    rka, rkE, _ = dopri45_coeffs()
+    Q = [q.copy() for q in Q]
+    dt0 = dt
+    K = [None] * 7
+    K[0] = rhs_fun(Q)[0]
+    t, i, prev = 0.0, 0, 0.0
+    hist = {"t": [0.0], "dt": [dt], "err": [0.0], "rhstest": [0.0], "rhstest_visc": [0.0], "accepted": []}
+    while t < T and i < max_attempts:
+        for k in range(1, 7):
+            kk = [np.zeros_like(q) for q in Q]
+            for s_ in range(k):
+                kk = [a + rka[k, s_] * b for a, b in zip(kk, K[s_])]
+            Qtmp = [q + dt * a for q, a in zip(Q, kk)]
+            K[k], rt, rtv = rhs_fun(Qtmp)
+        ev = [np.zeros_like(q) for q in Q]
+        for s_ in range(7):
+            ev = [a + rkE[s_] * b for a, b in zip(ev, K[s_])]
+        err = 0.0
+        for f in range(len(Q)):
+            err += np.sum((np.abs(ev[f]) / (err_tol * (1 + np.abs(Q[f])))) ** 2)
+        err = np.sqrt(err / (Q[0].size * 4))
+        ok = err < 1.0
+        if ok:
+            Q = Qtmp
+            t += dt
+            K[0] = K[6]
+        order = 5
+        dtnew = .8 * dt * (.9 / err) ** (.4 / (order + 1))
+        if i > 0:
+            dtnew *= (prev / max(1e-14, err)) ** (.3 / (order + 1))
+        dt = max(min(10 * dt0, dtnew), 1e-9)
+        prev = err
+        i += 1
+        hist["t"].append(t); hist["dt"].append(dt); hist["err"].append(err)
+        hist["rhstest"].append(rt); hist["rhstest_visc"].append(rtv); hist["accepted"].append(bool(ok))
+    return Q, hist

@@ -118,3 +118,26 @@ def test_golden_cns_fixture():
     scale = np.abs(g["rhs"]).max()
     assert np.abs(np.stack(r) - g["rhs"]).max() < 1e-12 * scale
     assert abs(rt - g["rhstest"]) < 1e-13 and abs(rtv - g["rhstest_visc"]) < 1e-13
+
+
+def test_dopri45_coefficients_and_controller():
+    """Butcher-table consistency (rows sum to c, 5th-order weights sum to 1, error weights to 0) and a short
+    adaptive run of the cavity: steps are accepted, dt grows from the conservative start, entropy decays."""
+    a, E, c = cns.dopri45_coeffs()
+    assert np.abs(a.sum(axis=1) - c).max() < 1e-14
+    assert abs(a[6].sum() - 1) < 1e-14 and abs(E.sum()) < 1e-15
+    rd, md, ops, bc, Q = cns.setup_cavity("quad", 2, 3)
+    par = cns.cavity_params()
+    Q1, hist = cns.dopri45(Q, lambda q: cns.rhsRK(q, md, ops, bc, par), T=1e9, dt=1e-3, max_attempts=6)
+    assert all(np.isfinite(q).all() for q in Q1)
+    assert any(hist["accepted"]) and hist["t"][-1] > 0
+    assert hist["dt"][-1] > hist["dt"][0]
+    assert hist["rhstest"][-1] <= 1e-12
+    # against a fine-step LSRK45 integration to the same time
+    from oracle import solvers as SV
+    T = hist["t"][-1]
+    n = 40
+    Qr, res = [q.copy() for q in Q], [np.zeros_like(q) for q in Q]
+    for _ in range(n):
+        Qr, res, _ = SV.lsrk45_step(Qr, res, T / n, lambda q, w: cns.rhsRK(q, md, ops, bc, par)[:2])
+    assert max(np.abs(x - y).max() for x, y in zip(Q1, Qr)) < 1e-5
