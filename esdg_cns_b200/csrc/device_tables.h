@@ -33,6 +33,7 @@ struct GenericParams {
     long long K;            // local elements
     long long trace_stride; // doubles per field of the trace array (Nfq*K + n_halo)
     double gamma, lf_scale, volume_scale;
+    double lg1, igm1x2;     // log(gamma-1), 1/(2(gamma-1)) (host-computed)
     // operators
     Ell Vq;                 // Nq x Ns   (modal only)
     Ell Proj;               // collocated: Ef (Nfq x Nq); modal: VhP (Nh x Nq)
@@ -59,6 +60,10 @@ struct GenericParams {
     int want_rhstest;
     double* rhstest_partial; // one double per CTA
     int* bad_flag;
+    // operator tables are copied into shared memory at kernel start when they fit (byte offset of the table
+    // region in dynamic shared memory; 0 = leave them in global memory)
+    int stage_tables;
+    unsigned table_off;
 };
 
 }  // namespace esdg

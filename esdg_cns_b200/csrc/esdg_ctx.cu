@@ -21,6 +21,7 @@ void fill_params(esdg_ctx* ctx, GenericParams& p) {
     p.K = d.K;
     p.trace_stride = ctx->trace_stride;
     p.gamma = d.gamma; p.lf_scale = d.lf_scale; p.volume_scale = d.volume_scale;
+    p.lg1 = std::log(d.gamma - 1.0); p.igm1x2 = 1.0 / (2.0 * (d.gamma - 1.0));
     p.Vq = ctx->Vq.view();
     p.Proj = ctx->Proj.view();
     p.Ph = ctx->Ph.view();
@@ -41,6 +42,8 @@ void fill_params(esdg_ctx* ctx, GenericParams& p) {
     p.want_rhstest = 0;
     p.rhstest_partial = ctx->partials;
     p.bad_flag = ctx->bad_flag;
+    p.stage_tables = ctx->stage_tables;
+    p.table_off = ctx->table_off;
 }
 
 int grid_blocks(const esdg_ctx* ctx) { return (int)((ctx->d.K + ctx->EB - 1) / ctx->EB); }
@@ -387,14 +390,22 @@ static int finalize_cns(esdg_ctx* ctx) {
     // launch shape: generic modal block + CNS extras
     int maxsm = 0;
     CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    size_t tbl = ell_stage_bytes(ctx->Vq.rows, ctx->Vq.width) + ell_stage_bytes(ctx->Proj.rows, ctx->Proj.width) +
+                 ell_stage_bytes(ctx->Ph.rows, ctx->Ph.width) + ell_stage_bytes(ctx->Lf.rows, ctx->Lf.width) +
+                 pair_stage_bytes(Nh, ctx->qp_width) + ell_stage_bytes(c.Pq.rows, c.Pq.width) +
+                 ell_stage_bytes(c.Vf.rows, c.Vf.width) + ell_stage_bytes(c.Dr.rows, c.Dr.width) +
+                 ell_stage_bytes(c.Ds.rows, c.Ds.width);
+    ctx->stage_tables = tbl <= 64 * 1024 && getenv("ESDG_STAGE_TABLES") != nullptr;   // see esdg_finalize
+    if (!ctx->stage_tables) tbl = 0;
     auto bytes = [&](int EB) {
         return generic_smem_bytes(2, EB, d.Ns, d.Nq, d.Nfq, Nh, 0) + cns_extra_doubles(EB, d.Ns, d.Nq, d.Nfq) * sizeof(double);
     };
     int EB = std::min(16, std::max(1, ESDG_GENERIC_MAX_THREADS / Nh));
-    while (EB > 1 && bytes(EB) > (size_t)maxsm / 2) --EB;
-    if (bytes(EB) > (size_t)maxsm) return fail(ctx, ESDG_EINVAL, "esdg_finalize: element too large for shared memory (CNS)");
+    while (EB > 1 && bytes(EB) + tbl > (size_t)maxsm / 2) --EB;
+    if (bytes(EB) + tbl > (size_t)maxsm) return fail(ctx, ESDG_EINVAL, "esdg_finalize: element too large for shared memory (CNS)");
     ctx->EB = EB;
-    ctx->smem_bytes = bytes(EB);
+    ctx->table_off = (unsigned)bytes(EB);
+    ctx->smem_bytes = bytes(EB) + tbl;
     ctx->threads = std::min(ESDG_GENERIC_MAX_THREADS, ((EB * Nh + 31) / 32) * 32);
     CK(cudaFuncSetAttribute(k_cns_traces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
     CK(cudaFuncSetAttribute(k_cns_sigma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
@@ -545,11 +556,20 @@ int esdg_finalize(esdg_ctx* ctx) {
     // ---- launch shape ------------------------------------------------------------
     int maxsm = 0;
     CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    // operator tables go to shared memory when they are small next to the element data (<= 48 KB)
+    size_t tbl = ell_stage_bytes(ctx->Vq.rows, ctx->Vq.width) + ell_stage_bytes(ctx->Proj.rows, ctx->Proj.width) +
+                 ell_stage_bytes(ctx->Ph.rows, ctx->Ph.width) + ell_stage_bytes(ctx->Lf.rows, ctx->Lf.width) +
+                 pair_stage_bytes(Nh, ctx->qp_width);
+    // measured slower than L1-cached table reads on B200 (copying ~30 KB per 10-element CTA costs more than it
+    // saves: quad N=3 rhs 4.9 -> 5.2 ms): off unless ESDG_STAGE_TABLES=1
+    ctx->stage_tables = tbl <= 48 * 1024 && getenv("ESDG_STAGE_TABLES") != nullptr;
+    if (!ctx->stage_tables) tbl = 0;
     int EB = std::max(1, ESDG_GENERIC_MAX_THREADS / Nh);
     EB = std::min<int64_t>(EB, 16);
-    while (EB > 1 && generic_smem_bytes(DIM, EB, d.Ns, d.Nq, d.Nfq, Nh, d.collocated) > (size_t)maxsm / 2) --EB;
+    while (EB > 1 && generic_smem_bytes(DIM, EB, d.Ns, d.Nq, d.Nfq, Nh, d.collocated) + tbl > (size_t)maxsm / 2) --EB;
     ctx->EB = EB;
-    ctx->smem_bytes = generic_smem_bytes(DIM, EB, d.Ns, d.Nq, d.Nfq, Nh, d.collocated);
+    ctx->table_off = (unsigned)generic_smem_bytes(DIM, EB, d.Ns, d.Nq, d.Nfq, Nh, d.collocated);
+    ctx->smem_bytes = ctx->table_off + tbl;
     if (ctx->smem_bytes > (size_t)maxsm) return fail(ctx, ESDG_EINVAL, "esdg_finalize: element too large for shared memory");
     ctx->threads = std::min(ESDG_GENERIC_MAX_THREADS, ((EB * Nh + 31) / 32) * 32);
     if (DIM == 2) {

@@ -141,7 +141,7 @@ __device__ __forceinline__ void cns_entropy_vars(const GenericParams& p, Generic
         const int eb = i / p.Nq, q = i - eb * p.Nq;
         double U[4], V[4];
         ell_row<4>(p.Vq, q, s.U + (size_t)eb * 4 * p.Ns, p.Ns, U);
-        v_of_u<2>(U, p.gamma, V, bad);
+        v_of_u<2>(U, p.gamma, p.lg1, V, bad);
 #pragma unroll
         for (int f = 0; f < 4; ++f) s.V[(eb * 4 + f) * p.Nq + q] = V[f];
     }
@@ -149,9 +149,10 @@ __device__ __forceinline__ void cns_entropy_vars(const GenericParams& p, Generic
 }
 
 // Kernel 1: entropy-variable traces  VUf = (Vh Pq)[face rows] * v(Vq Q)
-__global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_traces(const __grid_constant__ CnsParams P) {
-    const GenericParams& p = P.g;
+__global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_traces(const __grid_constant__ CnsParams Pin) {
     extern __shared__ double smem[];
+    GenericParams p = Pin.g;
+    stage_generic_tables(p, smem, ST_VQ | ST_PROJ);   // visible after the first barrier of cns_entropy_vars
     GenericSmem<2> s(smem, p);
     const long long e0 = (long long)blockIdx.x * p.EB;
     const int nb = (int)min((long long)p.EB, p.K - e0);
@@ -168,9 +169,17 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_traces(const _
 }
 
 // Kernel 2: BR1 gradient of the projected entropy variables, sigma = K(v) theta, projection.
-__global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_sigma(const __grid_constant__ CnsParams P) {
-    const GenericParams& p = P.g;
+__global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_sigma(const __grid_constant__ CnsParams Pin) {
     extern __shared__ double smem[];
+    CnsParams P = Pin;
+    GenericParams& p = P.g;
+    {
+        char* sp = stage_generic_tables(p, smem, ST_VQ | ST_LF);
+        if (p.stage_tables) {
+            P.Pq = stage_ell(P.Pq, sp); P.Vf = stage_ell(P.Vf, sp);
+            P.Dr = stage_ell(P.Dr, sp); P.Ds = stage_ell(P.Ds, sp);
+        }   // visible after the first barrier of cns_entropy_vars
+    }
     GenericSmem<2> s(smem, p);
     CnsSmem c = cns_carve(s.R + p.EB * 4 * p.Ns, p);
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -206,7 +215,10 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_sigma(const __
             for (int f = 0; f < 4; ++f) VP[f] = p.traces[f * p.trace_stride + ip];
         }
         const int code = P.bc[self];
-        if (code & 3) bc_entropy_vars(P, code & 3, (code & 3) == 2 ? P.vlid[self] : 0.0, nxJ / sJ, nyJ / sJ, Vf, VP);
+        if (code & 3) {
+            const double isJ = fast_rcp(sJ);
+            bc_entropy_vars(P, code & 3, (code & 3) == 2 ? P.vlid[self] : 0.0, nxJ * isJ, nyJ * isJ, Vf, VP);
+        }
 #pragma unroll
         for (int f = 1; f < 4; ++f) {
             const double h = .5 * (VP[f] - Vf[f]);
@@ -225,11 +237,11 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_sigma(const __
         ell_row<3>(P.Ds, r, c.A + (size_t)(eb * 4 + 1) * Np, Np, vs);
         ell_row<3>(p.Lf, r, c.Jx + (size_t)(eb * 4 + 1) * Nfq, Nfq, lx);
         ell_row<3>(p.Lf, r, c.Jy + (size_t)(eb * 4 + 1) * Nfq, Nfq, ly);
-        const double J = G[4];
+        const double iJ = fast_rcp(G[4]);
 #pragma unroll
         for (int f = 0; f < 3; ++f) {
-            c.Tx[(eb * 3 + f) * Np + r] = (G[0] * vr[f] + G[1] * vs[f] + lx[f]) / J;
-            c.Ty[(eb * 3 + f) * Np + r] = (G[2] * vr[f] + G[3] * vs[f] + ly[f]) / J;
+            c.Tx[(eb * 3 + f) * Np + r] = (G[0] * vr[f] + G[1] * vs[f] + lx[f]) * iJ;
+            c.Ty[(eb * 3 + f) * Np + r] = (G[2] * vr[f] + G[3] * vs[f] + ly[f]) * iJ;
         }
     }
     __syncthreads();
@@ -244,15 +256,16 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_sigma(const __
         ell_row<3>(p.Vq, q, c.Ty + (size_t)eb * 3 * Np, Np, ty);
         const double v2 = v[1], v3 = v[2], v4 = v[3];
         const double lam = P.lam, mu = P.mu, l2m = lam + 2.0 * mu;
-        const double ic = 1.0 / (v4 * v4 * v4);
+        const double ic = fast_rcp(v4 * v4 * v4);
+        const double gmp = p.gamma * mu / P.Pr;
         const double v44 = v4 * v4;
         // Kxx, Kxy, Kyy rows/cols 2..4 (indices 0..2 here), :613-645
         const double xx00 = ic * -l2m * v44, xx02 = ic * l2m * v2 * v4, xx11 = ic * -mu * v44, xx12 = ic * mu * v3 * v4;
-        const double xx22 = ic * -(l2m * v2 * v2 + mu * v3 * v3 - p.gamma * mu * v4 / P.Pr);
+        const double xx22 = ic * -(l2m * v2 * v2 + mu * v3 * v3 - gmp * v4);
         const double xy01 = ic * -lam * v44, xy02 = ic * lam * v3 * v4, xy10 = ic * -mu * v44, xy12 = ic * mu * v2 * v4;
         const double xy20 = ic * mu * v3 * v4, xy21 = ic * lam * v2 * v4, xy22 = ic * (lam + mu) * (-v2 * v3);
         const double yy00 = ic * -mu * v44, yy02 = ic * mu * v2 * v4, yy11 = ic * -l2m * v44, yy12 = ic * l2m * v3 * v4;
-        const double yy22 = ic * -(l2m * v3 * v3 + mu * v2 * v2 - p.gamma * mu * v4 / P.Pr);
+        const double yy22 = ic * -(l2m * v3 * v3 + mu * v2 * v2 - gmp * v4);
         double sx[3], sy[3];
         // sigma_x[row] = sum_col Kxx[row,col] tx[col] + Kxy[row,col] ty[col]
         sx[0] = xx00 * tx[0] + xy01 * ty[1] + (xx02 * tx[2] + xy02 * ty[2]);
@@ -312,10 +325,15 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_sigma(const __
 }
 
 // Kernel 3: inviscid rhs + BR1 divergence + penalisation -> rhs or LSRK stage.
-__global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_rhs(const __grid_constant__ CnsParams P) {
-    const GenericParams& p = P.g;
+__global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_rhs(const __grid_constant__ CnsParams Pin) {
+    CnsParams P = Pin;
+    GenericParams& p = P.g;
     constexpr int NF = 4;
     extern __shared__ double smem[];
+    {
+        char* sp = stage_generic_tables(p, smem, ST_VQ | ST_PROJ | ST_PH | ST_LF | ST_QP);
+        if (p.stage_tables) { P.Dr = stage_ell(P.Dr, sp); P.Ds = stage_ell(P.Ds, sp); }
+    }   // visible after the first barrier of project_batch
     GenericSmem<2> s(smem, p);
     CnsSmem c = cns_carve(s.R + p.EB * 4 * p.Ns, p);
     s.Vface = c.Vfc;
@@ -341,8 +359,8 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_rhs(const __gr
         const long long e = e0 + eb;
         const double* g = p.geo + e * p.geo_stride + 5 + (k / p.Nfp) * 3;
         const double nJ[2] = {g[0], g[1]};
-        const double sJ = g[2], isJ = 1.0 / sJ;
-        const double nx = nJ[0] / sJ, ny = nJ[1] / sJ;
+        const double sJ = g[2], isJ = fast_rcp(sJ);
+        const double nx = nJ[0] * isJ, ny = nJ[1] * isJ;
         const long long self = e * Nfq + k;
         const long long ip = p.mapP[self];
         const int code = P.bc[self];
@@ -365,7 +383,7 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_rhs(const __gr
         } else {
 #pragma unroll
             for (int f = 0; f < NF; ++f) VPv[f] = p.traces[f * p.trace_stride + ip];
-            u_of_v<2>(VPv, p.gamma, UP);
+            u_of_v<2>(VPv, p.gamma, p.lg1, UP);
             prim_of_u<2>(UP, p.gamma, PP);
         }
         if (kind) {
@@ -376,7 +394,7 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_rhs(const __gr
             PP.vel[1] = PM.vel[1] - 2 * Un * ny;
         }
         double F[NF];
-        ec_flux_dot<2>(PP, PM, nJ, 2.0 * (p.gamma - 1.0), F);          // update_flux! evaluates (QP, QM) (:311)
+        ec_flux_dot<2>(PP, PM, nJ, p.igm1x2, F);          // update_flux! evaluates (QP, QM) (:311)
         if (p.lf_scale != 0.0) {
             const double unM = (UM[1] * nJ[0] + UM[2] * nJ[1]) * isJ;
             const double unP = (UP[1] * nJ[0] + UP[2] * nJ[1]) * isJ;
@@ -406,13 +424,14 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_rhs(const __gr
         // penalisation tau*[[v]] (:817-840)
         if (P.viscous_dissp) {
             if (kind) bc_entropy_vars(P, kind, vlid, nx, ny, VM, VPv);
-            const double tau = -1.0 / P.Re / VM[3];
+            const double iv4 = fast_rcp(VM[3]);
+            const double tau = -iv4 / P.Re;
             const double d1 = VPv[1] - VM[1], d2 = VPv[2] - VM[2], d3 = VPv[3] - VM[3];
             double p3 = tau * d3;
             if (code & 4) {
                 const double a1 = .5 * (VPv[1] + VM[1]), a2 = .5 * (VPv[2] + VM[2]);
-                p3 = P.bctype == 1 ? -tau * (a1 * d1 + a2 * d2) / VM[3]
-                                   : -tau * (a1 * d1 + a2 * d2 + d3 * d3 / 2) / VM[3];
+                p3 = P.bctype == 1 ? -tau * (a1 * d1 + a2 * d2) * iv4
+                                   : -tau * (a1 * d1 + a2 * d2 + d3 * d3 * .5) * iv4;
             }
             c.Jy[(eb * 4 + 1) * Nfq + k] = tau * d1;
             c.Jy[(eb * 4 + 2) * Nfq + k] = tau * d2;
@@ -432,18 +451,19 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_rhs(const __gr
         Pi.rho = w[r]; Pi.vel[0] = w[p.Nh + r]; Pi.vel[1] = w[2 * p.Nh + r];
         Pi.beta = w[3 * p.Nh + r]; Pi.lrho = w[4 * p.Nh + r]; Pi.lbeta = w[5 * p.Nh + r];
         double acc[NF] = {0.0, 0.0, 0.0, 0.0};
+        const double G0 = G[0], G1 = G[1], G2 = G[2], G3 = G[3];
         const int n = p.Qp.cnt[r];
         for (int k = 0; k < n; ++k) {
             const int j = p.Qp.col[r * p.Qp.width + k];
             const double* cq = p.Qp.c + (size_t)(r * p.Qp.width + k) * 3;
             double cc[2];
-            cc[0] = fma(G[1], cq[1], G[0] * cq[0]);
-            cc[1] = fma(G[3], cq[1], G[2] * cq[0]);
+            cc[0] = fma(G1, cq[1], G0 * cq[0]);
+            cc[1] = fma(G3, cq[1], G2 * cq[0]);
             Prim<2> Pj;
             Pj.rho = w[j]; Pj.vel[0] = w[p.Nh + j]; Pj.vel[1] = w[2 * p.Nh + j];
             Pj.beta = w[3 * p.Nh + j]; Pj.lrho = w[4 * p.Nh + j]; Pj.lbeta = w[5 * p.Nh + j];
             double F[NF];
-            ec_flux_dot<2>(Pi, Pj, cc, 2.0 * (p.gamma - 1.0), F);
+            ec_flux_dot<2>(Pi, Pj, cc, p.igm1x2, F);
 #pragma unroll
             for (int f = 0; f < NF; ++f) acc[f] += F[f];
         }
@@ -466,12 +486,12 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_rhs(const __gr
         ell_row<3>(P.Ds, r, c.Tx + (size_t)eb * 3 * Np, Np, sxs);
         ell_row<3>(P.Dr, r, c.Ty + (size_t)eb * 3 * Np, Np, syr);
         ell_row<3>(P.Ds, r, c.Ty + (size_t)eb * 3 * Np, Np, sys);
-        const double mJ = -1.0 / J;
+        const double iJ = fast_rcp(J), mJ = -iJ;
         double rr[NF], rv[NF];
         rv[0] = 0.0;
 #pragma unroll
         for (int f = 0; f < 3; ++f)
-            rv[1 + f] = (G[0] * sxr[f] + G[1] * sxs[f] + G[2] * syr[f] + G[3] * sys[f] + sv[1 + f]) / J + pn[1 + f];
+            rv[1 + f] = (G[0] * sxr[f] + G[1] * sxs[f] + G[2] * syr[f] + G[3] * sys[f] + sv[1 + f]) * iJ + pn[1 + f];
 #pragma unroll
         for (int f = 0; f < NF; ++f) rr[f] = (b[f] + p.volume_scale * a[f]) * mJ + rv[f];
         const long long gidx = e * Np + r;

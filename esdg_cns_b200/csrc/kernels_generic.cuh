@@ -44,6 +44,55 @@ inline size_t generic_smem_bytes(int DIM, int EB, int Ns, int Nq, int Nfq, int N
     return n * sizeof(double);
 }
 
+// ---- operator tables -> shared memory ------------------------------------------------------------
+// The ELL tables are read once per (row, entry) by every element of the batch; from global memory
+// (L1-cached) those reads were the top stall of the table-driven kernels (lg_throttle / long_scoreboard).
+__host__ __device__ inline size_t ell_stage_bytes(int rows, int width) {
+    const size_t n = (size_t)rows * width;
+    return n * 8 + ((n + 1) / 2) * 8 + (((size_t)rows + 1) / 2) * 8;
+}
+__host__ __device__ inline size_t pair_stage_bytes(int rows, int width) {
+    const size_t n = (size_t)rows * width;
+    return n * 24 + ((n + 1) / 2) * 8 + (((size_t)rows + 1) / 2) * 8;
+}
+
+__device__ __forceinline__ Ell stage_ell(const Ell& g, char*& sp) {
+    const int n = g.rows * g.width;
+    double* v = (double*)sp;
+    int* c = (int*)(sp + (size_t)n * 8);
+    int* cn = (int*)(sp + (size_t)n * 8 + (size_t)((n + 1) / 2) * 8);
+    sp += ell_stage_bytes(g.rows, g.width);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { v[i] = g.val[i]; c[i] = g.col[i]; }
+    for (int i = threadIdx.x; i < g.rows; i += blockDim.x) cn[i] = g.cnt[i];
+    return Ell{g.rows, g.width, cn, c, v};
+}
+
+__device__ __forceinline__ PairEll stage_pairs(const PairEll& g, char*& sp) {
+    const int n = g.rows * g.width;
+    double* v = (double*)sp;
+    int* c = (int*)(sp + (size_t)n * 24);
+    int* cn = (int*)(sp + (size_t)n * 24 + (size_t)((n + 1) / 2) * 8);
+    sp += pair_stage_bytes(g.rows, g.width);
+    for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) v[i] = g.c[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) c[i] = g.col[i];
+    for (int i = threadIdx.x; i < g.rows; i += blockDim.x) cn[i] = g.cnt[i];
+    return PairEll{g.rows, g.width, cn, c, v};
+}
+
+enum { ST_VQ = 1, ST_PROJ = 2, ST_PH = 4, ST_LF = 8, ST_QP = 16 };
+
+// returns the running pointer so that callers (CNS) can append their own tables; the caller syncs
+__device__ __forceinline__ char* stage_generic_tables(GenericParams& p, double* smem, int mask) {
+    char* sp = (char*)smem + p.table_off;
+    if (!p.stage_tables) return sp;
+    if (mask & ST_VQ) p.Vq = stage_ell(p.Vq, sp);
+    if (mask & ST_PROJ) p.Proj = stage_ell(p.Proj, sp);
+    if (mask & ST_PH) p.Ph = stage_ell(p.Ph, sp);
+    if (mask & ST_LF) p.Lf = stage_ell(p.Lf, sp);
+    if (mask & ST_QP) p.Qp = stage_pairs(p.Qp, sp);
+    return sp;
+}
+
 // Phases 0-2: stage Q, entropy-project, build Qh (+logs) at all hybridized points.
 template <int DIM>
 __device__ __forceinline__ void project_batch(const GenericParams& p, GenericSmem<DIM>& s, long long e0, int nb,
@@ -77,7 +126,7 @@ __device__ __forceinline__ void project_batch(const GenericParams& p, GenericSme
                 for (int f = 0; f < NF; ++f) U[f] = fma(a, s.U[(eb * NF + f) * p.Ns + c], U[f]);
             }
         }
-        v_of_u<DIM>(U, p.gamma, V, bad);
+        v_of_u<DIM>(U, p.gamma, p.lg1, V, bad);
 #pragma unroll
         for (int f = 0; f < NF; ++f) s.V[(eb * NF + f) * p.Nq + q] = V[f];
     }
@@ -101,7 +150,7 @@ __device__ __forceinline__ void project_batch(const GenericParams& p, GenericSme
 #pragma unroll
                 for (int f = 0; f < NF; ++f) V[f] = fma(a, s.V[(eb * NF + f) * p.Nq + c], V[f]);
             }
-            u_of_v<DIM>(V, p.gamma, U);
+            u_of_v<DIM>(V, p.gamma, p.lg1, U);
             if (!p.collocated && r < p.Nq) {
                 // projected entropy variables at volume points are the rhstest weights (tri :180)
 #pragma unroll
@@ -131,9 +180,11 @@ __device__ __forceinline__ void project_batch(const GenericParams& p, GenericSme
 
 // Kernel A: face traces of the (projected) conservative variables.
 template <int DIM>
-__global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_traces(const __grid_constant__ GenericParams p) {
+__global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_traces(const __grid_constant__ GenericParams pin) {
     constexpr int NF = DIM + 2;
     extern __shared__ double smem[];
+    GenericParams p = pin;
+    stage_generic_tables(p, smem, ST_VQ | ST_PROJ);   // visible after the first barrier of project_batch
     GenericSmem<DIM> s(smem, p);
     const long long e0 = (long long)blockIdx.x * p.EB;
     const int nb = (int)min((long long)p.EB, p.K - e0);
@@ -151,9 +202,11 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_traces(con
 
 // Kernel B: surface + volume + lift + (rhs | LSRK stage).
 template <int DIM>
-__global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_rhs(const __grid_constant__ GenericParams p) {
+__global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_rhs(const __grid_constant__ GenericParams pin) {
     constexpr int NF = DIM + 2;
     extern __shared__ double smem[];
+    GenericParams p = pin;
+    stage_generic_tables(p, smem, ST_VQ | ST_PROJ | ST_PH | ST_LF | ST_QP);   // visible after the first barrier of project_batch
     GenericSmem<DIM> s(smem, p);
     const int tid = threadIdx.x, nt = blockDim.x;
     const long long e0 = (long long)blockIdx.x * p.EB;
@@ -171,7 +224,7 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_rhs(const 
 #pragma unroll
         for (int d = 0; d < DIM; ++d) nJ[d] = g[d];
         const double sJ = g[DIM];
-        const double isJ = 1.0 / sJ;
+        const double isJ = fast_rcp(sJ);
         // exterior state
         const long long ip = p.mapP[e * p.Nfq + k];
         double UP[NF], UM[NF];
@@ -190,7 +243,7 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_rhs(const 
         PM.lbeta = w[(3 + DIM) * p.Nh];
         prim_of_u<DIM>(UP, p.gamma, PP);
         double F[NF];
-        ec_flux_dot<DIM>(PM, PP, nJ, 2.0 * (p.gamma - 1.0), F);
+        ec_flux_dot<DIM>(PM, PP, nJ, p.igm1x2, F);
         if (p.lf_scale != 0.0) {
             double unM = 0.0, unP = 0.0;
 #pragma unroll
@@ -224,6 +277,9 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_rhs(const 
         double acc[NF];
 #pragma unroll
         for (int f = 0; f < NF; ++f) acc[f] = 0.0;
+        double Gr[DIM * DIM];
+#pragma unroll
+        for (int q = 0; q < DIM * DIM; ++q) Gr[q] = G[q];
         const int n = p.Qp.cnt[r];
         for (int k = 0; k < n; ++k) {
             const int j = p.Qp.col[r * p.Qp.width + k];
@@ -234,7 +290,7 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_rhs(const 
             for (int d = 0; d < DIM; ++d) {
                 double a = 0.0;
 #pragma unroll
-                for (int kk = 0; kk < DIM; ++kk) a = fma(G[d * DIM + kk], cq[kk], a);
+                for (int kk = 0; kk < DIM; ++kk) a = fma(Gr[d * DIM + kk], cq[kk], a);
                 c[d] = a;
             }
             Prim<DIM> Pj;
@@ -245,7 +301,7 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_rhs(const 
             Pj.lrho = w[(2 + DIM) * p.Nh + j];
             Pj.lbeta = w[(3 + DIM) * p.Nh + j];
             double F[NF];
-            ec_flux_dot<DIM>(Pi, Pj, c, 2.0 * (p.gamma - 1.0), F);
+            ec_flux_dot<DIM>(Pi, Pj, c, p.igm1x2, F);
 #pragma unroll
             for (int f = 0; f < NF; ++f) acc[f] += F[f];
         }
@@ -277,7 +333,7 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_rhs(const 
 #pragma unroll
             for (int f = 0; f < NF; ++f) b[f] = fma(v, s.Fl[(eb * NF + f) * p.Nfq + c], b[f]);
         }
-        const double mJ = -1.0 / J;
+        const double mJ = -fast_rcp(J);
         double rr[NF];
 #pragma unroll
         for (int f = 0; f < NF; ++f) rr[f] = (b[f] + p.volume_scale * a[f]) * mJ;
