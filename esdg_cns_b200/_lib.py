@@ -56,6 +56,7 @@ _SIGNATURES = {
     "esdg_upload_state": (C.c_int, [C.c_void_p, C.c_void_p]),
     "esdg_download_state": (C.c_int, [C.c_void_p, C.c_void_p]),
     "esdg_lsrk45_step": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p]),
+    "esdg_lsrk45_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int]),
     "esdg_dopri45_init": (C.c_int, [C.c_void_p]),
     "esdg_dopri45_step": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.c_double,
                                     C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_void_p]),

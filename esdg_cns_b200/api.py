@@ -157,6 +157,16 @@ class Solver:
         self._ck(self._lib.esdg_lsrk45_step(self._ctx, float(dt), int(nsteps), None))
         return None
 
+    def lsrk45_host(self, Q, dt, nsteps=1, out=None):
+        """``nsteps`` LSRK45 steps of the HOST state ``Q`` (list of Ns x K column-major arrays); the result is
+        written to ``out`` (default: in place).  Upload and download are pipelined with the first / last stage."""
+        qin = self._host_fields(Q)
+        qout = qin if out is None else self._host_fields(out)
+        if any(a is not b for a, b in zip(qin, Q)) and out is None:
+            raise ValueError("lsrk45_host works in place: pass column-major float64 arrays (or give out=)")
+        self._ck(self._lib.esdg_lsrk45_host(self._ctx, L.ptr_array(qin), L.ptr_array(qout), float(dt), int(nsteps)))
+        return qout
+
     def dopri45(self, T, dt, err_tol=1e-5, max_attempts=10 ** 9):
         """The adaptive time loop of dg2D_CNS_cavity_optimized.jl:974-1053 on the resident state:
         ``while t < T`` DOPRI45 steps with FSAL and the PI controller.  Returns the histories the

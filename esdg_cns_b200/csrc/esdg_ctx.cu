@@ -247,6 +247,10 @@ int esdg_destroy(esdg_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& t : ctx->timers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (cudaEvent_t e : ctx->chunk_up) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->chunk_done) cudaEventDestroy(e);
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     for (void* p : ctx->allocs) cudaFree(p);
     hexfast_destroy(ctx);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -691,6 +695,112 @@ int esdg_lsrk45_step(esdg_ctx* ctx, double dt, int nsteps, double* rhstest_last)
         return check_bad(ctx);
     }
     return ESDG_OK;
+}
+
+// ---- pipelined host step -----------------------------------------------------------------------------
+// upload -> nsteps x 5 stages -> download with the PCIe copies overlapped: the state travels in element
+// chunks; the traces of a chunk are computed as soon as it has landed and the first stage runs on every
+// chunk whose neighbours (through mapP) have landed too, while later chunks are still in flight; the
+// last stage runs chunk by chunk with the device->host copy of each finished chunk behind it.
+static int build_chunks(esdg_ctx* ctx) {
+    const esdg_desc& d = ctx->d;
+    const long long K = d.K;
+    const int EB = ctx->hex ? 2 * ctx->hex->EB : 1;               // even element offsets keep the TMA path aligned
+    int nchunk = (int)std::min<long long>(8, K / std::max<long long>(4096, EB));
+    if (nchunk < 2) nchunk = 1;
+    long long per = ((K + nchunk - 1) / nchunk + EB - 1) / EB * EB;
+    ctx->chunk_begin.clear();
+    for (long long b = 0; b < K; b += per) ctx->chunk_begin.push_back(b);
+    ctx->chunk_begin.push_back(K);
+    nchunk = (int)ctx->chunk_begin.size() - 1;
+    ctx->chunk_dep.assign(nchunk, 0u);
+    auto chunk_of = [&](long long e) {
+        int c = (int)(e / per);
+        return c < nchunk ? c : nchunk - 1;
+    };
+    for (int c = 0; c < nchunk; ++c) {
+        unsigned m = 1u << c;
+        for (long long e = ctx->chunk_begin[c]; e < ctx->chunk_begin[c + 1]; ++e)
+            for (int k = 0; k < d.Nfq; ++k) m |= 1u << chunk_of((ctx->mapP_host[(size_t)(e * d.Nfq + k)] - 1) / d.Nfq);
+        ctx->chunk_dep[c] = m;
+    }
+    CK(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    ctx->chunk_up.resize(nchunk);
+    ctx->chunk_done.resize(nchunk);
+    for (int c = 0; c < nchunk; ++c) {
+        CK(cudaEventCreateWithFlags(&ctx->chunk_up[c], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->chunk_done[c], cudaEventDisableTiming));
+    }
+    return ESDG_OK;
+}
+
+int esdg_lsrk45_host(esdg_ctx* ctx, const double* const* Q_in, double* const* Q_out, double dt, int nsteps) {
+    int rc = require_ready(ctx, "esdg_lsrk45_host");
+    if (rc) return rc;
+    if (!Q_in || !Q_out || nsteps < 1) return fail(ctx, ESDG_EINVAL, "esdg_lsrk45_host: bad argument");
+    if (ctx->d.n_halo != 0) return fail(ctx, ESDG_EINVAL, "esdg_lsrk45_host: single-GPU contexts only");
+    if (!ctx->hex || ctx->cns.on) {                               // other paths: plain upload / steps / download
+        if ((rc = esdg_upload_state(ctx, Q_in))) return rc;
+        if ((rc = esdg_lsrk45_step(ctx, dt, nsteps, nullptr))) return rc;
+        return esdg_download_state(ctx, Q_out);
+    }
+    if (ctx->chunk_begin.empty() && (rc = build_chunks(ctx))) return rc;
+    HexFast* h = ctx->hex;
+    const int nchunk = (int)ctx->chunk_begin.size() - 1;
+    const size_t n = (size_t)ctx->d.Ns * ctx->d.K;
+    const int Ns = ctx->d.Ns;
+    ctx->dopri.ready = false;
+    // order the copy stream after everything already queued on the main stream
+    cudaEvent_t fence = ctx->chunk_done[0];
+    CK(cudaEventRecord(fence, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->h2d_stream, fence, 0));
+    CK(cudaMemsetAsync(ctx->res, 0, ctx->NF * n * sizeof(double), ctx->stream));
+    h->prod ^= 1;                                                 // fresh trace / log buffers for the uploaded state
+    h->cons = h->prod ^ 1;
+    const int bufU = h->prod;
+    unsigned landed = 0, started = 0;
+    auto first_stage = [&](int c) -> int {
+        h->cons = bufU;
+        h->prod = bufU ^ 1;
+        started |= 1u << c;
+        return hexfast_stage_range(ctx, ctx->Q, 1, RK4A[0], RK4B[0], dt, ctx->chunk_begin[c],
+                                   ctx->chunk_begin[c + 1] - ctx->chunk_begin[c]);
+    };
+    for (int c = 0; c < nchunk; ++c) {
+        const long long b = ctx->chunk_begin[c], len = ctx->chunk_begin[c + 1] - b;
+        for (int f = 0; f < ctx->NF; ++f)
+            CK(cudaMemcpyAsync(ctx->Q + f * n + b * Ns, Q_in[f] + b * Ns, (size_t)len * Ns * sizeof(double),
+                               cudaMemcpyHostToDevice, ctx->h2d_stream));
+        CK(cudaEventRecord(ctx->chunk_up[c], ctx->h2d_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_up[c], 0));
+        h->prod = bufU;
+        h->cons = bufU ^ 1;
+        if ((rc = hexfast_traces_range(ctx, ctx->Q, b, len))) return rc;
+        landed |= 1u << c;
+        for (int q = 0; q < nchunk; ++q)
+            if (!(started & (1u << q)) && (ctx->chunk_dep[q] & ~landed) == 0 && (rc = first_stage(q))) return rc;
+    }
+    h->cons = bufU;
+    h->prod = bufU ^ 1;
+    ctx->traces_valid = true;
+    const int nstage = 5 * nsteps;
+    for (int sidx = 1; sidx < nstage - 1; ++sidx)
+        if ((rc = do_stage(ctx, ctx->Q, 1, RK4A[sidx % 5], RK4B[sidx % 5], dt, 0, ESDG_PART_ALL))) return rc;
+    // last stage, chunk by chunk, each followed by its download
+    h->cons = h->prod;
+    h->prod = h->cons ^ 1;
+    for (int c = 0; c < nchunk; ++c) {
+        const long long b = ctx->chunk_begin[c], len = ctx->chunk_begin[c + 1] - b;
+        if ((rc = hexfast_stage_range(ctx, ctx->Q, 1, RK4A[4], RK4B[4], dt, b, len))) return rc;
+        CK(cudaEventRecord(ctx->chunk_done[c], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->chunk_done[c], 0));
+        for (int f = 0; f < ctx->NF; ++f)
+            CK(cudaMemcpyAsync(Q_out[f] + b * Ns, ctx->Q + f * n + b * Ns, (size_t)len * Ns * sizeof(double),
+                               cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    }
+    CK(cudaStreamSynchronize(ctx->d2h_stream));
+    return check_bad(ctx);
 }
 
 int esdg_sync(esdg_ctx* ctx) {

@@ -138,12 +138,13 @@ int set_attrs(esdg_ctx* ctx) {
 }
 
 template <int n>
-int launch_traces_n(esdg_ctx* ctx, const double* Q) {
+int launch_traces_n(esdg_ctx* ctx, const double* Q, long long e_begin = 0, long long e_count = -1) {
     HexFast* h = ctx->hex;
     HexParams p;
     fill_hex_params<n>(ctx, p);
     p.Q = Q;
-    const int blocks = (int)((ctx->d.K + h->EB_tr - 1) / h->EB_tr);
+    if (e_count >= 0) { p.e_begin = e_begin; p.e_count = e_count; }
+    const int blocks = (int)((p.e_count + h->EB_tr - 1) / h->EB_tr);
     tick(ctx, "hex_traces");
     k_hex_traces<n><<<blocks, h->threads_tr, h->smem_traces, ctx->stream>>>(p);
     tock(ctx);
@@ -287,6 +288,39 @@ int hexfast_traces(esdg_ctx* ctx, const double* Q) {
         case 5: return launch_traces_n<5>(ctx, Q);
     }
     return fail(ctx, ESDG_EINVAL, "hex path: unsupported degree");
+}
+
+int hexfast_traces_range(esdg_ctx* ctx, const double* Q, long long e_begin, long long e_count) {
+    switch (ctx->hex->n) {
+        case 2: return launch_traces_n<2>(ctx, Q, e_begin, e_count);
+        case 3: return launch_traces_n<3>(ctx, Q, e_begin, e_count);
+        case 4: return launch_traces_n<4>(ctx, Q, e_begin, e_count);
+        case 5: return launch_traces_n<5>(ctx, Q, e_begin, e_count);
+    }
+    return fail(ctx, ESDG_EINVAL, "hex path: unsupported degree");
+}
+
+int hexfast_stage_range(esdg_ctx* ctx, const double* Q, int mode, double a, double b, double dt, long long e_begin, long long e_count) {
+    HexFast* h = ctx->hex;
+    HexParams p;
+    switch (h->n) {
+        case 2: fill_hex_params<2>(ctx, p); break;
+        case 3: fill_hex_params<3>(ctx, p); break;
+        case 4: fill_hex_params<4>(ctx, p); break;
+        default: fill_hex_params<5>(ctx, p); break;
+    }
+    p.Q = Q;
+    p.e_begin = e_begin;
+    p.e_count = e_count;
+    p.mode = mode;
+    p.rk_a = a; p.rk_b = b; p.dt = dt;
+    const int blocks = (int)((e_count + h->EB - 1) / h->EB);
+    switch (h->n) {
+        case 2: return launch_stage_n<2>(ctx, p, blocks);
+        case 3: return launch_stage_n<3>(ctx, p, blocks);
+        case 4: return launch_stage_n<4>(ctx, p, blocks);
+        default: return launch_stage_n<5>(ctx, p, blocks);
+    }
 }
 
 int hexfast_stage(esdg_ctx* ctx, const double* Q, int mode, double a, double b, double dt, int want_rhstest, int part) {

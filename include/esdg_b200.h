@@ -137,6 +137,11 @@ int esdg_download_state(esdg_ctx* ctx, double* const* Q);
  * unless rhstest_last != NULL (then rhstest of the final stage is returned). */
 int esdg_lsrk45_step(esdg_ctx* ctx, double dt, int nsteps, double* rhstest_last);
 
+/* The same loop for HOST state (the Julia `Q`, `Vector{Matrix{Float64}}`): Q_in -> nsteps LSRK45 steps ->
+ * Q_out (may alias Q_in), with the host<->device copies pipelined against the first and last stage
+ * (chunks of elements; pinned host memory is needed for the copies to overlap).  Synchronous. */
+int esdg_lsrk45_host(esdg_ctx* ctx, const double* const* Q_in, double* const* Q_out, double dt, int nsteps);
+
 /* DOPRI45 adaptive driver of the CNS scripts (dg2D_CNS_cavity_optimized.jl:919-934 coefficients,
  * :974-1053 loop): FSAL, Hairer error semi-norm with tolerance err_tol (the script's errTol = 1e-5,
  * :1017), step accepted iff errEst < 1, P / PI step-size controller clipped to [1e-9, 10*dt0].
