@@ -124,6 +124,7 @@ int set_attrs(esdg_ctx* ctx) {
         h->EB = LD::EB;
         h->threads = LD::THREADS;
         h->smem_stage = (size_t)LD::SMEM_DOUBLES * sizeof(double);
+        if (const char* ex = getenv("ESDG_HEX_EXTRA_SMEM_KB")) h->smem_stage += (size_t)atoi(ex) * 1024;   // occupancy experiments
         CK(cudaFuncSetAttribute(k_hex_stage_line<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage));
         CK(cudaFuncSetAttribute(k_hex_stage_line<n, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage));
     } else {

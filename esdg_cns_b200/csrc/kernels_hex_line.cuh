@@ -76,7 +76,10 @@ struct LineDims {
 #endif
     static constexpr int EB = n == 5 ? ESDG_LINE_EB5 : (n == 4 ? 2 : (n == 3 ? 4 : 8));
     static constexpr int THREADS = ((EB * NL + 31) / 32) * 32;
-    static constexpr int MINB = (n == 5 && ESDG_LINE_EB5 == 2) ? 2 : 4;   // CTAs per SM the register budget is sized for
+#ifndef ESDG_LINE_MINB5
+#define ESDG_LINE_MINB5 2
+#endif
+    static constexpr int MINB = (n == 5 && ESDG_LINE_EB5 == 2) ? ESDG_LINE_MINB5 : 4;   // CTAs per SM the register budget is sized for
     static constexpr int EN = EB * Nq, EF = EB * Nfq;
     static constexpr int TAB = 5 * n + EB * 34;
     // WV[7][EN] WF[7][EF] P[7][EF] A[15][EN] Q[5][EN] R[5][EN]
@@ -498,7 +501,26 @@ __global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex
         for (int a = 0; a < n; ++a)
 #pragma unroll
             for (int f = 0; f < 5; ++f) acc[a][f] = 0.0;
+#ifndef ESDG_LINE_WC
+#define ESDG_LINE_WC 2   // pairs evaluated together in the line phase (1 lowers the register need by ~40)
+#endif
         // volume-volume pairs: acc_a += T[a][b] F(a,b), acc_b += T[b][a] F(a,b)
+#if ESDG_LINE_WC == 1
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            const int a = PT.a[k], b = PT.b[k];
+            NodeV<1> A, B;
+            set_lane(A, 0, nd[a]);
+            set_lane(B, 0, nd[b]);
+            VD<1> F[5];
+            pair_flux_v<1, DIAG>(A, B, g_1, c_igm, F);
+#pragma unroll
+            for (int f = 0; f < 5; ++f) {
+                acc[a][f] = fma(p.T[a * n + b], F[f].v[0], acc[a][f]);
+                acc[b][f] = fma(p.T[b * n + a], F[f].v[0], acc[b][f]);
+            }
+        }
+#else
 #pragma unroll
         for (int k = 0; k + 1 < NP; k += 2) {
             NodeV<2> A, B;
@@ -530,6 +552,7 @@ __global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex
                 acc[b][f] = fma(p.T[b * n + a], F[f].v[0], acc[b][f]);
             }
         }
+#endif
         // volume-face pairs: node a against the two face points its line ends in (lane = side)
         Node fn[2];
         int fidx[2];
@@ -550,6 +573,24 @@ __global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex
         double h[2][5];
 #pragma unroll
         for (int f = 0; f < 5; ++f) h[0][f] = h[1][f] = 0.0;
+#if ESDG_LINE_WC == 1
+#pragma unroll
+        for (int a = 0; a < n; ++a) {
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                NodeV<1> A, B;
+                set_lane(A, 0, nd[a]);
+                set_lane(B, 0, fn[side]);
+                VD<1> F[5];
+                pair_flux_v<1, DIAG>(A, B, g_1, c_igm, F);
+#pragma unroll
+                for (int f = 0; f < 5; ++f) {
+                    acc[a][f] = fma(side ? p.lpw[a] : -p.lmw[a], F[f].v[0], acc[a][f]);
+                    h[side][f] = fma(side ? p.lp[a] : p.lm[a], F[f].v[0], h[side][f]);
+                }
+            }
+        }
+#else
 #pragma unroll
         for (int a = 0; a < n; ++a) {
             NodeV<2> A;
@@ -565,6 +606,7 @@ __global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex
                 h[1][f] = fma(p.lp[a], F[f].v[1], h[1][f]);
             }
         }
+#endif
         // face rows: H = flux* -/+ sum_a l[a] F(a) (physical field order in shared memory); only the nodes
         // of THIS line lift from these two face points, so the lift (Lf as a 1-D sweep) is applied here
         {
