@@ -73,6 +73,19 @@ inline int build_ell(esdg_ctx* ctx, const HostMat& A, double tol, DevEll* out) {
     return ESDG_OK;
 }
 
+// dense column-major -> row-major, zero-padded to (ceil8(rows), ceil4(cols)), times `scale`; rows [r0, r0+nr)
+inline int build_dense(esdg_ctx* ctx, const HostMat& A, double scale, int r0, int nr, esdg::Dense* out) {
+    const int K = (int)A.cols, Mp = (nr + 7) / 8 * 8, Kp = (K + 3) / 4 * 4;
+    std::vector<double> h((size_t)Mp * Kp, 0.0);
+    for (int i = 0; i < nr; ++i)
+        for (int j = 0; j < K; ++j) h[(size_t)i * Kp + j] = scale * A.at(r0 + i, j);
+    double* d = nullptr;
+    int rc = dev_upload(ctx, &d, h);
+    if (rc) return rc;
+    *out = esdg::Dense{d, nr, K, Mp, Kp};
+    return ESDG_OK;
+}
+
 inline const HostMat* find(const std::map<std::string, HostMat>& m, const char* name) {
     auto it = m.find(name);
     return it == m.end() ? nullptr : &it->second;

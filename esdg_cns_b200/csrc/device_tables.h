@@ -2,6 +2,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "kernels_mma.cuh"
+
 namespace esdg {
 
 // Row-compressed (ELL) sparse matrix: row r holds `cnt[r]` entries at
@@ -40,6 +42,9 @@ struct GenericParams {
     Ell Ph;                 // Ns x Nh
     Ell Lf;                 // Ns x Nfq
     PairEll Qp;             // Nh rows
+    // modal path: the same operators dense + zero-padded for the tensor-core batch GEMMs (kernels_mma.cuh);
+    // dPh carries volume_scale, dProjF = face rows of VhP
+    Dense dVq, dProj, dProjF, dPh, dLf;
     const double* wq;       // Nq
     // geometry, per element: [e*geo_stride + ...]
     //   0..DIM*DIM-1 : G[d][k] = d(ref k)/d(x_d)*J  i.e. (rxJ,sxJ,txJ | ryJ,syJ,tyJ | rzJ,szJ,tzJ)

@@ -27,6 +27,7 @@ void fill_params(esdg_ctx* ctx, GenericParams& p) {
     p.Ph = ctx->Ph.view();
     p.Lf = ctx->Lf.view();
     p.Qp = PairEll{ctx->Nh, ctx->qp_width, ctx->qp_cnt, ctx->qp_col, ctx->qp_c};
+    p.dVq = ctx->dVq; p.dProj = ctx->dProj; p.dProjF = ctx->dProjF; p.dPh = ctx->dPh; p.dLf = ctx->dLf;
     p.wq = ctx->wq;
     p.geo = ctx->geo;
     p.geo_stride = ctx->geo_stride;
@@ -91,6 +92,7 @@ void fill_cns(esdg_ctx* ctx, CnsParams& P, const double* Qsrc) {
     P.g.Q = Qsrc;
     const CnsState& c = ctx->cns;
     P.Pq = c.Pq.view(); P.Vf = c.Vf.view(); P.Dr = c.Dr.view(); P.Ds = c.Ds.view();
+    P.dPq = c.dPq; P.dVf = c.dVf; P.dDr = c.dDr; P.dDs = c.dDs;
     P.bc = c.bc;
     P.vlid = c.vlid_dev;
     P.bctype = c.bctype;
@@ -351,14 +353,16 @@ static int finalize_cns(esdg_ctx* ctx) {
     CnsState& c = ctx->cns;
     const int Nh = ctx->Nh;
     if (d.n_halo != 0) return fail(ctx, ESDG_EINVAL, "esdg_finalize: the CNS path runs on one GPU per context (n_halo must be 0)");
-    struct { const char* n; int64_t r, cl; DevEll* out; } need[4] = {
-        {"Pq", d.Ns, d.Nq, &c.Pq}, {"Vf", d.Nfq, d.Ns, &c.Vf}, {"Dr", d.Ns, d.Ns, &c.Dr}, {"Ds", d.Ns, d.Ns, &c.Ds}};
+    struct { const char* n; int64_t r, cl; DevEll* out; Dense* dout; } need[4] = {
+        {"Pq", d.Ns, d.Nq, &c.Pq, &c.dPq}, {"Vf", d.Nfq, d.Ns, &c.Vf, &c.dVf}, {"Dr", d.Ns, d.Ns, &c.Dr, &c.dDr},
+        {"Ds", d.Ns, d.Ns, &c.Ds, &c.dDs}};
     int rc;
     for (auto& q : need) {
         const HostMat* m = find(ctx->ops, q.n);
         if (!m || m->rows != q.r || m->cols != q.cl)
             return fail(ctx, ESDG_EINVAL, std::string("esdg_finalize: CNS operator missing or mis-sized: ") + q.n);
         if ((rc = build_ell(ctx, *m, 0.0, q.out))) return rc;
+        if ((rc = build_dense(ctx, *m, 1.0, 0, (int)q.r, q.dout))) return rc;
     }
     const int64_t ntr = (int64_t)d.Nfq * d.K;
     std::vector<unsigned char> bc((size_t)ntr, 0);
@@ -405,6 +409,7 @@ static int finalize_cns(esdg_ctx* ctx) {
         return generic_smem_bytes(2, EB, d.Ns, d.Nq, d.Nfq, Nh, 0) + cns_extra_doubles(EB, d.Ns, d.Nq, d.Nfq) * sizeof(double);
     };
     int EB = std::min(16, std::max(1, ESDG_GENERIC_MAX_THREADS / Nh));
+    if (const char* ev = getenv("ESDG_CNS_EB")) EB = std::max(1, atoi(ev));   // launch-shape experiments
     while (EB > 1 && bytes(EB) + tbl > (size_t)maxsm / 2) --EB;
     if (bytes(EB) + tbl > (size_t)maxsm) return fail(ctx, ESDG_EINVAL, "esdg_finalize: element too large for shared memory (CNS)");
     ctx->EB = EB;
@@ -456,6 +461,9 @@ int esdg_finalize(esdg_ctx* ctx) {
         if (!Vq || !VhP) return ESDG_EINVAL;
         if ((rc = build_ell(ctx, *Vq, 0.0, &ctx->Vq))) return rc;
         if ((rc = build_ell(ctx, *VhP, 0.0, &ctx->Proj))) return rc;
+        if ((rc = build_dense(ctx, *Vq, 1.0, 0, d.Nq, &ctx->dVq))) return rc;
+        if ((rc = build_dense(ctx, *VhP, 1.0, 0, Nh, &ctx->dProj))) return rc;
+        if ((rc = build_dense(ctx, *VhP, 1.0, d.Nq, d.Nfq, &ctx->dProjF))) return rc;
     }
     const HostMat* Ph = need("Ph", d.Ns, Nh);
     const HostMat* Lf = need("Lf", d.Ns, d.Nfq);
@@ -463,6 +471,10 @@ int esdg_finalize(esdg_ctx* ctx) {
     if (!Ph || !Lf || !wq) return ESDG_EINVAL;
     if ((rc = build_ell(ctx, *Ph, d.collocated ? TOL : 0.0, &ctx->Ph))) return rc;
     if ((rc = build_ell(ctx, *Lf, d.collocated ? TOL : 0.0, &ctx->Lf))) return rc;
+    if (!d.collocated) {
+        if ((rc = build_dense(ctx, *Ph, d.volume_scale, 0, d.Ns, &ctx->dPh))) return rc;
+        if ((rc = build_dense(ctx, *Lf, 1.0, 0, d.Ns, &ctx->dLf))) return rc;
+    }
     if ((rc = dev_upload(ctx, &ctx->wq, wq->a))) return rc;
     const char* qn[3] = {"Qrh", "Qsh", "Qth"};
     const HostMat* Qm[3] = {nullptr, nullptr, nullptr};
@@ -570,6 +582,7 @@ int esdg_finalize(esdg_ctx* ctx) {
     if (!ctx->stage_tables) tbl = 0;
     int EB = std::max(1, ESDG_GENERIC_MAX_THREADS / Nh);
     EB = std::min<int64_t>(EB, 16);
+    if (const char* ev = getenv("ESDG_GENERIC_EB")) EB = std::max(1, atoi(ev));   // launch-shape experiments
     while (EB > 1 && generic_smem_bytes(DIM, EB, d.Ns, d.Nq, d.Nfq, Nh, d.collocated) + tbl > (size_t)maxsm / 2) --EB;
     ctx->EB = EB;
     ctx->table_off = (unsigned)generic_smem_bytes(DIM, EB, d.Ns, d.Nq, d.Nfq, Nh, d.collocated);

@@ -38,6 +38,7 @@ struct CnsState {
     std::vector<double> vlid;
     bool have_mapB = false;
     DevEll Pq, Vf, Dr, Ds;
+    esdg::Dense dPq{}, dVf{}, dDr{}, dDs{};
     unsigned char* bc = nullptr;
     double* vlid_dev = nullptr;
     double *sig = nullptr, *sig_tr = nullptr, *partial_visc = nullptr, *partial_vrhs = nullptr;
@@ -75,6 +76,7 @@ struct esdg_ctx {
 
     // device tables
     DevEll Vq, Proj, Ph, Lf;
+    esdg::Dense dVq{}, dProj{}, dProjF{}, dPh{}, dLf{};   // modal path (tensor-core batch GEMMs)
     int *qp_cnt = nullptr, *qp_col = nullptr;
     double* qp_c = nullptr;
     int qp_width = 0;

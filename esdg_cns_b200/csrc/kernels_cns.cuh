@@ -27,6 +27,7 @@ namespace esdg {
 struct CnsParams {
     GenericParams g;
     Ell Pq, Vf, Dr, Ds;          // Np x Nq, Nfq x Np, Np x Np, Np x Np
+    Dense dPq, dVf, dDr, dDs;    // the same, dense + padded for the tensor-core GEMMs
     const unsigned char* bc;     // [Nfq*K] bits 0-1: 0 interior, 1 wall, 2 lid ; bit 2: member of md.mapB
     const double* vlid;          // [Nfq*K] lid speed (read only where kind == 2) or nullptr
     int bctype;                  // 1 adiabatic no-slip, 2 isothermal, 3 slip   (:27)

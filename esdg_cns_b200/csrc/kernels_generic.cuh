@@ -108,38 +108,76 @@ __device__ __forceinline__ void project_batch(const GenericParams& p, GenericSme
         }
     }
     __syncthreads();
+    if (!p.collocated) {
+        // ---- modal path (dg2D_euler_tri.jl:138-140): the two projections are batch GEMMs on the tensor cores
+        // phase 1: Uq = Vq*Q, then v_ufun pointwise (in place in s.V)
+        mma_apply<false>(p.dVq, s.U, p.Ns, s.V, p.Nq, nb * NF);
+        __syncthreads();
+        for (int i = tid; i < nb * p.Nq; i += nt) {
+            const int eb = i / p.Nq, q = i - eb * p.Nq;
+            double U[NF], V[NF];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) U[f] = s.V[(eb * NF + f) * p.Nq + q];
+            v_of_u<DIM>(U, p.gamma, p.lg1, V, bad);
+#pragma unroll
+            for (int f = 0; f < NF; ++f) s.V[(eb * NF + f) * p.Nq + q] = V[f];
+        }
+        __syncthreads();
+        // phase 2: projected entropy variables at all hybridized points (s.QF as scratch), then u_vfun etc.
+        mma_apply<false>(p.dProj, s.V, p.Nq, s.QF, p.Nh, nb * NF);
+        __syncthreads();
+        for (int i = tid; i < nb * p.Nh; i += nt) {
+            const int eb = i / p.Nh, r = i - eb * p.Nh;
+            double U[NF], V[NF];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) V[f] = s.QF[(eb * NF + f) * p.Nh + r];
+            u_of_v<DIM>(V, p.gamma, p.lg1, U);
+            if (r < p.Nq) {
+                // projected entropy variables at volume points are the rhstest weights (tri :180)
+#pragma unroll
+                for (int f = 0; f < NF; ++f) s.VP[(eb * NF + f) * p.Nq + r] = V[f];
+            } else if (s.Vface) {
+#pragma unroll
+                for (int f = 0; f < NF; ++f) s.Vface[(eb * NF + f) * p.Nfq + (r - p.Nq)] = V[f];
+            }
+            Prim<DIM> P;
+            prim_of_u<DIM>(U, p.gamma, P);
+            double* w = s.W + (size_t)eb * (NF + 2) * p.Nh + r;
+            w[0] = P.rho;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) w[(1 + d) * p.Nh] = P.vel[d];
+            w[(1 + DIM) * p.Nh] = P.beta;
+            w[(2 + DIM) * p.Nh] = P.lrho;
+            w[(3 + DIM) * p.Nh] = P.lbeta;
+            if (r >= p.Nq) {
+#pragma unroll
+                for (int f = 0; f < NF; ++f) s.Uf[(eb * NF + f) * p.Nfq + (r - p.Nq)] = U[f];
+            }
+        }
+        __syncthreads();
+        return;
+    }
+    // ---- collocated path (dg2D_euler_quad.jl:149-155): state at the quadrature nodes, Ef is N+1 sparse
     // phase 1: entropy variables at the volume quadrature points
     for (int i = tid; i < nb * p.Nq; i += nt) {
         const int eb = i / p.Nq, q = i - eb * p.Nq;
         double U[NF], V[NF];
-        if (p.collocated) {
 #pragma unroll
-            for (int f = 0; f < NF; ++f) U[f] = s.U[(eb * NF + f) * p.Ns + q];
-        } else {
-#pragma unroll
-            for (int f = 0; f < NF; ++f) U[f] = 0.0;
-            const int n = p.Vq.cnt[q];
-            for (int k = 0; k < n; ++k) {
-                const int c = p.Vq.col[q * p.Vq.width + k];
-                const double a = p.Vq.val[q * p.Vq.width + k];
-#pragma unroll
-                for (int f = 0; f < NF; ++f) U[f] = fma(a, s.U[(eb * NF + f) * p.Ns + c], U[f]);
-            }
-        }
+        for (int f = 0; f < NF; ++f) U[f] = s.U[(eb * NF + f) * p.Ns + q];
         v_of_u<DIM>(U, p.gamma, p.lg1, V, bad);
 #pragma unroll
         for (int f = 0; f < NF; ++f) s.V[(eb * NF + f) * p.Nq + q] = V[f];
     }
     __syncthreads();
-    // phase 2: projected conservative variables -> primitive + logs
+    // phase 2: volume rows are the state itself, face rows u_vfun(Ef*VU) -> primitive + logs
     for (int i = tid; i < nb * p.Nh; i += nt) {
         const int eb = i / p.Nh, r = i - eb * p.Nh;
         double U[NF];
-        if (p.collocated && r < p.Nq) {
+        if (r < p.Nq) {
 #pragma unroll
             for (int f = 0; f < NF; ++f) U[f] = s.U[(eb * NF + f) * p.Ns + r];
         } else {
-            const int pr = p.collocated ? r - p.Nq : r;
+            const int pr = r - p.Nq;
             double V[NF];
 #pragma unroll
             for (int f = 0; f < NF; ++f) V[f] = 0.0;
@@ -151,15 +189,6 @@ __device__ __forceinline__ void project_batch(const GenericParams& p, GenericSme
                 for (int f = 0; f < NF; ++f) V[f] = fma(a, s.V[(eb * NF + f) * p.Nq + c], V[f]);
             }
             u_of_v<DIM>(V, p.gamma, p.lg1, U);
-            if (!p.collocated && r < p.Nq) {
-                // projected entropy variables at volume points are the rhstest weights (tri :180)
-#pragma unroll
-                for (int f = 0; f < NF; ++f) s.VP[(eb * NF + f) * p.Nq + r] = V[f];
-            }
-            if (s.Vface && r >= p.Nq) {
-#pragma unroll
-                for (int f = 0; f < NF; ++f) s.Vface[(eb * NF + f) * p.Nfq + (r - p.Nq)] = V[f];
-            }
         }
         Prim<DIM> P;
         prim_of_u<DIM>(U, p.gamma, P);
@@ -312,31 +341,43 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_rhs(const 
 
     // phase 5: test with Ph, lift, scale by -1/J; phase 6: output
     double tsum = 0.0;
+    if (!p.collocated) {
+        // modal: R = (vs Ph) QF + LIFT flux as two accumulating batch GEMMs (dg2D_euler_tri.jl:171-175)
+        mma_apply<false>(p.dPh, s.QF, p.Nh, s.R, p.Ns, nb * NF);
+        __syncthreads();
+        mma_apply<true>(p.dLf, s.Fl, p.Nfq, s.R, p.Ns, nb * NF);
+        __syncthreads();
+    }
     for (int i = tid; i < nb * p.Ns; i += nt) {
         const int eb = i / p.Ns, r = i - eb * p.Ns;
         const long long e = e0 + eb;
         const double J = p.geo[e * p.geo_stride + DIM * DIM];
-        double a[NF], b[NF];
-#pragma unroll
-        for (int f = 0; f < NF; ++f) a[f] = b[f] = 0.0;
-        int n = p.Ph.cnt[r];
-        for (int k = 0; k < n; ++k) {
-            const int c = p.Ph.col[r * p.Ph.width + k];
-            const double v = p.Ph.val[r * p.Ph.width + k];
-#pragma unroll
-            for (int f = 0; f < NF; ++f) a[f] = fma(v, s.QF[(eb * NF + f) * p.Nh + c], a[f]);
-        }
-        n = p.Lf.cnt[r];
-        for (int k = 0; k < n; ++k) {
-            const int c = p.Lf.col[r * p.Lf.width + k];
-            const double v = p.Lf.val[r * p.Lf.width + k];
-#pragma unroll
-            for (int f = 0; f < NF; ++f) b[f] = fma(v, s.Fl[(eb * NF + f) * p.Nfq + c], b[f]);
-        }
         const double mJ = -fast_rcp(J);
         double rr[NF];
+        if (!p.collocated) {
 #pragma unroll
-        for (int f = 0; f < NF; ++f) rr[f] = (b[f] + p.volume_scale * a[f]) * mJ;
+            for (int f = 0; f < NF; ++f) rr[f] = s.R[(eb * NF + f) * p.Ns + r] * mJ;
+        } else {
+            double a[NF], b[NF];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) a[f] = b[f] = 0.0;
+            int n = p.Ph.cnt[r];
+            for (int k = 0; k < n; ++k) {
+                const int c = p.Ph.col[r * p.Ph.width + k];
+                const double v = p.Ph.val[r * p.Ph.width + k];
+#pragma unroll
+                for (int f = 0; f < NF; ++f) a[f] = fma(v, s.QF[(eb * NF + f) * p.Nh + c], a[f]);
+            }
+            n = p.Lf.cnt[r];
+            for (int k = 0; k < n; ++k) {
+                const int c = p.Lf.col[r * p.Lf.width + k];
+                const double v = p.Lf.val[r * p.Lf.width + k];
+#pragma unroll
+                for (int f = 0; f < NF; ++f) b[f] = fma(v, s.Fl[(eb * NF + f) * p.Nfq + c], b[f]);
+            }
+#pragma unroll
+            for (int f = 0; f < NF; ++f) rr[f] = (b[f] + p.volume_scale * a[f]) * mJ;
+        }
         const long long g = e * p.Ns + r;
         if (p.want_rhstest) {
             if (p.collocated) {
@@ -363,21 +404,16 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_rhs(const 
     if (p.want_rhstest) {
         __syncthreads();
         if (!p.collocated) {
-            // tri: sum wJq .* VU[1:Nq] .* (Vq*rhs)   (dg2D_euler_tri.jl:177-183)
+            // tri: sum wJq .* VU[1:Nq] .* (Vq*rhs)   (dg2D_euler_tri.jl:177-183); Vq*rhs into s.V (free by now)
+            mma_apply<false>(p.dVq, s.R, p.Ns, s.V, p.Nq, nb * NF);
+            __syncthreads();
             for (int i = tid; i < nb * p.Nq; i += nt) {
                 const int eb = i / p.Nq, q = i - eb * p.Nq;
                 const long long e = e0 + eb;
                 const double J = p.geo[e * p.geo_stride + DIM * DIM];
                 const double wJ = p.wq[q] * J;
-                const int n = p.Vq.cnt[q];
 #pragma unroll
-                for (int f = 0; f < NF; ++f) {
-                    double v = 0.0;
-                    for (int k = 0; k < n; ++k)
-                        v = fma(p.Vq.val[q * p.Vq.width + k],
-                                s.R[(eb * NF + f) * p.Ns + p.Vq.col[q * p.Vq.width + k]], v);
-                    tsum += wJ * s.VP[(eb * NF + f) * p.Nq + q] * v;
-                }
+                for (int f = 0; f < NF; ++f) tsum += wJ * s.VP[(eb * NF + f) * p.Nq + q] * s.V[(eb * NF + f) * p.Nq + q];
             }
         }
         // deterministic block reduction -> one partial per CTA
