@@ -42,19 +42,22 @@ struct CnsParams {
 };
 
 struct CnsSmem {
-    // generic block first (project_batch fills it), CNS extras after it
-    double *Vfc;   // [EB][4][Nfq]  projected entropy variables at face points (own side)
-    double *A;     // [EB][4][Np]   scratch: VU (modal) / lifted results
-    double *Tx;    // [EB][3][Np]   theta_x (fields 2..4)  | kernel 3: sigma_x modal
-    double *Ty;    // [EB][3][Np]
-    double *Jx;    // [EB][4][Nfq]  face work array 1 (jump*nx | viscous surface term)
-    double *Jy;    // [EB][4][Nfq]  face work array 2 (jump*ny | penalisation)
-    double *Sq;    // [EB][6][Nq]   sigma at quadrature points
-    double *Rv;    // [EB][4][Np]   viscous rhs (for rhstest_visc)
+    // generic block first (project_batch fills it), CNS extras after it; every array is [EB][4 fields][n]
+    double *Vfc;   // [Nfq]  projected entropy variables at face points (own side)
+    double *A;     // [Np]   VU (modal)
+    double *B1;    // [Np]   Dr*VU            | rhs kernel: G0 sigma_x + G2 sigma_y
+    double *B2;    // [Np]   Ds*VU            | rhs kernel: G1 sigma_x + G3 sigma_y
+    double *Tx;    // [Np]   LIFT jump -> theta_x -> sigma_x (modal)
+    double *Ty;    // [Np]
+    double *Jx;    // [Nfq]  jump*nxJ | sigma_x at face points | rhs kernel: viscous surface term + J * penalisation
+    double *Jy;    // [Nfq]  jump*nyJ | sigma_y at face points
+    double *Q1;    // [Nq]   theta_x at quadrature points -> sigma_x   | rhs kernel: Vq * visc_rhs
+    double *Q2;    // [Nq]
+    double *Rv;    // [Np]   viscous rhs
 };
 
 inline size_t cns_extra_doubles(int EB, int Np, int Nq, int Nfq) {
-    return (size_t)EB * (4 * Nfq + 4 * Np + 6 * Np + 8 * Nfq + 6 * Nq + 4 * Np);
+    return (size_t)EB * 4 * (3 * Nfq + 6 * Np + 2 * Nq);
 }
 
 __device__ __forceinline__ CnsSmem cns_carve(double* base, const GenericParams& p) {
@@ -62,12 +65,15 @@ __device__ __forceinline__ CnsSmem cns_carve(double* base, const GenericParams& 
     const int EB = p.EB;
     c.Vfc = base;
     c.A = c.Vfc + EB * 4 * p.Nfq;
-    c.Tx = c.A + EB * 4 * p.Ns;
-    c.Ty = c.Tx + EB * 3 * p.Ns;
-    c.Jx = c.Ty + EB * 3 * p.Ns;
+    c.B1 = c.A + EB * 4 * p.Ns;
+    c.B2 = c.B1 + EB * 4 * p.Ns;
+    c.Tx = c.B2 + EB * 4 * p.Ns;
+    c.Ty = c.Tx + EB * 4 * p.Ns;
+    c.Jx = c.Ty + EB * 4 * p.Ns;
     c.Jy = c.Jx + EB * 4 * p.Nfq;
-    c.Sq = c.Jy + EB * 4 * p.Nfq;
-    c.Rv = c.Sq + EB * 6 * p.Nq;
+    c.Q1 = c.Jy + EB * 4 * p.Nfq;
+    c.Q2 = c.Q1 + EB * 4 * p.Nq;
+    c.Rv = c.Q2 + EB * 4 * p.Nq;
     return c;
 }
 
@@ -138,10 +144,13 @@ __device__ __forceinline__ void cns_entropy_vars(const GenericParams& p, Generic
         }
     }
     __syncthreads();
+    mma_apply<false>(p.dVq, s.U, p.Ns, s.V, p.Nq, nb * 4);
+    __syncthreads();
     for (int i = tid; i < nb * p.Nq; i += nt) {
         const int eb = i / p.Nq, q = i - eb * p.Nq;
         double U[4], V[4];
-        ell_row<4>(p.Vq, q, s.U + (size_t)eb * 4 * p.Ns, p.Ns, U);
+#pragma unroll
+        for (int f = 0; f < 4; ++f) U[f] = s.V[(eb * 4 + f) * p.Nq + q];
         v_of_u<2>(U, p.gamma, p.lg1, V, bad);
 #pragma unroll
         for (int f = 0; f < 4; ++f) s.V[(eb * 4 + f) * p.Nq + q] = V[f];
@@ -152,60 +161,54 @@ __device__ __forceinline__ void cns_entropy_vars(const GenericParams& p, Generic
 // Kernel 1: entropy-variable traces  VUf = (Vh Pq)[face rows] * v(Vq Q)
 __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_traces(const __grid_constant__ CnsParams Pin) {
     extern __shared__ double smem[];
-    GenericParams p = Pin.g;
-    stage_generic_tables(p, smem, ST_VQ | ST_PROJ);   // visible after the first barrier of cns_entropy_vars
+    const GenericParams& p = Pin.g;
     GenericSmem<2> s(smem, p);
     const long long e0 = (long long)blockIdx.x * p.EB;
     const int nb = (int)min((long long)p.EB, p.K - e0);
     bool bad = false;
     cns_entropy_vars(p, s, e0, nb, bad);
-    for (int i = threadIdx.x; i < nb * p.Nfq; i += blockDim.x) {
-        const int eb = i / p.Nfq, k = i - eb * p.Nfq;
-        double V[4];
-        ell_row<4>(p.Proj, p.Nq + k, s.V + (size_t)eb * 4 * p.Nq, p.Nq, V);
-#pragma unroll
-        for (int f = 0; f < 4; ++f) p.traces[f * p.trace_stride + e0 * p.Nfq + i] = V[f];
+    mma_apply<false>(p.dProjF, s.V, p.Nq, s.Uf, p.Nfq, nb * 4);
+    __syncthreads();
+    for (int f = 0; f < 4; ++f) {
+        double* dst = p.traces + f * p.trace_stride + e0 * p.Nfq;
+        for (int i = threadIdx.x; i < nb * p.Nfq; i += blockDim.x) {
+            const int eb = i / p.Nfq, k = i - eb * p.Nfq;
+            dst[i] = s.Uf[(eb * 4 + f) * p.Nfq + k];
+        }
     }
     if (bad) atomicOr(p.bad_flag, 1);
 }
 
 // Kernel 2: BR1 gradient of the projected entropy variables, sigma = K(v) theta, projection.
-__global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_sigma(const __grid_constant__ CnsParams Pin) {
+// Every operator application is a batch GEMM (kernels_mma.cuh); the pointwise steps between them are the
+// BCs / jumps at face points, the metric combination at nodes and K(v) theta at quadrature points.
+__global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_sigma(const __grid_constant__ CnsParams P) {
     extern __shared__ double smem[];
-    CnsParams P = Pin;
-    GenericParams& p = P.g;
-    {
-        char* sp = stage_generic_tables(p, smem, ST_VQ | ST_LF);
-        if (p.stage_tables) {
-            P.Pq = stage_ell(P.Pq, sp); P.Vf = stage_ell(P.Vf, sp);
-            P.Dr = stage_ell(P.Dr, sp); P.Ds = stage_ell(P.Ds, sp);
-        }   // visible after the first barrier of cns_entropy_vars
-    }
+    const GenericParams& p = P.g;
     GenericSmem<2> s(smem, p);
     CnsSmem c = cns_carve(s.R + p.EB * 4 * p.Ns, p);
     const int tid = threadIdx.x, nt = blockDim.x;
     const int Np = p.Ns, Nq = p.Nq, Nfq = p.Nfq;
     const long long e0 = (long long)blockIdx.x * p.EB;
     const int nb = (int)min((long long)p.EB, p.K - e0);
+    const int NC = nb * 4;
     bool bad = false;
     cns_entropy_vars(p, s, e0, nb, bad);
-    // VU = Pq * VUq  (:772)
-    for (int i = tid; i < nb * Np; i += nt) {
-        const int eb = i / Np, r = i - eb * Np;
-        double V[4];
-        ell_row<4>(P.Pq, r, s.V + (size_t)eb * 4 * Nq, Nq, V);
-#pragma unroll
-        for (int f = 0; f < 4; ++f) c.A[(eb * 4 + f) * Np + r] = V[f];
-    }
+    mma_apply<false>(P.dPq, s.V, Nq, c.A, Np, NC);                 // VU = Pq * VUq  (:772)
     __syncthreads();
-    // VUf = Vf*VU ; VUP = VUf[mapP] + BCs ; jump terms .5*(vP - vf)*nJ  (:775-777, :558-559)
+    mma_apply<false>(P.dVf, c.A, Np, c.Vfc, Nfq, NC);              // VUf = Vf * VU  (:775)
+    mma_apply<false>(P.dDr, c.A, Np, c.B1, Np, NC);                // Dr VU, Ds VU   (:553-554)
+    mma_apply<false>(P.dDs, c.A, Np, c.B2, Np, NC);
+    __syncthreads();
+    // VUP = VUf[mapP] + BCs ; jump terms .5*(vP - vf)*nJ  (:776-777, :558-559)
     for (int i = tid; i < nb * Nfq; i += nt) {
         const int eb = i / Nfq, k = i - eb * Nfq;
         const long long e = e0 + eb;
         const double* g = p.geo + e * p.geo_stride + 5 + (k / p.Nfp) * 3;
         const double nxJ = g[0], nyJ = g[1], sJ = g[2];
         double Vf[4], VP[4];
-        ell_row<4>(P.Vf, k, c.A + (size_t)eb * 4 * Np, Np, Vf);
+#pragma unroll
+        for (int f = 0; f < 4; ++f) Vf[f] = c.Vfc[(eb * 4 + f) * Nfq + k];
         const long long self = e * Nfq + k;
         const long long ip = p.mapP[self];
         if (ip == self) {
@@ -220,6 +223,8 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_sigma(const __
             const double isJ = fast_rcp(sJ);
             bc_entropy_vars(P, code & 3, (code & 3) == 2 ? P.vlid[self] : 0.0, nxJ * isJ, nyJ * isJ, Vf, VP);
         }
+        c.Jx[(eb * 4) * Nfq + k] = 0.0;
+        c.Jy[(eb * 4) * Nfq + k] = 0.0;
 #pragma unroll
         for (int f = 1; f < 4; ++f) {
             const double h = .5 * (VP[f] - Vf[f]);
@@ -228,34 +233,39 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_sigma(const __
         }
     }
     __syncthreads();
-    // dg_grad! (:548-569): theta = (G [Dr;Ds] v + LIFT jump)/J, fields 2..4
+    mma_apply<false>(p.dLf, c.Jx, Nfq, c.Tx, Np, NC);              // LIFT * jump
+    mma_apply<false>(p.dLf, c.Jy, Nfq, c.Ty, Np, NC);
+    __syncthreads();
+    // dg_grad! (:548-569): theta = (G [Dr;Ds] v + LIFT jump)/J
     for (int i = tid; i < nb * Np; i += nt) {
         const int eb = i / Np, r = i - eb * Np;
-        const long long e = e0 + eb;
-        const double* G = p.geo + e * p.geo_stride;   // rxJ, sxJ, ryJ, syJ, J
-        double vr[3], vs[3], lx[3], ly[3];
-        ell_row<3>(P.Dr, r, c.A + (size_t)(eb * 4 + 1) * Np, Np, vr);
-        ell_row<3>(P.Ds, r, c.A + (size_t)(eb * 4 + 1) * Np, Np, vs);
-        ell_row<3>(p.Lf, r, c.Jx + (size_t)(eb * 4 + 1) * Nfq, Nfq, lx);
-        ell_row<3>(p.Lf, r, c.Jy + (size_t)(eb * 4 + 1) * Nfq, Nfq, ly);
-        const double iJ = fast_rcp(G[4]);
+        const double* G = p.geo + (e0 + eb) * p.geo_stride;   // rxJ, sxJ, ryJ, syJ, J
+        const double G0 = G[0], G1 = G[1], G2 = G[2], G3 = G[3], iJ = fast_rcp(G[4]);
 #pragma unroll
-        for (int f = 0; f < 3; ++f) {
-            c.Tx[(eb * 3 + f) * Np + r] = (G[0] * vr[f] + G[1] * vs[f] + lx[f]) * iJ;
-            c.Ty[(eb * 3 + f) * Np + r] = (G[2] * vr[f] + G[3] * vs[f] + ly[f]) * iJ;
+        for (int f = 1; f < 4; ++f) {
+            const int o = (eb * 4 + f) * Np + r;
+            const double vr = c.B1[o], vs = c.B2[o];
+            c.Tx[o] = (G0 * vr + G1 * vs + c.Tx[o]) * iJ;
+            c.Ty[o] = (G2 * vr + G3 * vs + c.Ty[o]) * iJ;
         }
     }
+    __syncthreads();
+    mma_apply<false>(p.dVq, c.A, Np, s.V, Nq, NC);                 // VUq, VUx, VUy at the quadrature points (:780-782)
+    mma_apply<false>(p.dVq, c.Tx, Np, c.Q1, Nq, NC);
+    mma_apply<false>(p.dVq, c.Ty, Np, c.Q2, Nq, NC);
     __syncthreads();
     // quadrature points: sigma = K(v) theta (:786-800), rhstest_visc volume term (:802-806)
     double tsum = 0.0;
     for (int i = tid; i < nb * Nq; i += nt) {
         const int eb = i / Nq, q = i - eb * Nq;
         const long long e = e0 + eb;
-        double v[4], tx[3], ty[3];
-        ell_row<4>(p.Vq, q, c.A + (size_t)eb * 4 * Np, Np, v);
-        ell_row<3>(p.Vq, q, c.Tx + (size_t)eb * 3 * Np, Np, tx);
-        ell_row<3>(p.Vq, q, c.Ty + (size_t)eb * 3 * Np, Np, ty);
-        const double v2 = v[1], v3 = v[2], v4 = v[3];
+        double tx[3], ty[3];
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            tx[f] = c.Q1[(eb * 4 + 1 + f) * Nq + q];
+            ty[f] = c.Q2[(eb * 4 + 1 + f) * Nq + q];
+        }
+        const double v2 = s.V[(eb * 4 + 1) * Nq + q], v3 = s.V[(eb * 4 + 2) * Nq + q], v4 = s.V[(eb * 4 + 3) * Nq + q];
         const double lam = P.lam, mu = P.mu, l2m = lam + 2.0 * mu;
         const double ic = fast_rcp(v4 * v4 * v4);
         const double gmp = p.gamma * mu / P.Pr;
@@ -277,39 +287,37 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_sigma(const __
         sy[1] = xy01 * tx[0] + yy11 * ty[1] + (xy21 * tx[2] + yy12 * ty[2]);
         sy[2] = (xy02 * tx[0] + yy02 * ty[0]) + (xy12 * tx[1] + yy12 * ty[1]) + (xy22 * tx[2] + yy22 * ty[2]);
         const double wJ = p.wq[q] * p.geo[e * p.geo_stride + 4];
+        c.Q1[(eb * 4) * Nq + q] = 0.0;
+        c.Q2[(eb * 4) * Nq + q] = 0.0;
 #pragma unroll
         for (int f = 0; f < 3; ++f) {
             tsum += wJ * tx[f] * sx[f];
             tsum += wJ * ty[f] * sy[f];
-            c.Sq[(eb * 6 + f) * Nq + q] = sx[f];
-            c.Sq[(eb * 6 + 3 + f) * Nq + q] = sy[f];
+            c.Q1[(eb * 4 + 1 + f) * Nq + q] = sx[f];
+            c.Q2[(eb * 4 + 1 + f) * Nq + q] = sy[f];
         }
     }
     __syncthreads();
-    // sigma = Pq*sigma (:808-809) -> HBM (modal) ; reuse Tx/Ty as the modal store for the face evaluation
-    for (int i = tid; i < nb * Np; i += nt) {
+    mma_apply<false>(P.dPq, c.Q1, Nq, c.Tx, Np, NC);               // sigma = Pq * sigma (:808-809)
+    mma_apply<false>(P.dPq, c.Q2, Nq, c.Ty, Np, NC);
+    __syncthreads();
+    for (int i = tid; i < nb * Np; i += nt) {                      // modal sigma -> HBM (read again by k_cns_rhs)
         const int eb = i / Np, r = i - eb * Np;
-        double sg[6];
-        ell_row<6>(P.Pq, r, c.Sq + (size_t)eb * 6 * Nq, Nq, sg);
 #pragma unroll
         for (int f = 0; f < 3; ++f) {
-            c.Tx[(eb * 3 + f) * Np + r] = sg[f];
-            c.Ty[(eb * 3 + f) * Np + r] = sg[3 + f];
+            P.sig[f * P.sig_stride + e0 * Np + i] = c.Tx[(eb * 4 + 1 + f) * Np + r];
+            P.sig[(3 + f) * P.sig_stride + e0 * Np + i] = c.Ty[(eb * 4 + 1 + f) * Np + r];
         }
-#pragma unroll
-        for (int f = 0; f < 6; ++f) P.sig[f * P.sig_stride + e0 * Np + i] = sg[f];
     }
+    mma_apply<false>(P.dVf, c.Tx, Np, c.Jx, Nfq, NC);              // sigma_f = Vf * sigma (:811-812) -> sigma traces
+    mma_apply<false>(P.dVf, c.Ty, Np, c.Jy, Nfq, NC);
     __syncthreads();
-    // sigma_f = Vf*sigma (:811-812) -> sigma traces
     for (int i = tid; i < nb * Nfq; i += nt) {
         const int eb = i / Nfq, k = i - eb * Nfq;
-        double a[3], b[3];
-        ell_row<3>(P.Vf, k, c.Tx + (size_t)eb * 3 * Np, Np, a);
-        ell_row<3>(P.Vf, k, c.Ty + (size_t)eb * 3 * Np, Np, b);
 #pragma unroll
         for (int f = 0; f < 3; ++f) {
-            P.sig_tr[f * p.trace_stride + e0 * Nfq + i] = a[f];
-            P.sig_tr[(3 + f) * p.trace_stride + e0 * Nfq + i] = b[f];
+            P.sig_tr[f * p.trace_stride + e0 * Nfq + i] = c.Jx[(eb * 4 + 1 + f) * Nfq + k];
+            P.sig_tr[(3 + f) * p.trace_stride + e0 * Nfq + i] = c.Jy[(eb * 4 + 1 + f) * Nfq + k];
         }
     }
     // deterministic per-CTA partial of the viscous entropy term
@@ -326,15 +334,10 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_sigma(const __
 }
 
 // Kernel 3: inviscid rhs + BR1 divergence + penalisation -> rhs or LSRK stage.
-__global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_rhs(const __grid_constant__ CnsParams Pin) {
-    CnsParams P = Pin;
-    GenericParams& p = P.g;
+__global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_rhs(const __grid_constant__ CnsParams P) {
+    const GenericParams& p = P.g;
     constexpr int NF = 4;
     extern __shared__ double smem[];
-    {
-        char* sp = stage_generic_tables(p, smem, ST_VQ | ST_PROJ | ST_PH | ST_LF | ST_QP);
-        if (p.stage_tables) { P.Dr = stage_ell(P.Dr, sp); P.Ds = stage_ell(P.Ds, sp); }
-    }   // visible after the first barrier of project_batch
     GenericSmem<2> s(smem, p);
     CnsSmem c = cns_carve(s.R + p.EB * 4 * p.Ns, p);
     s.Vface = c.Vfc;
@@ -342,16 +345,22 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_rhs(const __gr
     const int Np = p.Ns, Nq = p.Nq, Nfq = p.Nfq;
     const long long e0 = (long long)blockIdx.x * p.EB;
     const int nb = (int)min((long long)p.EB, p.K - e0);
+    const int NC = nb * 4;
     bool bad = false;
     project_batch<2>(p, s, e0, nb, bad);
-    // sigma (modal) of this batch -> smem
-    for (int f = 0; f < 6; ++f) {
-        const double* src = P.sig + f * P.sig_stride + e0 * Np;
-        double* dst = f < 3 ? c.Tx : c.Ty;
-        const int ff = f < 3 ? f : f - 3;
-        for (int i = tid; i < nb * Np; i += nt) {
-            const int eb = i / Np, r = i - eb * Np;
-            dst[(eb * 3 + ff) * Np + r] = src[i];
+    // sigma (modal) of this batch, combined with the metric terms so that dg_div! (:590-611) becomes
+    //   Dr (rxJ sx + ryJ sy) + Ds (sxJ sx + syJ sy):  B1 = G0 sx + G2 sy, B2 = G1 sx + G3 sy
+    for (int i = tid; i < nb * Np; i += nt) {
+        const int eb = i / Np, r = i - eb * Np;
+        const double* G = p.geo + (e0 + eb) * p.geo_stride;
+        const double G0 = G[0], G1 = G[1], G2 = G[2], G3 = G[3];
+        c.B1[(eb * 4) * Np + r] = 0.0;
+        c.B2[(eb * 4) * Np + r] = 0.0;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            const double sx = P.sig[f * P.sig_stride + e0 * Np + i], sy = P.sig[(3 + f) * P.sig_stride + e0 * Np + i];
+            c.B1[(eb * 4 + 1 + f) * Np + r] = G0 * sx + G2 * sy;
+            c.B2[(eb * 4 + 1 + f) * Np + r] = G1 * sx + G3 * sy;
         }
     }
     // surface terms at the face points
@@ -417,11 +426,10 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_rhs(const __gr
             syP[f] = P.sig_tr[(3 + f) * p.trace_stride + ip];
         }
         if (kind) bc_stress(P, kind, vlid, nx, ny, sxf, syf, sxP, syP);
-        c.Jx[(eb * 4 + 0) * Nfq + k] = 0.0;
-        c.Jy[(eb * 4 + 0) * Nfq + k] = 0.0;
+        // viscous face term of this point: surf + J * pen, so that (vol + LIFT surf)/J + LIFT pen (:843-846) is one lift
+        double sv[3], pen[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-        for (int f = 0; f < 3; ++f)
-            c.Jx[(eb * 4 + 1 + f) * Nfq + k] = .5 * ((sxP[f] - sxf[f]) * nJ[0] + (syP[f] - syf[f]) * nJ[1]);
+        for (int f = 0; f < 3; ++f) sv[f] = .5 * ((sxP[f] - sxf[f]) * nJ[0] + (syP[f] - syf[f]) * nJ[1]);
         // penalisation tau*[[v]] (:817-840)
         if (P.viscous_dissp) {
             if (kind) bc_entropy_vars(P, kind, vlid, nx, ny, VM, VPv);
@@ -434,13 +442,14 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_rhs(const __gr
                 p3 = P.bctype == 1 ? -tau * (a1 * d1 + a2 * d2) * iv4
                                    : -tau * (a1 * d1 + a2 * d2 + d3 * d3 * .5) * iv4;
             }
-            c.Jy[(eb * 4 + 1) * Nfq + k] = tau * d1;
-            c.Jy[(eb * 4 + 2) * Nfq + k] = tau * d2;
-            c.Jy[(eb * 4 + 3) * Nfq + k] = p3;
-        } else {
-#pragma unroll
-            for (int f = 1; f < 4; ++f) c.Jy[(eb * 4 + f) * Nfq + k] = 0.0;
+            pen[0] = tau * d1;
+            pen[1] = tau * d2;
+            pen[2] = p3;
         }
+        const double Je = p.geo[e * p.geo_stride + 4];
+        c.Jx[(eb * 4) * Nfq + k] = 0.0;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) c.Jx[(eb * 4 + 1 + f) * Nfq + k] = fma(Je, pen[f], sv[f]);
     }
     // flux differencing: one hybridized row per item (row form of the symmetric loop :326-347)
     for (int i = tid; i < nb * p.Nh; i += nt) {
@@ -472,29 +481,24 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_rhs(const __gr
         for (int f = 0; f < NF; ++f) s.QF[(eb * NF + f) * p.Nh + r] = acc[f];
     }
     __syncthreads();
-    // assemble: inviscid -(LIFT flux + vs Ph QF)/J (:514-518) + viscous (G D sigma + LIFT surf)/J + LIFT pen (:590-611, :843-846)
+    // assemble with batch GEMMs: inviscid numerator R = (vs Ph) QF + LIFT flux (:514-517); viscous numerator
+    // Rv = Dr B1 + Ds B2 + LIFT (surf + J pen)  [= J * ((G D sigma + LIFT surf)/J + LIFT pen), :590-611, :843-846]
+    mma_apply<false>(p.dPh, s.QF, p.Nh, s.R, Np, NC);
+    mma_apply<true>(p.dLf, s.Fl, Nfq, s.R, Np, NC);
+    mma_apply<false>(P.dDr, c.B1, Np, c.Rv, Np, NC);
+    mma_apply<true>(P.dDs, c.B2, Np, c.Rv, Np, NC);
+    mma_apply<true>(p.dLf, c.Jx, Nfq, c.Rv, Np, NC);
+    __syncthreads();
     for (int i = tid; i < nb * Np; i += nt) {
         const int eb = i / Np, r = i - eb * Np;
         const long long e = e0 + eb;
-        const double* G = p.geo + e * p.geo_stride;
-        const double J = G[4];
-        double a[NF], b[NF], sv[NF], pn[NF], sxr[3], sxs[3], syr[3], sys[3];
-        ell_row<NF>(p.Ph, r, s.QF + (size_t)eb * NF * p.Nh, p.Nh, a);
-        ell_row<NF>(p.Lf, r, s.Fl + (size_t)eb * NF * Nfq, Nfq, b);
-        ell_row<NF>(p.Lf, r, c.Jx + (size_t)eb * 4 * Nfq, Nfq, sv);
-        ell_row<NF>(p.Lf, r, c.Jy + (size_t)eb * 4 * Nfq, Nfq, pn);
-        ell_row<3>(P.Dr, r, c.Tx + (size_t)eb * 3 * Np, Np, sxr);
-        ell_row<3>(P.Ds, r, c.Tx + (size_t)eb * 3 * Np, Np, sxs);
-        ell_row<3>(P.Dr, r, c.Ty + (size_t)eb * 3 * Np, Np, syr);
-        ell_row<3>(P.Ds, r, c.Ty + (size_t)eb * 3 * Np, Np, sys);
-        const double iJ = fast_rcp(J), mJ = -iJ;
+        const double iJ = fast_rcp(p.geo[e * p.geo_stride + 4]);
         double rr[NF], rv[NF];
-        rv[0] = 0.0;
 #pragma unroll
-        for (int f = 0; f < 3; ++f)
-            rv[1 + f] = (G[0] * sxr[f] + G[1] * sxs[f] + G[2] * syr[f] + G[3] * sys[f] + sv[1 + f]) * iJ + pn[1 + f];
-#pragma unroll
-        for (int f = 0; f < NF; ++f) rr[f] = (b[f] + p.volume_scale * a[f]) * mJ + rv[f];
+        for (int f = 0; f < NF; ++f) {
+            rv[f] = c.Rv[(eb * NF + f) * Np + r] * iJ;
+            rr[f] = rv[f] - s.R[(eb * NF + f) * Np + r] * iJ;
+        }
         const long long gidx = e * Np + r;
         if (p.want_rhstest) {
 #pragma unroll
@@ -518,19 +522,19 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_rhs(const __gr
     if (p.want_rhstest) {
         __syncthreads();
         // rhstest = sum wJq VUq (Vq*rhs), rhstest_visc = sum wJq VUq (Vq*visc_rhs) + visc_test (:960-971)
+        mma_apply<false>(p.dVq, s.R, Np, s.V, Nq, NC);
+        mma_apply<false>(p.dVq, c.Rv, Np, c.Q1, Nq, NC);
+        __syncthreads();
         double ta = 0.0, tv = 0.0;
         for (int i = tid; i < nb * Nq; i += nt) {
             const int eb = i / Nq, q = i - eb * Nq;
             const long long e = e0 + eb;
             const double wJ = p.wq[q] * p.geo[e * p.geo_stride + 4];
-            double ra[NF], rv[NF];
-            ell_row<NF>(p.Vq, q, s.R + (size_t)eb * NF * Np, Np, ra);
-            ell_row<NF>(p.Vq, q, c.Rv + (size_t)eb * NF * Np, Np, rv);
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
                 const double vq = s.VP[(eb * NF + f) * Nq + q];
-                ta += wJ * vq * ra[f];
-                tv += wJ * vq * rv[f];
+                ta += wJ * vq * s.V[(eb * NF + f) * Nq + q];
+                tv += wJ * vq * c.Q1[(eb * NF + f) * Nq + q];
             }
         }
         __shared__ double red[2][32];
