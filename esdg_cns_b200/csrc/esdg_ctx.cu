@@ -408,7 +408,9 @@ static int finalize_cns(esdg_ctx* ctx) {
     auto bytes = [&](int EB) {
         return generic_smem_bytes(2, EB, d.Ns, d.Nq, d.Nfq, Nh, 0) + cns_extra_doubles(EB, d.Ns, d.Nq, d.Nfq) * sizeof(double);
     };
-    int EB = std::min(16, std::max(1, ESDG_GENERIC_MAX_THREADS / Nh));
+    // 4 elements x 4 fields = 16 GEMM columns (two 8-wide DMMA tiles, no padding columns) in 128-thread CTAs:
+    // several CTAs per SM hide the barriers between the GEMM and pointwise phases (measured best of 2..10)
+    int EB = std::min(4, std::max(1, ESDG_GENERIC_MAX_THREADS / Nh));
     if (const char* ev = getenv("ESDG_CNS_EB")) EB = std::max(1, atoi(ev));   // launch-shape experiments
     while (EB > 1 && bytes(EB) + tbl > (size_t)maxsm / 2) --EB;
     if (bytes(EB) + tbl > (size_t)maxsm) return fail(ctx, ESDG_EINVAL, "esdg_finalize: element too large for shared memory (CNS)");
@@ -581,7 +583,7 @@ int esdg_finalize(esdg_ctx* ctx) {
     ctx->stage_tables = tbl <= 48 * 1024 && getenv("ESDG_STAGE_TABLES") != nullptr;
     if (!ctx->stage_tables) tbl = 0;
     int EB = std::max(1, ESDG_GENERIC_MAX_THREADS / Nh);
-    EB = std::min<int64_t>(EB, 16);
+    EB = std::min<int64_t>(EB, d.collocated ? 16 : 4);   // modal: see finalize_cns
     if (const char* ev = getenv("ESDG_GENERIC_EB")) EB = std::max(1, atoi(ev));   // launch-shape experiments
     while (EB > 1 && generic_smem_bytes(DIM, EB, d.Ns, d.Nq, d.Nfq, Nh, d.collocated) + tbl > (size_t)maxsm / 2) --EB;
     ctx->EB = EB;

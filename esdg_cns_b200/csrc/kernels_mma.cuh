@@ -36,12 +36,22 @@ __device__ __forceinline__ void mma_apply(const Dense& A, const double* X, int l
         const double* arow = A.a + m * A.Kp + lc;
         const double* xcol = X + cb * ldx + lc;
         const bool cok = cb < NC;
-        for (int k0 = 0; k0 < A.Kp; k0 += 4) {
-            const double a = arow[k0];
-            const double b = (cok && k0 + lc < A.K) ? xcol[k0] : 0.0;
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                         : "+d"(acc0), "+d"(acc1)
-                         : "d"(a), "d"(b));
+        // fragments of four k-steps are fetched together (A from global / L1, X from shared) before their DMMAs
+        for (int k0 = 0; k0 < A.Kp; k0 += 16) {
+            double a[4], b[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = k0 + 4 * j;
+                a[j] = k < A.Kp ? arow[k] : 0.0;
+                b[j] = (cok && k + lc < A.K) ? xcol[k] : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (k0 + 4 * j < A.Kp)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(acc0), "+d"(acc1)
+                                 : "d"(a[j]), "d"(b[j]));
+            }
         }
         if (m < A.M) {
             if (c0 < NC) Y[c0 * ldy + m] = acc0;
