@@ -67,6 +67,9 @@ _SIGNATURES = {
     "esdg_halo_ptr": (C.c_int, [C.c_void_p, _PP, C.POINTER(C.c_int64)]),
     "esdg_unpack_halo": (C.c_int, [C.c_void_p, C.c_void_p]),
     "esdg_stage_update": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int]),
+    "esdg_cns_sigma_pass": (C.c_int, [C.c_void_p, C.c_int]),
+    "esdg_pack_send_sigma": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "esdg_unpack_halo_sigma": (C.c_int, [C.c_void_p, C.c_void_p]),
     "esdg_trace_planes": (C.c_int, [C.c_void_p]),
     "esdg_read_rhstest": (C.c_int, [C.c_void_p, C.c_void_p]),
     "esdg_read_rhstest_visc": (C.c_int, [C.c_void_p, C.c_void_p]),

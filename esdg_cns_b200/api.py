@@ -215,6 +215,18 @@ class Solver:
     def trace_planes(self):
         return int(self._lib.esdg_trace_planes(self._ctx))
 
+    # CNS across GPUs: the sigma traces are the second exchange of a stage (include/esdg_b200.h)
+    SIGMA_PLANES = 6
+
+    def cns_sigma_pass(self, compute_rhstest=False):
+        self._ck(self._lib.esdg_cns_sigma_pass(self._ctx, int(bool(compute_rhstest))))
+
+    def pack_send_sigma(self, dev_ptr):
+        self._ck(self._lib.esdg_pack_send_sigma(self._ctx, C.c_void_p(int(dev_ptr))))
+
+    def unpack_halo_sigma(self, dev_ptr):
+        self._ck(self._lib.esdg_unpack_halo_sigma(self._ctx, C.c_void_p(int(dev_ptr))))
+
     def read_rhstest(self):
         rt = C.c_double(0.0)
         self._ck(self._lib.esdg_read_rhstest(self._ctx, C.byref(rt)))

@@ -118,17 +118,25 @@ int cns_traces(esdg_ctx* ctx, const double* Qsrc) {
     return ESDG_OK;
 }
 
-// sigma pass + rhs pass (the V traces of Qsrc must be valid)
-int cns_stage(esdg_ctx* ctx, const double* Qsrc, int mode, double a, double b, double dt, int want) {
+// sigma pass (the V traces of Qsrc, halo included, must be valid): sigma (modal) + sigma traces of the local elements
+int cns_sigma_pass(esdg_ctx* ctx, const double* Qsrc, int want) {
     CnsParams P;
     fill_cns(ctx, P, Qsrc);
-    P.g.mode = mode;
-    P.g.rk_a = a; P.g.rk_b = b; P.g.dt = dt;
     P.g.want_rhstest = want;
     tick(ctx, "cns_sigma");
     k_cns_sigma<<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(P);
     tock(ctx);
     CK(cudaGetLastError());
+    return ESDG_OK;
+}
+
+// rhs pass (V traces and sigma traces, halo included, must be valid)
+int cns_rhs_pass(esdg_ctx* ctx, const double* Qsrc, int mode, double a, double b, double dt, int want) {
+    CnsParams P;
+    fill_cns(ctx, P, Qsrc);
+    P.g.mode = mode;
+    P.g.rk_a = a; P.g.rk_b = b; P.g.dt = dt;
+    P.g.want_rhstest = want;
     tick(ctx, "cns_rhs");
     k_cns_rhs<<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(P);
     tock(ctx);
@@ -141,6 +149,13 @@ int cns_stage(esdg_ctx* ctx, const double* Qsrc, int mode, double a, double b, d
         CK(cudaGetLastError());
     }
     return ESDG_OK;
+}
+
+// sigma pass + rhs pass on one GPU
+int cns_stage(esdg_ctx* ctx, const double* Qsrc, int mode, double a, double b, double dt, int want) {
+    int rc = cns_sigma_pass(ctx, Qsrc, want);
+    if (rc) return rc;
+    return cns_rhs_pass(ctx, Qsrc, mode, a, b, dt, want);
 }
 
 // ---- path selection: tensor-product hex kernels when the operators allow, else generic ----
@@ -176,7 +191,14 @@ int do_stage(esdg_ctx* ctx, const double* Q, int mode, double a, double b, doubl
     int rc;
     if (ctx->cns.on) {
         if (part == ESDG_PART_INTERIOR) return ESDG_OK;
-        if ((rc = cns_stage(ctx, Q, mode, a, b, dt, want))) return rc;
+        if (ctx->d.n_halo != 0) {   // distributed: esdg_cns_sigma_pass + the sigma-trace exchange came first
+            if (!ctx->cns.sigma_valid) return fail(ctx, ESDG_EINVAL, "esdg_stage_update: call esdg_cns_sigma_pass (and exchange the sigma traces) first");
+            ctx->cns.sigma_valid = false;
+            rc = cns_rhs_pass(ctx, Q, mode, a, b, dt, want);
+        } else {
+            rc = cns_stage(ctx, Q, mode, a, b, dt, want);
+        }
+        if (rc) return rc;
         if (mode == 1) return cns_traces(ctx, ctx->Q);
         return ESDG_OK;
     }
@@ -352,7 +374,6 @@ static int finalize_cns(esdg_ctx* ctx) {
     const esdg_desc& d = ctx->d;
     CnsState& c = ctx->cns;
     const int Nh = ctx->Nh;
-    if (d.n_halo != 0) return fail(ctx, ESDG_EINVAL, "esdg_finalize: the CNS path runs on one GPU per context (n_halo must be 0)");
     struct { const char* n; int64_t r, cl; DevEll* out; Dense* dout; } need[4] = {
         {"Pq", d.Ns, d.Nq, &c.Pq, &c.dPq}, {"Vf", d.Nfq, d.Ns, &c.Vf, &c.dVf}, {"Dr", d.Ns, d.Ns, &c.Dr, &c.dDr},
         {"Ds", d.Ns, d.Ns, &c.Ds, &c.dDs}};
@@ -896,6 +917,41 @@ int esdg_unpack_halo(esdg_ctx* ctx, const void* recv_dev) {
     double* dst = cur_traces(ctx) + (long long)ctx->d.Nfq * ctx->d.K;
     CK(cudaMemcpy2DAsync(dst, ctx->trace_stride * sizeof(double), recv_dev, ctx->d.n_halo * sizeof(double),
                          ctx->d.n_halo * sizeof(double), cur_planes(ctx), cudaMemcpyDeviceToDevice, ctx->stream));
+    return ESDG_OK;
+}
+
+// ---- CNS across GPUs: the second exchange of a stage (sigma traces) ----
+int esdg_cns_sigma_pass(esdg_ctx* ctx, int compute_rhstest) {
+    int rc = require_ready(ctx, "esdg_cns_sigma_pass");
+    if (rc) return rc;
+    if (!ctx->cns.on) return fail(ctx, ESDG_EINVAL, "esdg_cns_sigma_pass: not a CNS context");
+    if (!ctx->traces_valid) return fail(ctx, ESDG_EINVAL, "esdg_cns_sigma_pass: call esdg_compute_traces (and exchange halos) after uploading a state");
+    if ((rc = cns_sigma_pass(ctx, ctx->Q, compute_rhstest))) return rc;
+    ctx->cns.sigma_valid = true;
+    return ESDG_OK;
+}
+
+int esdg_pack_send_sigma(esdg_ctx* ctx, void* send_dev) {
+    int rc = require_ready(ctx, "esdg_pack_send_sigma");
+    if (rc) return rc;
+    if (!ctx->cns.on) return fail(ctx, ESDG_EINVAL, "esdg_pack_send_sigma: not a CNS context");
+    if (ctx->n_send == 0) return ESDG_OK;
+    tick(ctx, "pack_send");
+    k_pack_send<<<(unsigned)((ctx->n_send + 255) / 256), 256, 0, ctx->stream>>>(ctx->cns.sig_tr, ctx->trace_stride, ctx->send_idx,
+                                                                               ctx->n_send, 6, (double*)send_dev);
+    tock(ctx);
+    CK(cudaGetLastError());
+    return ESDG_OK;
+}
+
+int esdg_unpack_halo_sigma(esdg_ctx* ctx, const void* recv_dev) {
+    int rc = require_ready(ctx, "esdg_unpack_halo_sigma");
+    if (rc) return rc;
+    if (!ctx->cns.on) return fail(ctx, ESDG_EINVAL, "esdg_unpack_halo_sigma: not a CNS context");
+    if (ctx->d.n_halo == 0) return ESDG_OK;
+    double* dst = ctx->cns.sig_tr + (long long)ctx->d.Nfq * ctx->d.K;
+    CK(cudaMemcpy2DAsync(dst, ctx->trace_stride * sizeof(double), recv_dev, ctx->d.n_halo * sizeof(double),
+                         ctx->d.n_halo * sizeof(double), 6, cudaMemcpyDeviceToDevice, ctx->stream));
     return ESDG_OK;
 }
 

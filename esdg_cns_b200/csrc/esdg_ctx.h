@@ -42,6 +42,7 @@ struct CnsState {
     unsigned char* bc = nullptr;
     double* vlid_dev = nullptr;
     double *sig = nullptr, *sig_tr = nullptr, *partial_visc = nullptr, *partial_vrhs = nullptr;
+    bool sigma_valid = false;             // distributed stage: sigma pass done, rhs pass pending
 };
 
 // DOPRI45 driver state (dg2D_CNS_cavity_optimized.jl:919-934, :974-1053)

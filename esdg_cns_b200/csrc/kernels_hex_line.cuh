@@ -246,8 +246,81 @@ __device__ __forceinline__ VD<W> wavespeed_v(const VD<W>& ir, const VD<W>& rhoun
     return vabs(vsqrt(vabs(rhoun * ir)) + vsqrt(pg * ir));
 }
 
+// W pairs of one line evaluated together (statement-interleaved): volume-volume pairs K0..K0+W-1 of PairTab<n>
+template <int n, bool DIAG, int K0, int W>
+__device__ __forceinline__ void line_vv_group(const Node (&nd)[n], double (&acc)[n][5], double g0, double g1, double g2, double c_igm,
+                                              const HexParams& p) {
+    constexpr PairTab<n> PT{};
+    const VD<W> g[3] = {vset<W>(g0), vset<W>(g1), vset<W>(g2)};
+    NodeV<W> A, B;
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        set_lane(A, q, nd[PT.a[K0 + q]]);
+        set_lane(B, q, nd[PT.b[K0 + q]]);
+    }
+    VD<W> F[5];
+    pair_flux_v<W, DIAG>(A, B, g, c_igm, F);
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        const int a = PT.a[K0 + q], b = PT.b[K0 + q];
+#pragma unroll
+        for (int f = 0; f < 5; ++f) {
+            acc[a][f] = fma(p.T[a * n + b], F[f].v[q], acc[a][f]);
+            acc[b][f] = fma(p.T[b * n + a], F[f].v[q], acc[b][f]);
+        }
+    }
+}
+template <int n, bool DIAG, int K0, int WC>
+__device__ __forceinline__ void line_vv_all(const Node (&nd)[n], double (&acc)[n][5], double g0, double g1, double g2, double c_igm,
+                                            const HexParams& p) {
+    constexpr int NP = PairTab<n>::NP;
+    if constexpr (K0 < NP) {
+        constexpr int W = NP - K0 < WC ? NP - K0 : WC;
+        line_vv_group<n, DIAG, K0, W>(nd, acc, g0, g1, g2, c_igm, p);
+        line_vv_all<n, DIAG, K0 + W, WC>(nd, acc, g0, g1, g2, c_igm, p);
+    }
+}
+// volume-face pairs J0..J0+W-1, item j = (node j/2, side j%2)
+template <int n, bool DIAG, int J0, int W>
+__device__ __forceinline__ void line_vf_group(const Node (&nd)[n], const Node (&fn)[2], double (&acc)[n][5], double (&h)[2][5], double g0,
+                                              double g1, double g2, double c_igm, const HexParams& p) {
+    const VD<W> g[3] = {vset<W>(g0), vset<W>(g1), vset<W>(g2)};
+    NodeV<W> A, B;
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        set_lane(A, q, nd[(J0 + q) / 2]);
+        set_lane(B, q, fn[(J0 + q) % 2]);
+    }
+    VD<W> F[5];
+    pair_flux_v<W, DIAG>(A, B, g, c_igm, F);
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        const int a = (J0 + q) / 2, side = (J0 + q) % 2;
+#pragma unroll
+        for (int f = 0; f < 5; ++f) {
+            acc[a][f] = fma(side ? p.lpw[a] : -p.lmw[a], F[f].v[q], acc[a][f]);
+            h[side][f] = fma(side ? p.lp[a] : p.lm[a], F[f].v[q], h[side][f]);
+        }
+    }
+}
+template <int n, bool DIAG, int J0, int WC>
+__device__ __forceinline__ void line_vf_all(const Node (&nd)[n], const Node (&fn)[2], double (&acc)[n][5], double (&h)[2][5], double g0,
+                                            double g1, double g2, double c_igm, const HexParams& p) {
+    if constexpr (J0 < 2 * n) {
+        constexpr int W = 2 * n - J0 < WC ? 2 * n - J0 : WC;
+        line_vf_group<n, DIAG, J0, W>(nd, fn, acc, h, g0, g1, g2, c_igm, p);
+        line_vf_all<n, DIAG, J0 + W, WC>(nd, fn, acc, h, g0, g1, g2, c_igm, p);
+    }
+}
+
+#ifdef ESDG_LINE_MAXNREG   // register-budget experiments (n = 5 only): explicit cap instead of the CTAs-per-SM hint
+#define ESDG_LINE_BOUNDS(n) __launch_bounds__(LineDims<n>::THREADS) __maxnreg__(n == 5 ? ESDG_LINE_MAXNREG : 128)
+#else
+#define ESDG_LINE_BOUNDS(n) __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB)
+#endif
+
 template <int n, bool DIAG>
-__global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex_stage_line(
+__global__ void ESDG_LINE_BOUNDS(n) k_hex_stage_line(
     const __grid_constant__ HexParams p) {
     using D = LineDims<n>;
     constexpr int Nq = D::Nq, nfp = D::nfp, Nfq = D::Nfq, NL = D::NL, EB = D::EB, NT = D::THREADS;
@@ -471,8 +544,6 @@ __global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex
 
     // ---- C: one line per thread, two pairs at a time -----------------------------------------------
     if (tid < nb * NL) {
-        constexpr PairTab<n> PT{};
-        constexpr int NP = PairTab<n>::NP;
         const int eb = tid / NL, l = tid - eb * NL;
         const int d = l / nfp, m = l - d * nfp;
         int base, stride;
@@ -482,8 +553,6 @@ __global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex
         const int pl0 = 1 + d, pl1 = 1 + c1, pl2 = 1 + c2;
         const double* G = sGeo + eb * 34;
         const double g0 = G[3 * d + d], g1 = G[3 * c1 + d], g2 = G[3 * c2 + d];   // (r_x, r_y, r_z) J of direction d, rotated
-        const VD<2> g_2[3] = {vset<2>(g0), vset<2>(g1), vset<2>(g2)};
-        const VD<1> g_1[3] = {vset<1>(g0), vset<1>(g1), vset<1>(g2)};
         Node nd[n];
 #pragma unroll
         for (int a = 0; a < n; ++a) {
@@ -505,54 +574,7 @@ __global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex
 #define ESDG_LINE_WC 2   // pairs evaluated together in the line phase (1 lowers the register need by ~40)
 #endif
         // volume-volume pairs: acc_a += T[a][b] F(a,b), acc_b += T[b][a] F(a,b)
-#if ESDG_LINE_WC == 1
-#pragma unroll
-        for (int k = 0; k < NP; ++k) {
-            const int a = PT.a[k], b = PT.b[k];
-            NodeV<1> A, B;
-            set_lane(A, 0, nd[a]);
-            set_lane(B, 0, nd[b]);
-            VD<1> F[5];
-            pair_flux_v<1, DIAG>(A, B, g_1, c_igm, F);
-#pragma unroll
-            for (int f = 0; f < 5; ++f) {
-                acc[a][f] = fma(p.T[a * n + b], F[f].v[0], acc[a][f]);
-                acc[b][f] = fma(p.T[b * n + a], F[f].v[0], acc[b][f]);
-            }
-        }
-#else
-#pragma unroll
-        for (int k = 0; k + 1 < NP; k += 2) {
-            NodeV<2> A, B;
-            set_lane(A, 0, nd[PT.a[k]]);     set_lane(B, 0, nd[PT.b[k]]);
-            set_lane(A, 1, nd[PT.a[k + 1]]); set_lane(B, 1, nd[PT.b[k + 1]]);
-            VD<2> F[5];
-            pair_flux_v<2, DIAG>(A, B, g_2, c_igm, F);
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int a = PT.a[k + q], b = PT.b[k + q];
-#pragma unroll
-                for (int f = 0; f < 5; ++f) {
-                    acc[a][f] = fma(p.T[a * n + b], F[f].v[q], acc[a][f]);
-                    acc[b][f] = fma(p.T[b * n + a], F[f].v[q], acc[b][f]);
-                }
-            }
-        }
-        if (NP % 2 == 1) {
-            constexpr int k = NP > 0 ? NP - 1 : 0;
-            const int a = PT.a[k], b = PT.b[k];
-            NodeV<1> A, B;
-            set_lane(A, 0, nd[a]);
-            set_lane(B, 0, nd[b]);
-            VD<1> F[5];
-            pair_flux_v<1, DIAG>(A, B, g_1, c_igm, F);
-#pragma unroll
-            for (int f = 0; f < 5; ++f) {
-                acc[a][f] = fma(p.T[a * n + b], F[f].v[0], acc[a][f]);
-                acc[b][f] = fma(p.T[b * n + a], F[f].v[0], acc[b][f]);
-            }
-        }
-#endif
+        line_vv_all<n, DIAG, 0, ESDG_LINE_WC>(nd, acc, g0, g1, g2, c_igm, p);
         // volume-face pairs: node a against the two face points its line ends in (lane = side)
         Node fn[2];
         int fidx[2];
@@ -567,46 +589,10 @@ __global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex
             fn[side].lr = sWF[5 * EF + fidx[side]];
             fn[side].lb = sWF[6 * EF + fidx[side]];
         }
-        NodeV<2> FB;
-        set_lane(FB, 0, fn[0]);
-        set_lane(FB, 1, fn[1]);
         double h[2][5];
 #pragma unroll
         for (int f = 0; f < 5; ++f) h[0][f] = h[1][f] = 0.0;
-#if ESDG_LINE_WC == 1
-#pragma unroll
-        for (int a = 0; a < n; ++a) {
-#pragma unroll
-            for (int side = 0; side < 2; ++side) {
-                NodeV<1> A, B;
-                set_lane(A, 0, nd[a]);
-                set_lane(B, 0, fn[side]);
-                VD<1> F[5];
-                pair_flux_v<1, DIAG>(A, B, g_1, c_igm, F);
-#pragma unroll
-                for (int f = 0; f < 5; ++f) {
-                    acc[a][f] = fma(side ? p.lpw[a] : -p.lmw[a], F[f].v[0], acc[a][f]);
-                    h[side][f] = fma(side ? p.lp[a] : p.lm[a], F[f].v[0], h[side][f]);
-                }
-            }
-        }
-#else
-#pragma unroll
-        for (int a = 0; a < n; ++a) {
-            NodeV<2> A;
-            set_lane(A, 0, nd[a]);
-            set_lane(A, 1, nd[a]);
-            VD<2> F[5];
-            pair_flux_v<2, DIAG>(A, FB, g_2, c_igm, F);
-#pragma unroll
-            for (int f = 0; f < 5; ++f) {
-                acc[a][f] = fma(-p.lmw[a], F[f].v[0], acc[a][f]);
-                acc[a][f] = fma(p.lpw[a], F[f].v[1], acc[a][f]);
-                h[0][f] = fma(p.lm[a], F[f].v[0], h[0][f]);
-                h[1][f] = fma(p.lp[a], F[f].v[1], h[1][f]);
-            }
-        }
-#endif
+        line_vf_all<n, DIAG, 0, ESDG_LINE_WC>(nd, fn, acc, h, g0, g1, g2, c_igm, p);
         // face rows: H = flux* -/+ sum_a l[a] F(a) (physical field order in shared memory); only the nodes
         // of THIS line lift from these two face points, so the lift (Lf as a 1-D sweep) is applied here
         {

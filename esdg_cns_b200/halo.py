@@ -93,3 +93,101 @@ class GpuSlabStepper:
             else:
                 s.stage_update(k, dt, want, s.PART_ALL)
                 self._exchange()
+
+
+class GpuSlabStepperCNS:
+    """LSRK45 of the compressible Navier-Stokes rhs (rhsRK!, dg2D_CNS_cavity_optimized.jl:955-972) on a slab
+    of elements.  rhsRK! has two inter-element dependences, so a stage has two exchanges:
+    the projected entropy-variable traces (4 planes; they serve the inviscid flux, the BR1 gradient and the
+    penalisation) and the stress traces of the BR1 divergence (6 planes)."""
+
+    def __init__(self, solver, md, dist, torch, device):
+        self.s = solver
+        self.halo_v = SlabHalo(md, solver.trace_planes(), dist, torch, device)
+        self.halo_s = SlabHalo(md, solver.SIGMA_PLANES, dist, torch, device)
+        solver.set_send_list(self.halo_v.send_list)
+        self.fresh = True
+
+    def mark_fresh(self):
+        self.fresh = True
+
+    def _exchange_v(self):
+        self.s.pack_send(self.halo_v.send.data_ptr())
+        self.halo_v.exchange()
+        self.s.unpack_halo(self.halo_v.recv.data_ptr())
+
+    def _exchange_sigma(self):
+        self.s.pack_send_sigma(self.halo_s.send.data_ptr())
+        self.halo_s.exchange()
+        self.s.unpack_halo_sigma(self.halo_s.recv.data_ptr())
+
+    def step(self, dt, want_rhstest=False):
+        s = self.s
+        if self.fresh:
+            s.compute_traces()
+            self._exchange_v()
+            self.fresh = False
+        for k in range(5):
+            want = want_rhstest and k == 4
+            s.cns_sigma_pass(want)
+            self._exchange_sigma()
+            s.stage_update(k, dt, want, s.PART_ALL)   # rhs pass + entropy-variable traces of the new state
+            self._exchange_v()
+
+
+def exchange_in_process(halos):
+    """The exchange of ``SlabHalo.exchange`` for slabs that live in ONE process (contexts on the same GPU or
+    on several GPUs driven by one host thread): ``halos[r]`` is rank r's SlabHalo with ``send`` filled;
+    device-to-device copies take the place of the NCCL send/recv pairs.  All contexts must share the stream
+    (or be synchronised by the caller)."""
+    for r, h in enumerate(halos):
+        half = h.n_halo // 2
+        if h.lower is not None:
+            lo = halos[h.lower]
+            h.recv[:, :half].copy_(lo.send[:, lo.n_lo:])       # the lower slab's send_upper block
+        if h.upper is not None:
+            up = halos[h.upper]
+            h.recv[:, half:].copy_(up.send[:, :up.n_lo])       # the upper slab's send_lower block
+    return [h.recv for h in halos]
+
+
+class LocalSlabsCNS:
+    """GpuSlabStepperCNS for several slabs held by one process (same call sequence per stage; the two
+    exchanges are device-to-device copies).  Used by the single-GPU test of the distributed CNS path."""
+
+    def __init__(self, solvers, mds, torch, device):
+        self.s = solvers
+        self.hv = [SlabHalo(md, s.trace_planes(), None, torch, device) for s, md in zip(solvers, mds)]
+        self.hs = [SlabHalo(md, s.SIGMA_PLANES, None, torch, device) for s, md in zip(solvers, mds)]
+        for s, h in zip(solvers, self.hv):
+            s.set_send_list(h.send_list)
+        self.fresh = True
+
+    def _exchange_v(self):
+        for s, h in zip(self.s, self.hv):
+            s.pack_send(h.send.data_ptr())
+        exchange_in_process(self.hv)
+        for s, h in zip(self.s, self.hv):
+            s.unpack_halo(h.recv.data_ptr())
+
+    def _exchange_sigma(self):
+        for s, h in zip(self.s, self.hs):
+            s.pack_send_sigma(h.send.data_ptr())
+        exchange_in_process(self.hs)
+        for s, h in zip(self.s, self.hs):
+            s.unpack_halo_sigma(h.recv.data_ptr())
+
+    def step(self, dt, want_rhstest=False):
+        if self.fresh:
+            for s in self.s:
+                s.compute_traces()
+            self._exchange_v()
+            self.fresh = False
+        for k in range(5):
+            want = want_rhstest and k == 4
+            for s in self.s:
+                s.cns_sigma_pass(want)
+            self._exchange_sigma()
+            for s in self.s:
+                s.stage_update(k, dt, want, s.PART_ALL)
+            self._exchange_v()

@@ -209,16 +209,30 @@ def cavity_bc_sets(md):
 
 
 # --------------------------------------------------------------------- meshes
-def uniform_quad_mesh_md(rd, Kx, Ky, domain=((-1.0, 1.0), (-1.0, 1.0)), periodic=(True, True)):
-    """MeshData of a uniform Kx x Ky quad mesh (elements x-fastest, UniformQuadMesh.jl:37-44)."""
+def uniform_quad_mesh_md(rd, Kx, Ky, domain=((-1.0, 1.0), (-1.0, 1.0)), periodic=(True, True), yslab=None):
+    """MeshData of a uniform Kx x Ky quad mesh (elements x-fastest, UniformQuadMesh.jl:37-44).
+
+    ``yslab=(rank, nranks)`` builds only the rank's contiguous range of element rows: trace
+    points owned by the slab below / above are mapped to halo slots appended after ``Nfq*K`` (lower
+    neighbour's s=+1 faces first, then the upper neighbour's s=-1 faces); ``md.send_lower`` /
+    ``md.send_upper`` list the local trace points each neighbour needs, in the order of its halo slots.
+    """
     n = rd.N + 1
     Nfq = 4 * n
-    K = Kx * Ky
     (x0, x1), (y0, y1) = domain
     hx, hy = (x1 - x0) / Kx, (y1 - y0) / Ky
+    if yslab is None:
+        j0, j1, nranks = 0, Ky, 1
+    else:
+        rank, nranks = yslab
+        if Ky % nranks:
+            raise ValueError("Ky must be divisible by the number of ranks")
+        j0, j1 = rank * (Ky // nranks), (rank + 1) * (Ky // nranks)
+    split = yslab is not None and nranks > 1
+    K = Kx * (j1 - j0)
     ex = np.arange(K) % Kx
-    ey = np.arange(K) // Kx
-    md = SimpleNamespace(K=K, dim=2)
+    ey = np.arange(K) // Kx + j0
+    md = SimpleNamespace(K=K, dim=2, Kxy=(Kx, Ky), yrange=(j0, j1))
     md.xq = (x0 + hx * ex)[None, :] + hx / 2 * (1 + rd.rq)[:, None]
     md.yq = (y0 + hy * ey)[None, :] + hy / 2 * (1 + rd.sq)[:, None]
     md.xf = (x0 + hx * ex)[None, :] + hx / 2 * (1 + rd.rf)[:, None]
@@ -248,11 +262,27 @@ def uniform_quad_mesh_md(rd, Kx, Ky, domain=((-1.0, 1.0), (-1.0, 1.0)), periodic
             ny_ = ny_ % Ky
         else:
             ok &= (ny_ >= 0) & (ny_ < Ky)
-        en = np.where(ok, nx_ + Kx * ny_, 0)
+        local = (ny_ >= j0) & (ny_ < j1)
+        en = np.where(ok & local, nx_ + Kx * (ny_ - j0), 0)
         tgt = (fn * n + (n - 1 - m))[:, None] + Nfq * en[None, :]
+        if split and dy != 0:
+            # the neighbour row lives on another rank: slot = its elements in x order, its face points in order
+            slot = nx_[None, :] * n + (n - 1 - m)[:, None]
+            tgt = np.where(local[None, :], tgt, Nfq * K + slot + (0 if dy < 0 else Kx * n))
         rows = f * n + m
         mapP[rows[:, None], np.arange(K)[None, :]] = np.where(ok[None, :], tgt, mapP[rows, :])
     md.mapP = mapP
+    md.n_halo = 0
+    if split:
+        md.n_halo = 2 * Kx * n
+        bottom = np.nonzero(ey == j0)[0]
+        top = np.nonzero(ey == j1 - 1)[0]
+        md.send_lower = ((0 * n + m)[None, :] + Nfq * bottom[:, None]).reshape(-1)   # my s=-1 faces (face 1)
+        md.send_upper = ((2 * n + m)[None, :] + Nfq * top[:, None]).reshape(-1)      # my s=+1 faces (face 3)
+        has_lower = periodic[1] or j0 > 0
+        has_upper = periodic[1] or j1 < Ky
+        md.lower_rank = (rank - 1) % nranks if has_lower else None
+        md.upper_rank = (rank + 1) % nranks if has_upper else None
     return md
 
 

@@ -175,6 +175,16 @@ int esdg_unpack_halo(esdg_ctx* ctx, const void* recv_dev);
  * After the call(s) the traces of the NEW state are valid locally: pack / exchange / unpack them
  * before the next stage. */
 int esdg_stage_update(esdg_ctx* ctx, int stage /*0..4*/, double dt, int compute_rhstest, int part);
+/* CNS contexts with halo points (rhsRK! has two inter-element dependences: the entropy-variable traces
+ * `VUP = VUf[mapP]` dg2D_CNS_cavity_optimized.jl:776 and the stress traces `sigma_f[mapP]` :591-600), so one
+ * distributed stage is
+ *   esdg_cns_sigma_pass ; esdg_pack_send_sigma ; <exchange> ; esdg_unpack_halo_sigma ;
+ *   esdg_stage_update(stage, part = 0) ; esdg_pack_send ; <exchange> ; esdg_unpack_halo
+ * The sigma buffers hold 6 planes (sigma_x, sigma_y of fields 2..4) per trace point, the entropy-variable
+ * buffers esdg_trace_planes() = 4.  compute_rhstest must agree between the two calls of a stage. */
+int esdg_cns_sigma_pass(esdg_ctx* ctx, int compute_rhstest);
+int esdg_pack_send_sigma(esdg_ctx* ctx, void* send_dev /* 6*n doubles, device */);
+int esdg_unpack_halo_sigma(esdg_ctx* ctx, const void* recv_dev /* 6*n_halo doubles, device */);
 /* number of double planes per trace point in the pack/unpack buffers (5 = Uf of the generic path,
  * 7 = rho,u,v,w,beta,log rho,log beta of the tensor-product hex path) */
 int esdg_trace_planes(esdg_ctx* ctx);

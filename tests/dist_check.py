@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--overlap", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--generic", type=int, default=0)
+    ap.add_argument("--cns", type=int, default=0, help="1: compressible Navier-Stokes cavity on y-slabs of a quad mesh")
     a = ap.parse_args()
     if a.generic:
         os.environ["ESDG_FORCE_GENERIC"] = "1"
@@ -37,6 +38,13 @@ def main():
     torch.cuda.set_device(lr)
     dev = torch.device("cuda", lr)
     dist.init_process_group("nccl", device_id=dev)
+    if a.cns:
+        ok = cns_check(a, rank, world, lr, dev, torch, dist, api, H, SD)
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.broadcast(flag, 0)
+        dist.barrier()
+        dist.destroy_process_group()
+        sys.exit(0 if int(flag[0]) == 1 else 1)
     N, Kxyz = a.N, tuple(a.K)
     dom = ((-np.pi, np.pi),) * 3
     prd, pops = SD.reference_hex(N)
@@ -75,6 +83,53 @@ def main():
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if int(flag[0]) == 1 else 1)
+
+
+def cns_check(a, rank, world, lr, dev, torch, dist, api, H, SD):
+    """CNS lid-driven cavity (config 3 shape) on y-slabs: two halo exchanges per stage (entropy-variable
+    traces, sigma traces) over NCCL; must equal the single-GPU run bit for bit."""
+    from types import SimpleNamespace
+    N, Kx, Ky = a.N, a.K[0], a.K[1] * world
+    prd, pops = SD.reference_quad_modal(N)
+
+    def settings(md):
+        bc = SD.cavity_bc_sets(md)
+        return SimpleNamespace(Re=100.0, mu=1e-2, lam=-2e-2 / 3, Pr=.71, bctype=1, inviscid_dissp=True,
+                               viscous_dissp=True, wall=bc.wall, lid=bc.lid, vlid=bc.vlid, mapB=bc.mapB)
+
+    def state(md):
+        x, y = md.x, md.y
+        rho = 1 + .1 * np.sin(np.pi * x) * np.cos(np.pi * y)
+        u, v = .2 * np.cos(np.pi * x), -.1 * np.sin(np.pi * y) * np.cos(np.pi * x)
+        p = 1 / (.3 ** 2 * 1.4) * (1 + .05 * np.cos(np.pi * (x + y)))
+        return SD.primitive_to_conservative(rho, (u, v), p)
+    md = SD.uniform_quad_mesh_md(prd, Kx, Ky, periodic=(False, False), yslab=(rank, world))
+    dt = 2e-4
+    s = api.Solver(md, pops, device=lr, n_halo=md.n_halo, cns=settings(md), stream=torch.cuda.current_stream().cuda_stream)
+    st = H.GpuSlabStepperCNS(s, md, dist, torch, dev)
+    s.upload(state(md))
+    for k in range(a.steps):
+        st.step(dt, want_rhstest=(k == a.steps - 1))
+    rt_local = torch.tensor([s.read_rhstest(), s.read_rhstest_visc()], dtype=torch.float64, device=dev)
+    dist.all_reduce(rt_local)
+    t = torch.from_numpy(np.ascontiguousarray(np.stack(s.download()))).to(dev)
+    parts = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+    dist.gather(t, parts, dst=0)
+    ok = True
+    if rank == 0:
+        full = np.concatenate([p.cpu().numpy() for p in parts], axis=2)
+        mdf = SD.uniform_quad_mesh_md(prd, Kx, Ky, periodic=(False, False))
+        s1 = api.Solver(mdf, pops, device=lr, cns=settings(mdf))
+        s1.upload(state(mdf))
+        rt1 = s1.lsrk45(dt, a.steps, want_rhstest=True)
+        rtv1 = s1.read_rhstest_visc()
+        ref = np.stack(s1.download())
+        diff = np.abs(full - ref).max()
+        print(f"dist_check CNS world={world} N={N} K={Kx}x{Ky}: state max diff {diff:.3e}; rhstest {float(rt_local[0]):.12e} vs "
+              f"{rt1:.12e}; rhstest_visc {float(rt_local[1]):.12e} vs {rtv1:.12e}")
+        ok = diff == 0.0 and abs(float(rt_local[0]) - rt1) < 1e-10 * max(1.0, abs(rt1)) and \
+            abs(float(rt_local[1]) - rtv1) < 1e-10 * max(1.0, abs(rtv1))
+    return ok
 
 
 if __name__ == "__main__":

@@ -207,3 +207,56 @@ def test_dopri45_on_euler_hex_context():
     Ql = s.download()
     assert T >= 0.02 and all(h["accepted"][-1:])
     assert relerr(Qd, Ql) < 1e-6
+
+
+@pytest.mark.parametrize("nslabs,periodic", [(2, False), (3, False), (2, True)])
+def test_cns_slabs_with_halo_exchange_match_single_context(nslabs, periodic):
+    """Distributed CNS stage (two exchanges per stage, entropy-variable traces + sigma traces):
+    the cavity mesh split into y-slabs, one context per slab with halo slots, must reproduce the
+    single-context state bit for bit (same kernels, same per-element arithmetic; only the trace transport
+    differs) and the same entropy residuals up to summation order."""
+    import torch
+    from esdg_cns_b200 import api, halo as H, setup_dg as SD
+    N, Kx, Ky = 3, 5, 6
+    per = (periodic, periodic)
+    prd, pops = SD.reference_quad_modal(N)
+    mdg = SD.uniform_quad_mesh_md(prd, Kx, Ky, periodic=per)
+    rng = np.random.default_rng(3)
+    x, y = mdg.x, mdg.y
+    rho = 1 + .1 * np.sin(np.pi * x) * np.cos(np.pi * y) + .01 * rng.random(x.shape)
+    u, v = .2 * np.cos(np.pi * x), -.1 * np.sin(np.pi * y) * np.cos(np.pi * x)
+    p = 1 / (.3 ** 2 * 1.4) * (1 + .05 * np.cos(np.pi * (x + y)))
+    Q = SD.primitive_to_conservative(rho, (u, v), p)
+
+    def settings(md):
+        bc = SD.cavity_bc_sets(md) if not periodic else SimpleNamespace(
+            wall=np.zeros(0, np.int64), lid=np.zeros(0, np.int64), vlid=np.zeros(0), mapB=np.zeros(0, np.int64))
+        return SimpleNamespace(Re=100.0, mu=1e-2, lam=-2e-2 / 3, Pr=.71, bctype=1, inviscid_dissp=True,
+                               viscous_dissp=True, wall=bc.wall, lid=bc.lid, vlid=bc.vlid, mapB=bc.mapB)
+    dt, nsteps = 2e-4, 2
+    stream = torch.cuda.current_stream().cuda_stream
+    ref = api.Solver(mdg, pops, cns=settings(mdg), stream=stream)
+    ref.upload(Q)
+    rt_ref = ref.lsrk45(dt, nsteps, want_rhstest=True)
+    rtv_ref = ref.read_rhstest_visc()
+    Qref = ref.download()
+    mds = [SD.uniform_quad_mesh_md(prd, Kx, Ky, periodic=per, yslab=(r, nslabs)) for r in range(nslabs)]
+    sol = [api.Solver(md, pops, n_halo=md.n_halo, cns=settings(md), stream=stream) for md in mds]
+    e0 = 0
+    for s, md in zip(sol, mds):
+        s.upload([np.asfortranarray(q[:, e0:e0 + md.K]) for q in Q])
+        e0 += md.K
+    st = H.LocalSlabsCNS(sol, mds, torch, torch.device("cuda", 0))
+    for k in range(nsteps):
+        st.step(dt, want_rhstest=(k == nsteps - 1))
+    Qs = [s.download() for s in sol]
+    full = [np.concatenate([q[f] for q in Qs], axis=1) for f in range(4)]
+    rt = sum(s.read_rhstest() for s in sol)
+    rtv = sum(s.read_rhstest_visc() for s in sol)
+    diff = max(np.abs(a - b).max() for a, b in zip(full, Qref))
+    print(f"cns {nslabs} slabs periodic={periodic}: max |dQ| {diff:.2e}, rhstest {rt:.6e} vs {rt_ref:.6e}, visc {rtv:.6e} vs {rtv_ref:.6e}")
+    assert diff == 0.0
+    assert abs(rt - rt_ref) < 1e-12 * max(1.0, abs(rt_ref)) and abs(rtv - rtv_ref) < 1e-12 * max(1.0, abs(rtv_ref))
+    # a stage without the sigma pass is refused
+    with pytest.raises(Exception):
+        sol[0].stage_update(0, dt, False, 0)

@@ -28,3 +28,16 @@ def test_two_gpu_slabs_match_single_gpu(overlap, generic, N):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0
+
+
+@pytest.mark.gpu
+def test_two_gpu_cns_slabs_match_single_gpu():
+    """Distributed CNS (two NCCL halo exchanges per stage) on 2 GPUs against the single-GPU run."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29571",
+           os.path.join(ROOT, "tests", "dist_check.py"), "--cns", "1", "--N", "3", "--K", "6", "4", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0
