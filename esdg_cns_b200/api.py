@@ -42,7 +42,7 @@ def euler_fluxes(*_a, **_k):
 class Solver:
     """One GPU context: operators, geometry and maps resident in HBM."""
 
-    def __init__(self, md, ops, device=0, n_halo=0, stream=None, map_index_base=0, cns=None):
+    def __init__(self, md, ops, device=0, n_halo=0, stream=None, map_index_base=0, cns=None, affine=None):
         """``cns``: None (Euler) or a namespace with the CNS script globals ``Re, mu, lam, Pr, bctype,
         inviscid_dissp, viscous_dissp`` (dg2D_CNS_cavity_optimized.jl:21-36) and the boundary node
         sets ``wall, lid, vlid, mapB`` (0-based unless map_index_base=1; :139-147)."""
@@ -58,8 +58,22 @@ class Solver:
         Nfq = int(np.asarray(ops.Lf).shape[1])
         Ns = int(np.asarray(ops.Ph).shape[0])
         self.Ns, self.K = Ns, int(md.K)
+        # curved elements (hex script only, dg3D_euler_hex.jl:90-101, :145-151): volume geometric factors that vary
+        # inside an element; the 2-D scripts read `[1,e]` whatever the mesh
+        if affine is not None:
+            affine = int(affine)                 # caller's claim; esdg_finalize verifies a claimed affine mesh
+        else:
+            affine = 1
+            if dim == 3 and collocated:
+                scale = float(np.abs(np.asarray(md.J)).max()) ** (2.0 / 3.0)
+                for n in ("rxJ", "sxJ", "txJ", "ryJ", "syJ", "tyJ", "rzJ", "szJ", "tzJ"):
+                    a = np.atleast_2d(getattr(md, n))
+                    if a.shape[0] > 1 and float(np.abs(a - a[:1]).max()) > 1e-10 * scale:
+                        affine = 0
+                        break
+        self.affine = affine
         d = L.esdg_desc(dim=dim, elem=ELEM_CODE[ops.elem], N=int(ops.N), Nfields=nf, Ns=Ns, Nq=Nq, Nfq=Nfq,
-                        Nfaces=int(ops.Nfaces), collocated=collocated, affine=1, K=int(md.K), n_halo=int(n_halo),
+                        Nfaces=int(ops.Nfaces), collocated=collocated, affine=affine, K=int(md.K), n_halo=int(n_halo),
                         gamma=1.4, volume_scale=float(ops.volume_scale),
                         lf_scale=float(ops.lf_scale) if (cns is None or cns.inviscid_dissp) else 0.0)
         self.desc = d

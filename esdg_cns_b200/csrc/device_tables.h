@@ -52,6 +52,10 @@ struct GenericParams {
     //   then per face: nxJ,nyJ[,nzJ],sJ
     const double* geo;
     int geo_stride;
+    // curved hexes (desc.affine = 0; dg3D_euler_hex.jl:90-101, :145-151): geometric factors at every hybridized
+    // point, J at every node, scaled normals at every face point.  Per element: [e][9][Nh], [e][Nq], [e][4][Nfq].
+    int curved;
+    const double *geoG, *geoJ, *geoN;
     const int* mapP;        // [K][Nfq] 0-based index into the per-field trace array
     // state / work arrays (field-major: base + f*stride)
     const double* Q;        // Ns*K per field

@@ -31,6 +31,8 @@ void fill_params(esdg_ctx* ctx, GenericParams& p) {
     p.wq = ctx->wq;
     p.geo = ctx->geo;
     p.geo_stride = ctx->geo_stride;
+    p.curved = ctx->d.affine == 0;
+    p.geoG = ctx->geoG; p.geoJ = ctx->geoJ; p.geoN = ctx->geoN;
     p.mapP = ctx->mapP;
     p.Q = ctx->Q;
     p.q_stride = (long long)d.Ns * d.K;
@@ -247,7 +249,9 @@ int esdg_create(const esdg_desc* desc, int device, esdg_ctx** out) {
     if (!(d.dim == 2 || d.dim == 3) || d.Nfields != d.dim + 2 || d.K <= 0 || d.Ns <= 0 || d.Nq <= 0 ||
         d.Nfq <= 0 || d.Nfaces <= 0 || d.Nfq % d.Nfaces != 0 || d.n_halo < 0)
         return fail(ctx, ESDG_EINVAL, "esdg_create: inconsistent descriptor");
-    if (d.affine != 1) return fail(ctx, ESDG_EINVAL, "esdg_create: only affine meshes are supported (desc.affine must be 1)");
+    if (d.affine != 1 && !(d.affine == 0 && d.dim == 3 && d.collocated))
+        return fail(ctx, ESDG_EINVAL, "esdg_create: desc.affine = 0 (curved elements) is supported for collocated hexes only; "
+                                      "the 2-D scripts read the geometric factors of the first node (`[1,e]`)");
     if (d.collocated && d.Ns != d.Nq) return fail(ctx, ESDG_EINVAL, "esdg_create: collocated needs Ns == Nq");
     if ((double)d.Nfq * (double)d.K + (double)d.n_halo > 2.0e9)
         return fail(ctx, ESDG_EINVAL, "esdg_create: Nfq*K+n_halo exceeds 32-bit trace indexing");
@@ -439,6 +443,7 @@ static int finalize_cns(esdg_ctx* ctx) {
     ctx->table_off = (unsigned)bytes(EB);
     ctx->smem_bytes = bytes(EB) + tbl;
     ctx->threads = std::min(ESDG_GENERIC_MAX_THREADS, ((EB * Nh + 31) / 32) * 32);
+    if (const char* tv = getenv("ESDG_CNS_THREADS")) ctx->threads = std::max(32, (atoi(tv) / 32) * 32);   // launch-shape experiments
     CK(cudaFuncSetAttribute(k_cns_traces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
     CK(cudaFuncSetAttribute(k_cns_sigma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
     CK(cudaFuncSetAttribute(k_cns_rhs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
@@ -566,20 +571,48 @@ int esdg_finalize(esdg_ctx* ctx) {
                     const int64_t row0 = (Nn[k]->rows == d.Nfaces) ? f : (int64_t)f * ctx->Nfp;
                     const double v0 = Nn[k]->at(row0, e);
                     g[DIM * DIM + 1 + f * (DIM + 1) + k] = v0;
-                    if (Nn[k]->rows == d.Nfq) {  // affine check: constant along the face
+                    if (Nn[k]->rows == d.Nfq && d.affine) {  // affine check: constant along the face
                         for (int q = 1; q < ctx->Nfp; ++q)
                             if (std::fabs(Nn[k]->at(row0 + q, e) - v0) > 1e-10 * (std::fabs(v0) + g[DIM * DIM]))
                                 return fail(ctx, ESDG_EINVAL, "esdg_finalize: face normals vary along a face (mesh not affine)");
                     }
                 }
             // affine check on the volume geofacs / J when full arrays were given
-            for (int k = 0; k < DIM * DIM; ++k)
+            for (int k = 0; k < DIM * DIM && d.affine; ++k)
                 for (int64_t r = 1; r < G[k]->rows; ++r)
                     if (std::fabs(G[k]->at(r, e) - g[k]) > 1e-10 * (std::fabs(g[k]) + 1e-300 + std::fabs(g[DIM * DIM])))
                         return fail(ctx, ESDG_EINVAL, "esdg_finalize: volume geometric factors vary inside an element (mesh not affine)");
         }
     }
     if ((rc = dev_upload(ctx, &ctx->geo, geo))) return rc;
+    if (!d.affine) {
+        // curved hexes: the full arrays of the script, rxJ.. = [Vq;Vf]*rxJ.. (Nh x K), J = Vq*J (Nq x K),
+        // nxJ.. at the face points (Nfq x K)   (dg3D_euler_hex.jl:69-101)
+        std::vector<double> gG((size_t)d.K * 9 * Nh), gJ((size_t)d.K * d.Nq), gN((size_t)d.K * 4 * d.Nfq);
+        const HostMat* J = find(ctx->geom, "J");
+        if (J->rows != d.Nq) return fail(ctx, ESDG_EINVAL, "esdg_finalize: curved mesh needs J at every node (Nq x K)");
+        for (int k = 0; k < 9; ++k) {
+            const HostMat* G = find(ctx->geom, g3[k]);
+            if (G->rows != Nh) return fail(ctx, ESDG_EINVAL, std::string("esdg_finalize: curved mesh needs ") + g3[k] + " at every hybridized point (Nh x K)");
+            for (int64_t e = 0; e < d.K; ++e)
+                for (int r = 0; r < Nh; ++r) gG[((size_t)e * 9 + k) * Nh + r] = G->at(r, e);
+        }
+        for (int64_t e = 0; e < d.K; ++e)
+            for (int r = 0; r < d.Nq; ++r) {
+                const double v = J->at(r, e);
+                if (!(v > 0.0)) return fail(ctx, ESDG_EINVAL, "esdg_finalize: non-positive Jacobian J");
+                gJ[(size_t)e * d.Nq + r] = v;
+            }
+        for (int k = 0; k < 4; ++k) {
+            const HostMat* Nk = find(ctx->geom, nn[k]);
+            if (Nk->rows != d.Nfq) return fail(ctx, ESDG_EINVAL, std::string("esdg_finalize: curved mesh needs ") + nn[k] + " at every face point (Nfq x K)");
+            for (int64_t e = 0; e < d.K; ++e)
+                for (int r = 0; r < d.Nfq; ++r) gN[((size_t)e * 4 + k) * d.Nfq + r] = Nk->at(r, e);
+        }
+        if ((rc = dev_upload(ctx, &ctx->geoG, gG))) return rc;
+        if ((rc = dev_upload(ctx, &ctx->geoJ, gJ))) return rc;
+        if ((rc = dev_upload(ctx, &ctx->geoN, gN))) return rc;
+    }
     // ---- maps ------------------------------------------------------------------
     if ((int64_t)ctx->mapP_host.size() != (int64_t)d.Nfq * d.K)
         return fail(ctx, ESDG_EINVAL, "esdg_finalize: mapP missing (esdg_set_maps)");

@@ -83,6 +83,7 @@ struct esdg_ctx {
     int qp_width = 0;
     double* wq = nullptr;
     double* geo = nullptr;
+    double *geoG = nullptr, *geoJ = nullptr, *geoN = nullptr;   // curved hexes (desc.affine = 0)
     int* mapP = nullptr;
     int* send_idx = nullptr;
     long long n_send = 0;

@@ -187,6 +187,7 @@ int hexfast_try_create(esdg_ctx* ctx) {
     const esdg_desc& d = ctx->d;
     if (d.elem != ESDG_HEX || d.dim != 3 || !d.collocated) return ESDG_OK;
     if (getenv("ESDG_FORCE_GENERIC")) return ESDG_OK;
+    if (!d.affine) return ESDG_OK;   // curved elements: per-point geometric factors, generic kernels
     int n = (int)std::lround(std::cbrt((double)d.Nq));
     if (n * n * n != d.Nq || n < 2 || n > 5 || d.Nfaces != 6 || d.Nfq != 6 * n * n) return ESDG_OK;
     const int Nq = d.Nq, nfp = n * n, Nfq = d.Nfq, Nh = Nq + Nfq;

@@ -252,7 +252,13 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_rhs(const 
         double nJ[DIM];
 #pragma unroll
         for (int d = 0; d < DIM; ++d) nJ[d] = g[d];
-        const double sJ = g[DIM];
+        double sJ = g[DIM];
+        if (DIM == 3 && p.curved) {   // normals of the face point itself (dg3D_euler_hex.jl:80-84)
+            const double* gn = p.geoN + (size_t)e * 4 * p.Nfq + k;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) nJ[d] = gn[d * p.Nfq];
+            sJ = gn[DIM * p.Nfq];
+        }
         const double isJ = fast_rcp(sJ);
         // exterior state
         const long long ip = p.mapP[e * p.Nfq + k];
@@ -309,10 +315,21 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_rhs(const 
         double Gr[DIM * DIM];
 #pragma unroll
         for (int q = 0; q < DIM * DIM; ++q) Gr[q] = G[q];
+        const bool curved = DIM == 3 && p.curved;
+        const double* Ge = curved ? p.geoG + (size_t)e * (DIM * DIM) * p.Nh : nullptr;
+        double Gi[DIM * DIM];
+        if (curved) {
+#pragma unroll
+            for (int q = 0; q < DIM * DIM; ++q) Gi[q] = Ge[q * p.Nh + r];
+        }
         const int n = p.Qp.cnt[r];
         for (int k = 0; k < n; ++k) {
             const int j = p.Qp.col[r * p.Qp.width + k];
             const double* cq = p.Qp.c + (size_t)(r * p.Qp.width + k) * 3;
+            if (curved) {   // geofacs of the pair averaged: .5*(rxJ[i]+rxJ[j]) ... (dg3D_euler_hex.jl:145-151)
+#pragma unroll
+                for (int q = 0; q < DIM * DIM; ++q) Gr[q] = .5 * (Gi[q] + Ge[q * p.Nh + j]);
+            }
             // c_d = sum_k G[d][k] * Q_k[i,j]   (Fr = rxJ*Fx + ryJ*Fy ..., :126-129)
             double c[DIM];
 #pragma unroll
@@ -351,7 +368,8 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_rhs(const 
     for (int i = tid; i < nb * p.Ns; i += nt) {
         const int eb = i / p.Ns, r = i - eb * p.Ns;
         const long long e = e0 + eb;
-        const double J = p.geo[e * p.geo_stride + DIM * DIM];
+        double J = p.geo[e * p.geo_stride + DIM * DIM];
+        if (DIM == 3 && p.curved) J = p.geoJ[(size_t)e * p.Nq + r];   // collocated: Ns == Nq (rhsQ ./ J, :212)
         const double mJ = -fast_rcp(J);
         double rr[NF];
         if (!p.collocated) {

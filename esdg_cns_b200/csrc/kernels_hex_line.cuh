@@ -357,7 +357,11 @@ __global__ void ESDG_LINE_BOUNDS(n) k_hex_stage_line(
 #pragma unroll
     for (int r = 0; r < MAXF; ++r) {
         const int it = tid + r * NT;
+#ifndef ESDG_LINE_NOLOAD
         ipv[r] = it < nb * Nfq ? p.mapP[gf0 + it] : -1;
+#else
+        ipv[r] = -1;
+#endif
     }
     PHASE_MARK(12);
     if (tid == 0) mbar_init(&mbar, 1);
@@ -380,6 +384,7 @@ __global__ void ESDG_LINE_BOUNDS(n) k_hex_stage_line(
     // 16-byte alignment of every run (uniform per CTA); otherwise the 8-byte cp.async path
     const bool bulk = (((p.q_stride | gq0 | (long long)(nb * Nq) | p.t_stride | gf0 | (long long)(nb * Nfq)) & 1) == 0) &&
                       ((((size_t)p.Q | (size_t)p.res | (size_t)p.Lcur | (size_t)p.Tcur) & 15) == 0);
+#ifndef ESDG_LINE_NOLOAD   // NOLOAD: upper-bound experiment without any global read (garbage in shared memory)
     if (bulk) {
         // 19 (mode 1) / 14 runs, one per lane-0 of the warps in turn: TMA issue costs ~90 cycles per copy when
         // one thread issues them back to back
@@ -447,10 +452,13 @@ __global__ void ESDG_LINE_BOUNDS(n) k_hex_stage_line(
             }
         }
     }
+#endif
     PHASE_MARK(0);
     cp_async_wait_all();
     __syncthreads();
+#ifndef ESDG_LINE_NOLOAD
     if (bulk) mbar_wait(&mbar, 0);
+#endif
     PHASE_MARK(1);
 
     // ---- A: volume primitives -> shared (W nodes per thread, interleaved) -------------------------
@@ -755,7 +763,9 @@ __global__ void ESDG_LINE_BOUNDS(n) k_hex_stage_line(
             p.partial[blockIdx.x] = t;
         }
     }
+#ifndef ESDG_LINE_NOLOAD
     if (bad) atomicOr(p.bad, 1);
+#endif
 }
 
 }  // namespace esdg

@@ -30,7 +30,7 @@ typedef struct esdg_ctx esdg_ctx;
 
 typedef enum {
     ESDG_OK = 0,
-    ESDG_EINVAL = 1,  /* bad argument / missing operator / non-affine mesh     */
+    ESDG_EINVAL = 1,  /* bad argument / missing operator / mesh not as declared */
     ESDG_ECUDA = 2,   /* CUDA runtime error (esdg_last_error has the string)    */
     ESDG_ENCCL = 3,   /* reserved                                               */
     ESDG_ENOMEM = 4,  /* device allocation failed                               */
@@ -55,8 +55,11 @@ typedef struct {
                               (dg2D_euler_quad.jl:149-151, dg3D_euler_hex.jl:176-178)
                            0: Vq / VhP projection of every hybridized point
                               (dg2D_euler_tri.jl:138-140)                                   */
-    int32_t affine;     /* must be 1: geofacs constant per element (`vgeo[1,e]`,
-                           dg2D_euler_quad.jl:175).  Curved meshes: SURVEY 8(f) rank 2.    */
+    int32_t affine;     /* 1: geofacs constant per element (`vgeo[1,e]`, dg2D_euler_quad.jl:175);
+                           verified by esdg_finalize.  0 (collocated hexes only): curved
+                           elements, geofacs at every hybridized point averaged per pair
+                           (dg3D_euler_hex.jl:90-101, :145-151), J per node, normals per face
+                           point; esdg_set_geometry then needs the full Nh / Nq / Nfq x K arrays */
     int64_t K;          /* elements owned by this context (md.K, or the local slab)        */
     int64_t n_halo;     /* extra trace points appended after Nfq*K that mapP may point to
                            (neighbour-rank face traces); 0 on a single GPU                  */

@@ -318,3 +318,25 @@ def setup_hex(N=2, K1D=4, scale=(1.0, 1.0, 1.0), shift=(0.0, 0.0, 0.0)):
     ops = build_sbp_ops(rd)
     interp_geofacs(md, rd, ops)
     return rd, md, ops
+
+
+def setup_hex_curved(N=2, K1D=3, amp=.08, scale=(1.0, 1.0, 1.0), seed=1):
+    """``setup_hex`` with the interior mesh vertices displaced (trilinear, non-affine elements): the
+    curved-mesh branch of dg3D_euler_hex.jl (geometric factors at every hybridized point, :69-101, averaged per
+    pair in the Hadamard sum, :145-151).  Boundary vertices stay put, so the periodic matching is unchanged."""
+    if np.isscalar(K1D):
+        K1D = (K1D, K1D, K1D)
+    VX, VY, VZ, EToV = M.uniform_hex_mesh(*K1D)
+    rng = np.random.default_rng(seed)
+    inner = (np.abs(VX) < 1 - 1e-12) & (np.abs(VY) < 1 - 1e-12) & (np.abs(VZ) < 1 - 1e-12)
+    h = 2.0 / np.asarray(K1D)
+    VX = VX + inner * amp * h[0] * rng.uniform(-1, 1, VX.shape)
+    VY = VY + inner * amp * h[1] * rng.uniform(-1, 1, VY.shape)
+    VZ = VZ + inner * amp * h[2] * rng.uniform(-1, 1, VZ.shape)
+    VX, VY, VZ = scale[0] * VX, scale[1] * VY, scale[2] * VZ
+    rd = S.init_reference_hex(N)
+    md = S.init_mesh((VX, VY, VZ), EToV, rd)
+    S.make_periodic(md, rd, (2 * scale[0], 2 * scale[1], 2 * scale[2]))
+    ops = build_sbp_ops(rd)
+    interp_geofacs(md, rd, ops)
+    return rd, md, ops

@@ -74,6 +74,24 @@ def test_hex_entropy_conservation_random_state():
     assert rt < 0
 
 
+def test_curved_hex_entropy_conservation_and_freestream():
+    """Curved (trilinear) hexes, the per-point geometric-factor branch of dg3D_euler_hex.jl:69-101,145-151."""
+    rd, md, ops = SV.setup_hex_curved(2, 3)
+    assert np.abs(md.rxJ - md.rxJ[:1]).max() > 1e-3 and md.J.min() > 0
+    one = np.ones_like(md.xq)
+    Qc = list(P.primitive_to_conservative(1.2 * one, (.3 * one, -.2 * one, .1 * one), .9 * one))
+    r, _ = SV.rhs_collocated(Qc, md, ops, rd, .25)
+    assert max(np.abs(x).max() for x in r) < 1e-12
+    rng = np.random.default_rng(0)
+    rho = 2 + .1 * rng.random(md.xq.shape)
+    p = 1 + .1 * rng.random(rho.shape)
+    Q = list(P.primitive_to_conservative(rho, (0 * one, one, 0 * one), p))
+    _, rt = SV.rhs_collocated(Q, md, ops, rd, 0.0, True)
+    assert abs(rt) < 1e-13
+    _, rt = SV.rhs_collocated(Q, md, ops, rd, .25, True)
+    assert rt < 0
+
+
 def test_tri_entropy_and_freestream():
     rd, md, ops, Q = SV.setup_tri_vortex(3, 4, 4)
     _, rt = SV.rhs_tri(Q, md, ops, rd, 0.0, True)
