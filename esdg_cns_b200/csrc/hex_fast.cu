@@ -127,6 +127,18 @@ int set_attrs(esdg_ctx* ctx) {
         if (const char* ex = getenv("ESDG_HEX_EXTRA_SMEM_KB")) h->smem_stage += (size_t)atoi(ex) * 1024;   // occupancy experiments
         CK(cudaFuncSetAttribute(k_hex_stage_line<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage));
         CK(cudaFuncSetAttribute(k_hex_stage_line<n, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage));
+        // persistent producer-warp variant (kernels_hex_line.cuh): measured 5.40 ms against 5.27 ms per stage for the
+        // one-shot kernel on 128x128x16 N=4 (the two resident CTAs already hide each other's loads), so it is opt-in:
+        // ESDG_HEX_PERSIST=1
+        const char* pv = getenv("ESDG_HEX_PERSIST");
+        h->persist = pv && atoi(pv) != 0;
+        h->smem_stage_p = (size_t)LineDimsP<n>::SMEM_DOUBLES * sizeof(double);
+        h->threads_p = LineDimsP<n>::THREADS;
+        CK(cudaFuncSetAttribute(k_hex_stage_line_p<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage_p));
+        CK(cudaFuncSetAttribute(k_hex_stage_line_p<n, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage_p));
+        int sms = 0;
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        h->grid_p = sms * LD::MINB;
     } else {
         h->EB = D::EB;
         h->threads = D::THREADS;
@@ -157,7 +169,34 @@ template <int n>
 int launch_stage_n(esdg_ctx* ctx, const HexParams& p, int blocks) {
     HexFast* h = ctx->hex;
     tick(ctx, "hex_stage");
-    if (h->line) {
+    if (h->line && h->persist) {
+        // full batches with 16-byte aligned runs go to the persistent kernel, a ragged tail to the one-shot kernel
+        using LD = LineDims<n>;
+        const bool aligned = (((p.q_stride | (p.e_begin * LD::Nq) | p.t_stride | (p.e_begin * LD::Nfq)) & 1) == 0) &&
+                             ((((size_t)p.Q | (size_t)p.res | (size_t)p.Lcur | (size_t)p.Tcur) & 15) == 0);
+        const long long nbatch = aligned ? p.e_count / LD::EB : 0;
+        if (nbatch > 0) {
+            HexParams pp = p;
+            pp.e_count = nbatch * LD::EB;
+            const int grid = (int)std::min<long long>(nbatch, h->grid_p);
+            if (h->diag)
+                k_hex_stage_line_p<n, true><<<grid, h->threads_p, h->smem_stage_p, ctx->stream>>>(pp);
+            else
+                k_hex_stage_line_p<n, false><<<grid, h->threads_p, h->smem_stage_p, ctx->stream>>>(pp);
+        }
+        const long long done = nbatch * LD::EB;
+        if (done < p.e_count) {
+            HexParams pt = p;
+            pt.e_begin = p.e_begin + done;
+            pt.e_count = p.e_count - done;
+            pt.partial = p.partial + nbatch;
+            const int tb = (int)((pt.e_count + h->EB - 1) / h->EB);
+            if (h->diag)
+                k_hex_stage_line<n, true><<<tb, h->threads, h->smem_stage, ctx->stream>>>(pt);
+            else
+                k_hex_stage_line<n, false><<<tb, h->threads, h->smem_stage, ctx->stream>>>(pt);
+        }
+    } else if (h->line) {
         if (h->diag)
             k_hex_stage_line<n, true><<<blocks, h->threads, h->smem_stage, ctx->stream>>>(p);
         else

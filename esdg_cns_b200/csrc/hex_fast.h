@@ -16,6 +16,9 @@ struct HexFast {
     int threads = 0, EB = 1;           // stage kernel launch shape
     int threads_tr = 0, EB_tr = 1;     // k_hex_traces launch shape
     bool line = true;                  // line-per-thread stage kernel (kernels_hex_line.cuh); false: node-per-thread
+    bool persist = false;              // persistent producer-warp variant of the line kernel
+    size_t smem_stage_p = 0;
+    int threads_p = 0, grid_p = 0;
 };
 
 enum { ESDG_PART_ALL = 0, ESDG_PART_BOUNDARY = 1, ESDG_PART_INTERIOR = 2 };

@@ -111,23 +111,29 @@ __device__ __forceinline__ void set_lane(NodeV<W>& d, int q, const Node& s) {
 
 // pair_flux (kernels_hex.cuh) on W independent pairs: EC flux (euler_fluxes.jl:51-89, logmean.jl:14-28)
 // contracted with g; one reciprocal per pair serves rholog, 1/betalog and pa.
+// Instruction diet (all within an ulp of the reference formulas):
+//  * sums instead of means: with s = aL + aR the Taylor argument is f/2 = da/s, f^2 = 4 (da/s)^2, and the
+//    branch test |da| < 1e-4 (s/2) is the same predicate written as |da| < 5e-5 s (exact scaling by 2);
+//  * in the Taylor branch |f| < 1e-4, so f^4 terms of logmean.jl:18-27 are < 5.2e-18, a twentieth of an ulp of
+//    the leading 1: 1 - .2 f^2 is the reference polynomial to double precision;
+//  * DIAG (axis-aligned elements): every flux component is proportional to the single metric term g[0]; it is
+//    factored out here and applied once to the line's accumulated sums (GSCALED = false: F is F/g[0]).
 template <int W, bool DIAG>
 __device__ __forceinline__ void pair_flux_v(const NodeV<W>& A, const NodeV<W>& B, const VD<W>* g, double c_igm, VD<W>* F) {
-    const VD<W> dar = B.rho - A.rho, hr = .5 * (A.rho + B.rho);
-    const VD<W> dab = B.beta - A.beta, sb = A.beta + B.beta, hb = .5 * sb;
-    const VB<W> tr = vlt(vabs(dar), 1e-4 * hr), tb = vlt(vabs(dab), 1e-4 * hb);
-    const VD<W> X = vsel(tr, hr, B.lr - A.lr);
-    const VD<W> Y = vsel(tb, hb, dab);
+    const VD<W> dar = B.rho - A.rho, sr = A.rho + B.rho;
+    const VD<W> dab = B.beta - A.beta, sb = A.beta + B.beta;
+    const VB<W> tr = vlt(vabs(dar), 5e-5 * sr), tb = vlt(vabs(dab), 5e-5 * sb);
+    const VD<W> X = vsel(tr, sr, B.lr - A.lr);
+    const VD<W> Y = vsel(tb, sb, dab);
     const VD<W> XY = X * Y;
     const VD<W> R = vrcp(XY * sb);
     const VD<W> iX = R * (Y * sb), iY = R * (X * sb), iZ = R * XY;
-    const VD<W> qr = dar * iX;                     // f (Taylor branch) or the log mean itself
+    const VD<W> qr = dar * iX;                     // f/2 (Taylor branch) or the log mean itself
     const VD<W> fb = dab * iY;
-    const VD<W> vr = qr * qr, vb = fb * fb;
-    const VD<W> rholog = vsel(tr, hr * vfma(vr, vfma(vr, vfma(vr, 0.026038857142857, -.0512), -.2), 1.0), qr);
-    const VD<W> xb = vb * vfma(vb, vfma(vb, 0.026038857142857, -.0512), -.2);
-    const VD<W> ibl = iY * vsel(tb, 1.0 - xb, B.lb - A.lb);   // 1/betalog
-    const VD<W> pa = hr * iZ;                                  // rhoavg/(betaL+betaR)
+    const VD<W> vr = qr * qr, vb = fb * fb;        // f^2 / 4
+    const VD<W> rholog = vsel(tr, sr * vfma(vr, -.4, .5), qr);                    // (s/2)(1 - .2 f^2)
+    const VD<W> ibl = iY * vsel(tb, vfma(vb, 1.6, 2.0), B.lb - A.lb);             // 1/betalog = (2/s)(1 + .2 f^2)
+    const VD<W> pa = (.5 * sr) * iZ;                                              // rhoavg/(betaL+betaR)
     VD<W> uavg[3], unorm, un;
     uavg[0] = A.u[0] + B.u[0];                                 // Node.u holds HALF velocities
     uavg[1] = A.u[1] + B.u[1];
@@ -135,23 +141,25 @@ __device__ __forceinline__ void pair_flux_v(const NodeV<W>& A, const NodeV<W>& B
     unorm = A.u[0] * B.u[0];
     unorm = vfma(A.u[1], B.u[1], unorm);
     unorm = vfma(A.u[2], B.u[2], unorm);                       // = uL.uR / 4
-    un = g[0] * uavg[0];
-    if (!DIAG) {
-        un = vfma(g[1], uavg[1], un);
-        un = vfma(g[2], uavg[2], un);
-    }
     const VD<W> Ep = vfma(rholog, vfma(unorm, 2.0, ibl * c_igm), pa);   // rholog/(2(g-1)betalog)+pa+.5 rholog uL.uR
-    const VD<W> m = rholog * un;
-    F[0] = m;
-    F[1] = vfma(m, uavg[0], pa * g[0]);
     if (DIAG) {
+        const VD<W> m = rholog * uavg[0];                      // fluxes / g[0]
+        F[0] = m;
+        F[1] = vfma(m, uavg[0], pa);
         F[2] = m * uavg[1];
         F[3] = m * uavg[2];
+        F[4] = Ep * uavg[0];
     } else {
+        un = g[0] * uavg[0];
+        un = vfma(g[1], uavg[1], un);
+        un = vfma(g[2], uavg[2], un);
+        const VD<W> m = rholog * un;
+        F[0] = m;
+        F[1] = vfma(m, uavg[0], pa * g[0]);
         F[2] = vfma(m, uavg[1], pa * g[1]);
         F[3] = vfma(m, uavg[2], pa * g[2]);
+        F[4] = Ep * un;
     }
-    F[4] = Ep * un;
 }
 
 // log_pos / exp_mod of kernels_hex.cuh on W lanes
@@ -461,311 +469,173 @@ __global__ void ESDG_LINE_BOUNDS(n) k_hex_stage_line(
 #endif
     PHASE_MARK(1);
 
-    // ---- A: volume primitives -> shared (W nodes per thread, interleaved) -------------------------
-#pragma unroll 1
-    for (int r = 0; r < GV; ++r) {
-        int it[W];
-        bool act[W];
-        VD<W> U[5], rho, hu[3], beta, rhoe;
-        VFOR {
-            it[q_] = tid + (r * W + q_) * NT;
-            act[q_] = it[q_] < nb * Nq;
-            it[q_] = act[q_] ? it[q_] : 0;
-        }
-#pragma unroll
-        for (int f = 0; f < 5; ++f) VFOR U[f].v[q_] = sQ[f * EN + it[q_]];
-        vol_prim_v<W>(U, p.gamma, rho, hu, beta, rhoe);
-        VFOR {
-            if (act[q_]) {
-                bad = bad || !(U[0].v[q_] > 0.0) || !(rhoe.v[q_] > 0.0);
-                sWV[it[q_]] = rho.v[q_];
-                sWV[EN + it[q_]] = hu[0].v[q_];
-                sWV[2 * EN + it[q_]] = hu[1].v[q_];
-                sWV[3 * EN + it[q_]] = hu[2].v[q_];
-                sWV[4 * EN + it[q_]] = beta.v[q_];
-            }
-        }
-    }
-
-    PHASE_MARK(2);
-    // ---- B: surface flux at face points (dg3D_euler_hex.jl:182-197), W points per thread ----------
-#pragma unroll 1
-    for (int r = 0; r < GF; ++r) {
-        int it[W];
-        bool act[W];
-        NodeV<W> M, P;
-        VD<W> nJ[3], sJ;
-        VFOR {
-            it[q_] = tid + (r * W + q_) * NT;
-            act[q_] = it[q_] < nb * Nfq;
-            it[q_] = act[q_] ? it[q_] : 0;
-            const int b2 = it[q_] / Nfq, k = it[q_] - b2 * Nfq;
-            const double* gf = sGeo + b2 * 34 + 10 + (k / nfp) * 4;
-            nJ[0].v[q_] = gf[0]; nJ[1].v[q_] = gf[1]; nJ[2].v[q_] = gf[2]; sJ.v[q_] = gf[3];
-            set_lane(M, q_, ld_node(sWF, EF, it[q_]));
-            set_lane(P, q_, ld_node(sP, EF, it[q_]));
-        }
-        VD<W> F[5];
-        pair_flux_v<W, false>(M, P, nJ, c_igm, F);
-        if (p.lf_scale != 0.0) {
-            // conservative states from the primitive traces: E = p/(g-1) + .5 rho |u|^2, p = rho/(2 beta)
-            const double ig1 = 1.0 / (p.gamma - 1.0);
-            const VD<W> isJ = vrcp(sJ);
-            const VD<W> irM = vrcp(M.rho), irP = vrcp(P.rho);
-            VD<W> UM[5], UP[5], unM, unP, kM, kP;
-            UM[0] = M.rho;
-            UP[0] = P.rho;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const VD<W> uM = 2.0 * M.u[d], uP = 2.0 * P.u[d];
-                UM[1 + d] = M.rho * uM;
-                UP[1 + d] = P.rho * uP;
-                if (d == 0) {
-                    kM = UM[1] * uM; kP = UP[1] * uP;
-                    unM = UM[1] * nJ[0]; unP = UP[1] * nJ[0];
-                } else {
-                    kM = vfma(UM[1 + d], uM, kM);
-                    kP = vfma(UP[1 + d], uP, kP);
-                    unM = vfma(UM[1 + d], nJ[d], unM);
-                    unP = vfma(UP[1 + d], nJ[d], unP);
-                }
-            }
-            const VD<W> pM = .5 * M.rho * vrcp(M.beta), pP = .5 * P.rho * vrcp(P.beta);
-            UM[4] = vfma(kM, .5, pM * ig1);
-            UP[4] = vfma(kP, .5, pP * ig1);
-            const VD<W> lamM = wavespeed_v<W>(irM, unM * isJ, UM[4], p.gamma);
-            const VD<W> lamP = wavespeed_v<W>(irP, unP * isJ, UP[4], p.gamma);
-            const VD<W> LFc = p.lf_scale * vmax(lamM, lamP) * sJ;
-#pragma unroll
-            for (int f = 0; f < 5; ++f) F[f] = vfma(-LFc, UP[f] - UM[f], F[f]);
-        }
-        VFOR {
-            if (act[q_]) {
-#pragma unroll
-                for (int f = 0; f < 5; ++f) sP[f * EF + it[q_]] = F[f].v[q_];
-            }
-        }
-    }
-    PHASE_MARK(3);
-    __syncthreads();
-    PHASE_MARK(4);
-
-    // ---- C: one line per thread, two pairs at a time -----------------------------------------------
-    if (tid < nb * NL) {
-        const int eb = tid / NL, l = tid - eb * NL;
-        const int d = l / nfp, m = l - d * nfp;
-        int base, stride;
-        face_line<n>(d, m, base, stride);
-        base += eb * Nq;
-        const int c1 = d == 2 ? 0 : d + 1, c2 = c1 == 2 ? 0 : c1 + 1;   // physical components in rotated order d,c1,c2
-        const int pl0 = 1 + d, pl1 = 1 + c1, pl2 = 1 + c2;
-        const double* G = sGeo + eb * 34;
-        const double g0 = G[3 * d + d], g1 = G[3 * c1 + d], g2 = G[3 * c2 + d];   // (r_x, r_y, r_z) J of direction d, rotated
-        Node nd[n];
-#pragma unroll
-        for (int a = 0; a < n; ++a) {
-            const int idx = base + a * stride;
-            nd[a].rho = sWV[idx];
-            nd[a].u[0] = sWV[pl0 * EN + idx];
-            nd[a].u[1] = sWV[pl1 * EN + idx];
-            nd[a].u[2] = sWV[pl2 * EN + idx];
-            nd[a].beta = sWV[4 * EN + idx];
-            nd[a].lr = sWV[5 * EN + idx];
-            nd[a].lb = sWV[6 * EN + idx];
-        }
-        double acc[n][5];
-#pragma unroll
-        for (int a = 0; a < n; ++a)
-#pragma unroll
-            for (int f = 0; f < 5; ++f) acc[a][f] = 0.0;
-#ifndef ESDG_LINE_WC
-#define ESDG_LINE_WC 2   // pairs evaluated together in the line phase (1 lowers the register need by ~40)
-#endif
-        // volume-volume pairs: acc_a += T[a][b] F(a,b), acc_b += T[b][a] F(a,b)
-        line_vv_all<n, DIAG, 0, ESDG_LINE_WC>(nd, acc, g0, g1, g2, c_igm, p);
-        // volume-face pairs: node a against the two face points its line ends in (lane = side)
-        Node fn[2];
-        int fidx[2];
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            fidx[side] = eb * Nfq + (2 * d + side) * nfp + m;
-            fn[side].rho = sWF[fidx[side]];
-            fn[side].u[0] = sWF[pl0 * EF + fidx[side]];
-            fn[side].u[1] = sWF[pl1 * EF + fidx[side]];
-            fn[side].u[2] = sWF[pl2 * EF + fidx[side]];
-            fn[side].beta = sWF[4 * EF + fidx[side]];
-            fn[side].lr = sWF[5 * EF + fidx[side]];
-            fn[side].lb = sWF[6 * EF + fidx[side]];
-        }
-        double h[2][5];
-#pragma unroll
-        for (int f = 0; f < 5; ++f) h[0][f] = h[1][f] = 0.0;
-        line_vf_all<n, DIAG, 0, ESDG_LINE_WC>(nd, fn, acc, h, g0, g1, g2, c_igm, p);
-        // face rows: H = flux* -/+ sum_a l[a] F(a) (physical field order in shared memory); only the nodes
-        // of THIS line lift from these two face points, so the lift (Lf as a 1-D sweep) is applied here
-        {
-            const double* fl = sP + fidx[0];
-            const double Hm[5] = {fl[0] + h[0][0], fl[pl0 * EF] + h[0][1], fl[pl1 * EF] + h[0][2], fl[pl2 * EF] + h[0][3],
-                                  fl[4 * EF] + h[0][4]};
-            fl = sP + fidx[1];
-            const double Hp[5] = {fl[0] - h[1][0], fl[pl0 * EF] - h[1][1], fl[pl1 * EF] - h[1][2], fl[pl2 * EF] - h[1][3],
-                                  fl[4 * EF] - h[1][4]};
-#pragma unroll
-            for (int a = 0; a < n; ++a)
-#pragma unroll
-                for (int f = 0; f < 5; ++f) acc[a][f] = fma(p.lpw[a], Hp[f], fma(p.lmw[a], Hm[f], acc[a][f]));
-        }
-        double* A = sA + d * 5 * EN;
-#pragma unroll
-        for (int a = 0; a < n; ++a) {
-            const int idx = base + a * stride;
-            A[idx] = acc[a][0];
-            A[pl0 * EN + idx] = acc[a][1];
-            A[pl1 * EN + idx] = acc[a][2];
-            A[pl2 * EN + idx] = acc[a][3];
-            A[4 * EN + idx] = acc[a][4];
-        }
-    }
-    PHASE_MARK(5);
-    __syncthreads();
-    PHASE_MARK(6);
-
-    // ---- E: lift, scale, rhstest, LSRK stage; F (volume part): entropy variables of the new state ----
-    double tsum = 0.0;
-#pragma unroll 1
-    for (int r = 0; r < GV; ++r) {
-        int it[W];
-        bool act[W];
-        VD<W> acc[5], U[5], J, wJ;
-        VFOR {
-            it[q_] = tid + (r * W + q_) * NT;
-            act[q_] = it[q_] < nb * Nq;
-            it[q_] = act[q_] ? it[q_] : 0;
-        }
-#pragma unroll
-        for (int f = 0; f < 5; ++f)
-            VFOR acc[f].v[q_] = (sA[f * EN + it[q_]] + sA[(5 + f) * EN + it[q_]]) + sA[(10 + f) * EN + it[q_]];
-        VFOR {
-            const int eb = it[q_] / Nq, i = it[q_] - eb * Nq;
-            J.v[q_] = sGeo[eb * 34 + 9];
-            if (p.want_rhstest) {
-                const int xa = i % n, xb = (i / n) % n, xc = i / (n * n);
-                wJ.v[q_] = s_w[xa] * s_w[xb] * s_w[xc] * J.v[q_];
-            }
-        }
-        const VD<W> mJ = -vrcp(J);
-        VD<W> rr[5];
-#pragma unroll
-        for (int f = 0; f < 5; ++f) {
-            rr[f] = acc[f] * mJ;
-            VFOR U[f].v[q_] = sQ[f * EN + it[q_]];
-        }
-        if (p.want_rhstest) {
-            VD<W> V[5], lr, lb;
-            VFOR { lr.v[q_] = sWV[5 * EN + it[q_]]; lb.v[q_] = sWV[6 * EN + it[q_]]; }
-            const VD<W> hir = .5 * vrcp(U[0]);
-            const VD<W> ke = hir * vfma(U[1], U[1], vfma(U[2], U[2], U[3] * U[3]));
-            entropy_vars_v<W>(U, U[4] - ke, lr, lb, p.gamma, V);
-            VFOR {
-                if (act[q_]) {
-#pragma unroll
-                    for (int f = 0; f < 5; ++f) tsum = fma(wJ.v[q_] * V[f].v[q_], rr[f].v[q_], tsum);
-                }
-            }
-        }
-        if (p.mode == 0) {
-            VFOR {
-                if (act[q_]) {
-#pragma unroll
-                    for (int f = 0; f < 5; ++f) p.rhs[f * p.q_stride + e0 * Nq + it[q_]] = rr[f].v[q_];
-                }
-            }
-        } else {
-            VD<W> Un[5], rs[5];
-#pragma unroll
-            for (int f = 0; f < 5; ++f) {
-                VFOR rs[f].v[q_] = fma(p.rk_a, sR[f * EN + it[q_]], p.dt * rr[f].v[q_]);
-                Un[f] = vfma(p.rk_b, rs[f], U[f]);
-            }
-            VFOR {
-                if (act[q_]) {
-#pragma unroll
-                    for (int f = 0; f < 5; ++f) {
-                        p.res[f * p.q_stride + e0 * Nq + it[q_]] = rs[f].v[q_];
-                        p.Qout[f * p.q_stride + e0 * Nq + it[q_]] = Un[f].v[q_];
-                    }
-                }
-            }
-            VD<W> rho, hu[3], beta, rhoen, V[5];
-            vol_prim_v<W>(Un, p.gamma, rho, hu, beta, rhoen);
-            const VD<W> lr = vlog_pos<W>(rho), lb = vlog_pos<W>(beta);
-            entropy_vars_v<W>(Un, rhoen, lr, lb, p.gamma, V);
-            VFOR {
-                if (act[q_]) {
-                    bad = bad || !(Un[0].v[q_] > 0.0) || !(rhoen.v[q_] > 0.0);
-                    p.Lnext[e0 * Nq + it[q_]] = lr.v[q_];
-                    p.Lnext[p.q_stride + e0 * Nq + it[q_]] = lb.v[q_];
-                    // V[5][EN] aliases the d = 0 accumulator block: this thread is the only reader of those slots
-#pragma unroll
-                    for (int f = 0; f < 5; ++f) sA[f * EN + it[q_]] = V[f].v[q_];
-                }
-            }
-        }
-    }
-    PHASE_MARK(7);
-    if (p.mode == 1) {
-        __syncthreads();
-        PHASE_MARK(8);
-        // ---- F: project to the faces, 7-plane traces of the new state ----------------------------
-#pragma unroll 1
-        for (int r = 0; r < GF; ++r) {
-            int it[W];
-            bool act[W];
-            VD<W> V[5];
-            VFOR {
-                it[q_] = tid + (r * W + q_) * NT;
-                act[q_] = it[q_] < nb * Nfq;
-                it[q_] = act[q_] ? it[q_] : 0;
-                const int eb = it[q_] / Nfq, k = it[q_] - eb * Nfq;
-                const int face = k / nfp, m = k - face * nfp;
-                int base, stride;
-                face_line<n>(face >> 1, m, base, stride);
-                const double* l = (face & 1) ? s_lp : s_lm;
-                const double* v = sA + eb * Nq + base;
-#pragma unroll
-                for (int f = 0; f < 5; ++f) V[f].v[q_] = 0.0;
-#pragma unroll
-                for (int a = 0; a < n; ++a) {
-                    const double la = l[a];
-#pragma unroll
-                    for (int f = 0; f < 5; ++f) V[f].v[q_] = fma(la, v[f * EN + a * stride], V[f].v[q_]);
-                }
-            }
-            VD<W> Tv[HEX_TP];
-            trace_from_entropy_v<W>(V, p.gamma, p.lg1, p.l2g1, Tv);
-            VFOR {
-                if (act[q_]) {
-#pragma unroll
-                    for (int q = 0; q < HEX_TP; ++q) p.Tnext[q * p.t_stride + e0 * Nfq + it[q_]] = Tv[q].v[q_];
-                }
-            }
-        }
-    }
-    PHASE_MARK(9);
-    if (p.want_rhstest) {
-        __shared__ double red[32];
-        for (int o = 16; o > 0; o >>= 1) tsum += __shfl_down_sync(0xffffffffu, tsum, o);
-        if ((tid & 31) == 0) red[tid >> 5] = tsum;
-        __syncthreads();
-        if (tid == 0) {
-            double t = 0.0;
-            for (int wv = 0; wv < NT / 32; ++wv) t += red[wv];
-            p.partial[blockIdx.x] = t;
-        }
-    }
+#define LINE_CSYNC() __syncthreads()
+#define LINE_SGEO sGeo
+#define LINE_PARTIAL_IDX blockIdx.x
+#define LINE_AFTER_C()
+#define LINE_AFTER_E()
+#include "hex_line_phases.inc"
+#undef LINE_CSYNC
+#undef LINE_SGEO
+#undef LINE_PARTIAL_IDX
+#undef LINE_AFTER_C
+#undef LINE_AFTER_E
 #ifndef ESDG_LINE_NOLOAD
     if (bad) atomicOr(p.bad, 1);
 #endif
+}
+
+// ---- persistent variant with a producer warp -----------------------------------------------------------
+// The one-shot kernel spends 16 % of its time issuing and awaiting its own loads (measured with ESDG_LINE_NOLOAD),
+// and the register file leaves a sixth warp per CTA unused (5 compute warps are allocated as 6).  Here every CTA
+// stays resident and walks over its batches; warp 5 is a PRODUCER that fetches the next batch into the shared
+// arrays the compute warps have released, so loads overlap phases E/F of the previous batch:
+//   full_T  : own traces (7 TMA bulk copies), log stash (2), exterior traces (mapP gather, cp.async), geometry
+//   full_Q  : Q (5 TMA bulk copies) and the LSRK register (5)
+//   empty_T : compute threads arrive after the line phase (traces, exterior traces / flux*, stash consumed)
+//   empty_Q : compute threads arrive after the update phase
+// Full batches with 16-byte aligned runs only (the host sends a ragged tail to the one-shot kernel).
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(unsigned long long* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+template <int n>
+struct LineDimsP {
+    using D = LineDims<n>;
+    static constexpr int THREADS = D::THREADS + 32;                      // compute warps + the producer warp
+    static constexpr int SMEM_DOUBLES = D::SMEM_DOUBLES + D::EB * 34;    // geometry records double-buffered
+};
+
+template <int n, bool DIAG>
+__global__ void __launch_bounds__(LineDimsP<n>::THREADS, LineDims<n>::MINB) k_hex_stage_line_p(const __grid_constant__ HexParams p) {
+    using D = LineDims<n>;
+    constexpr int Nq = D::Nq, nfp = D::nfp, Nfq = D::Nfq, NL = D::NL, EB = D::EB, NT = D::THREADS;
+    constexpr int EN = D::EN, EF = D::EF;
+    constexpr int W = ESDG_LINE_WI;
+    extern __shared__ __align__(16) double sm[];
+    __shared__ unsigned long long pbar[4];   // full_T, full_Q, empty_T, empty_Q
+    double* sWV = sm;
+    double* sWF = sWV + 7 * EN;
+    double* sP = sWF + 7 * EF;
+    double* sA = sP + 7 * EF;
+    double* sQ = sA + 15 * EN;
+    double* sR = sQ + 5 * EN;
+    double* s_lm = sR + 5 * EN;
+    double* s_lp = s_lm + n;
+    double* s_lmw = s_lp + n;
+    double* s_lpw = s_lmw + n;
+    double* s_w = s_lpw + n;
+    double* sGeo2 = s_w + n;            // [2][EB][34]
+    const int tid = threadIdx.x;
+#ifdef ESDG_PHASE_TIMING
+    long long t_phase = clock64();
+#endif
+    if (tid == 0) {
+        mbar_init(&pbar[0], 33);        // expect_tx arrive of producer lane 0 + one cp.async arrive per producer lane
+        mbar_init(&pbar[1], 1);
+        mbar_init(&pbar[2], NT);
+        mbar_init(&pbar[3], NT);
+    }
+    if (tid < n) {
+        s_lm[tid] = p.lm[tid];
+        s_lp[tid] = p.lp[tid];
+        s_lmw[tid] = p.lmw[tid];
+        s_lpw[tid] = p.lpw[tid];
+        s_w[tid] = p.w[tid];
+    }
+    __syncthreads();
+    const long long nbatch = p.e_count / EB;
+    constexpr unsigned bq = (unsigned)(EB * Nq * 8), bf = (unsigned)(EB * Nfq * 8);
+
+    if (tid >= NT) {
+        // ---- producer warp ------------------------------------------------------------------------
+        const int lane = tid - NT;
+        constexpr int MAXFP = (EF + 31) / 32;
+        unsigned it = 0;
+        for (long long bi = blockIdx.x; bi < nbatch; bi += gridDim.x, ++it) {
+            const long long e0 = p.e_begin + bi * EB;
+            const long long gq0 = e0 * Nq, gf0 = e0 * Nfq;
+            int ipv[MAXFP];
+#pragma unroll
+            for (int r = 0; r < MAXFP; ++r) {
+                const int k = lane + r * 32;
+                ipv[r] = k < EF ? p.mapP[gf0 + k] : -1;
+            }
+            if (it > 0) mbar_wait(&pbar[2], (it - 1) & 1);
+            if (lane == 0) mbar_expect_tx(&pbar[0], 7u * bf + 2u * bq);
+            __syncwarp();
+            if (lane < 7) bulk_g2s(sWF + lane * EF, p.Tcur + lane * p.t_stride + gf0, bf, &pbar[0]);
+            else if (lane < 9) bulk_g2s(sWV + (lane - 2) * EN, p.Lcur + (lane - 7) * p.q_stride + gq0, bq, &pbar[0]);
+#pragma unroll
+            for (int r = 0; r < MAXFP; ++r) {
+                const int k = lane + r * 32;
+                if (k < EF) {
+#pragma unroll
+                    for (int q = 0; q < HEX_TP; ++q) cp_async8(sP + q * EF + k, p.Tcur + q * p.t_stride + ipv[r]);
+                }
+            }
+            double* sG = sGeo2 + (it & 1) * (EB * 34);
+            for (int k = lane; k < EB * 34; k += 32) cp_async8(sG + k, p.geo + e0 * 34 + k);
+            cp_async_mbar_arrive(&pbar[0]);
+            if (it > 0) mbar_wait(&pbar[3], (it - 1) & 1);
+            if (lane == 0) mbar_expect_tx(&pbar[1], (p.mode == 1 ? 10u : 5u) * bq);
+            __syncwarp();
+            if (lane < 5) bulk_g2s(sQ + lane * EN, p.Q + lane * p.q_stride + gq0, bq, &pbar[1]);
+            else if (lane < 10 && p.mode == 1) bulk_g2s(sR + (lane - 5) * EN, p.res + (lane - 5) * p.q_stride + gq0, bq, &pbar[1]);
+            // warm L2 for this CTA's next batch (fetched one batch time from now)
+            const long long b1 = bi + gridDim.x;
+            if (b1 < nbatch) {
+                const long long e1 = p.e_begin + b1 * EB;
+                for (int k = lane * 16; k < EN; k += 32 * 16) {
+                    const long long g1 = e1 * Nq + k;
+#pragma unroll
+                    for (int f = 0; f < 5; ++f) prefetch_l2(p.Q + f * p.q_stride + g1);
+                    prefetch_l2(p.Lcur + g1);
+                    prefetch_l2(p.Lcur + p.q_stride + g1);
+                    if (p.mode == 1) {
+#pragma unroll
+                        for (int f = 0; f < 5; ++f) prefetch_l2(p.res + f * p.q_stride + g1);
+                    }
+                }
+                for (int k = lane * 16; k < EF; k += 32 * 16) {
+                    prefetch_l2(p.mapP + e1 * Nfq + k);
+#pragma unroll
+                    for (int q = 0; q < HEX_TP; ++q) prefetch_l2(p.Tcur + q * p.t_stride + e1 * Nfq + k);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- compute warps ------------------------------------------------------------------------------
+    constexpr int MAXF = (EF + NT - 1) / NT, MAXV = (EN + NT - 1) / NT;
+    constexpr int GF = (MAXF + W - 1) / W, GV = (MAXV + W - 1) / W;
+    const double c_igm = 1.0 / (2.0 * (p.gamma - 1.0));
+    bool bad = false;
+    constexpr int nb = EB;
+    unsigned iter = 0;
+    for (long long bi = blockIdx.x; bi < nbatch; bi += gridDim.x, ++iter) {
+        const long long e0 = p.e_begin + bi * EB;
+        const double* sGeoC = sGeo2 + (iter & 1) * (EB * 34);
+        mbar_wait(&pbar[1], iter & 1);    // Q (phase A) and the LSRK register
+        mbar_wait(&pbar[0], iter & 1);    // traces, exterior traces, log stash, geometry
+        PHASE_MARK(1);
+#define LINE_CSYNC() asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory")
+#define LINE_SGEO sGeoC
+#define LINE_PARTIAL_IDX bi
+#define LINE_AFTER_C() do { if (!p.want_rhstest) mbar_arrive(&pbar[2]); } while (0)
+#define LINE_AFTER_E() do { if (p.want_rhstest) mbar_arrive(&pbar[2]); mbar_arrive(&pbar[3]); } while (0)
+#include "hex_line_phases.inc"
+#undef LINE_CSYNC
+#undef LINE_SGEO
+#undef LINE_PARTIAL_IDX
+#undef LINE_AFTER_C
+#undef LINE_AFTER_E
+    }
+    if (bad) atomicOr(p.bad, 1);
 }
 
 }  // namespace esdg
