@@ -42,6 +42,12 @@ struct GenericParams {
     Ell Ph;                 // Ns x Nh
     Ell Lf;                 // Ns x Nfq
     PairEll Qp;             // Nh rows
+    // symmetric schedule of the same pairs (skew operators, symmetric flux: each unordered pair once):
+    // in round t the thread of row r evaluates F(r, sym_dst[t*Nh + r]) (or idles when it is < 0) with the
+    // coefficients sym_c[(t*Nh + r)*3 + d] = Q_d[r][dst]; no row is the destination of two threads in a round
+    int sym_rounds;         // 0: row-wise evaluation of Qp
+    const int* sym_dst;
+    const double* sym_c;
     // modal path: the same operators dense + zero-padded for the tensor-core batch GEMMs (kernels_mma.cuh);
     // dPh carries volume_scale, dProjF = face rows of VhP
     Dense dVq, dProj, dProjF, dPh, dLf;

@@ -27,6 +27,9 @@ void fill_params(esdg_ctx* ctx, GenericParams& p) {
     p.Ph = ctx->Ph.view();
     p.Lf = ctx->Lf.view();
     p.Qp = PairEll{ctx->Nh, ctx->qp_width, ctx->qp_cnt, ctx->qp_col, ctx->qp_c};
+    p.sym_rounds = (ctx->sym_rounds > 0 && ctx->threads >= ctx->EB * ctx->Nh) ? ctx->sym_rounds : 0;
+    p.sym_dst = ctx->sym_dst;
+    p.sym_c = ctx->sym_c;
     p.dVq = ctx->dVq; p.dProj = ctx->dProj; p.dProjF = ctx->dProjF; p.dPh = ctx->dPh; p.dLf = ctx->dLf;
     p.wq = ctx->wq;
     p.geo = ctx->geo;
@@ -535,6 +538,91 @@ int esdg_finalize(esdg_ctx* ctx) {
                 }
         }
         ctx->qp_width = width;
+        // ---- symmetric schedule: every unordered pair once (operators skew to round-off, else stay row-wise)
+        {
+            bool skew = true;
+            double qmax = 0.0;
+            for (int k = 0; k < DIM; ++k)
+                for (int i = 0; i < Nh; ++i)
+                    for (int j = 0; j < Nh; ++j) qmax = std::max(qmax, std::fabs(Qm[k]->at(i, j)));
+            for (int k = 0; k < DIM && skew; ++k)
+                for (int i = 0; i < Nh && skew; ++i)
+                    for (int j = i; j < Nh; ++j)
+                        if (std::fabs(Qm[k]->at(i, j) + Qm[k]->at(j, i)) > 1e-13 * qmax) { skew = false; break; }
+            const char* ev = getenv("ESDG_SYM_PAIRS");
+            if (ev && atoi(ev) == 0) skew = false;
+            ctx->sym_rounds = 0;
+            if (skew) {
+                std::vector<std::pair<int, int>> edges;
+                for (int i = 0; i < Nh; ++i)
+                    for (int j = i + 1; j < Nh; ++j)
+                        if (nz(i, j) || nz(j, i)) edges.push_back({i, j});
+                // greedy: an edge goes to the earliest round in which its source has not evaluated and its
+                // destination has not been written, trying both orientations; high-degree rows first
+                std::vector<int> deg(Nh, 0);
+                for (auto& e2 : edges) { deg[e2.first]++; deg[e2.second]++; }
+                std::stable_sort(edges.begin(), edges.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+                    return std::max(deg[a.first], deg[a.second]) > std::max(deg[b.first], deg[b.second]);
+                });
+                std::vector<std::vector<char>> src_busy, dst_busy;
+                std::vector<std::vector<int>> dst_of;
+                auto ensure = [&](size_t t) {
+                    while (src_busy.size() <= t) {
+                        src_busy.emplace_back(Nh, 0);
+                        dst_busy.emplace_back(Nh, 0);
+                        dst_of.emplace_back(Nh, -1);
+                    }
+                };
+                auto place_greedy = [&]() {
+                    for (auto& e2 : edges) {
+                        for (size_t t = 0;; ++t) {
+                            ensure(t);
+                            int a = e2.first, b = e2.second;
+                            bool ok1 = !src_busy[t][a] && !dst_busy[t][b], ok2 = !src_busy[t][b] && !dst_busy[t][a];
+                            if (!ok1 && !ok2) continue;
+                            if (!ok1) std::swap(a, b);
+                            src_busy[t][a] = 1; dst_busy[t][b] = 1; dst_of[t][a] = b;
+                            break;
+                        }
+                    }
+                };
+                place_greedy();
+                int rounds = (int)dst_of.size();
+                // circulant schedule i -> (i + k) mod Nh: optimal for dense operators (triangles)
+                const int circ = Nh / 2;
+                if (circ < rounds) {
+                    dst_of.assign(circ, std::vector<int>(Nh, -1));
+                    for (int k = 1; k <= circ; ++k)
+                        for (int i = 0; i < Nh; ++i) {
+                            if (Nh % 2 == 0 && k == circ && i >= circ) continue;
+                            const int j = (i + k) % Nh;
+                            if (nz(i, j) || nz(j, i)) dst_of[k - 1][i] = j;
+                        }
+                    rounds = circ;
+                }
+                std::vector<int> sd((size_t)rounds * Nh, -1);
+                std::vector<double> sc((size_t)rounds * Nh * 3, 0.0);
+                for (int t = 0; t < rounds; ++t)
+                    for (int i = 0; i < Nh; ++i) {
+                        const int j = dst_of[t][i];
+                        sd[(size_t)t * Nh + i] = j;
+                        if (j >= 0)
+                            for (int q = 0; q < DIM; ++q) {
+                                const double v = Qm[q]->at(i, j);
+                                sc[((size_t)t * Nh + i) * 3 + q] = std::fabs(v) > TOL ? v : 0.0;
+                            }
+                    }
+                // a round costs a CTA barrier and idles the rows without a partner: measured on B200 the schedule wins on
+                // the dense triangle operators (config 2, 15 rounds against 30 entries per row: 1.04 -> 0.98 ms) and loses
+                // on the sparse quad operators (4.97 -> 5.36 ms), so it is used only when it really halves the row length
+                const bool force = ev && atoi(ev) == 2;
+                if (force || 10 * rounds <= 6 * width) {
+                    ctx->sym_rounds = rounds;
+                    if ((rc = dev_upload(ctx, &ctx->sym_dst, sd))) return rc;
+                    if ((rc = dev_upload(ctx, &ctx->sym_c, sc))) return rc;
+                }
+            }
+        }
         if ((rc = dev_upload(ctx, &ctx->qp_cnt, cnt))) return rc;
         if ((rc = dev_upload(ctx, &ctx->qp_col, col))) return rc;
         if ((rc = dev_upload(ctx, &ctx->qp_c, c))) return rc;

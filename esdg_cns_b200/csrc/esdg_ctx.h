@@ -81,6 +81,9 @@ struct esdg_ctx {
     int *qp_cnt = nullptr, *qp_col = nullptr;
     double* qp_c = nullptr;
     int qp_width = 0;
+    int sym_rounds = 0;              // symmetric pair schedule (device_tables.h); 0 = row-wise
+    int* sym_dst = nullptr;
+    double* sym_c = nullptr;
     double* wq = nullptr;
     double* geo = nullptr;
     double *geoG = nullptr, *geoJ = nullptr, *geoN = nullptr;   // curved hexes (desc.affine = 0)

@@ -451,7 +451,9 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_rhs(const __gr
 #pragma unroll
         for (int f = 0; f < 3; ++f) c.Jx[(eb * 4 + 1 + f) * Nfq + k] = fma(Je, pen[f], sv[f]);
     }
-    // flux differencing: one hybridized row per item (row form of the symmetric loop :326-347)
+    // flux differencing (:326-347): symmetric schedule (kernels_generic.cuh: hadamard_sym) or one hybridized row per item
+    if (p.sym_rounds > 0) hadamard_sym<2>(p, s, e0, nb);
+    else
     for (int i = tid; i < nb * p.Nh; i += nt) {
         const int eb = i / p.Nh, r = i - eb * p.Nh;
         const long long e = e0 + eb;

@@ -207,6 +207,85 @@ __device__ __forceinline__ void project_batch(const GenericParams& p, GenericSme
     __syncthreads();
 }
 
+// Phase 4, symmetric form (the loop of CompressibleNS/dg2D_CNS_cavity_optimized.jl:326-347): the hybridized
+// operators are skew and the two-point flux is symmetric, so pair {i,j} contributes +c.F(i,j) to row i and
+// -c.F(i,j) to row j.  One thread per hybridized row; in every round of the host-built schedule a thread evaluates at
+// most one pair, keeps its own contribution in registers and subtracts the partner's from the partner's slot of
+// s.QF -- no two threads address the same slot in a round, so plain read-modify-write with a barrier per round is
+// race-free and the summation order is fixed (bitwise reproducible).  Halves the flux evaluations of the row-wise form.
+template <int DIM>
+__device__ __forceinline__ void hadamard_sym(const GenericParams& p, GenericSmem<DIM>& s, long long e0, int nb) {
+    constexpr int NF = DIM + 2;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < nb * NF * p.Nh; i += nt) s.QF[i] = 0.0;
+    __syncthreads();
+    const bool act = tid < nb * p.Nh;
+    const int eb = act ? tid / p.Nh : 0, r = act ? tid - eb * p.Nh : 0;
+    const long long e = e0 + eb;
+    const double* w = s.W + (size_t)eb * (NF + 2) * p.Nh;
+    Prim<DIM> Pi;
+    Pi.rho = w[r];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) Pi.vel[d] = w[(1 + d) * p.Nh + r];
+    Pi.beta = w[(1 + DIM) * p.Nh + r];
+    Pi.lrho = w[(2 + DIM) * p.Nh + r];
+    Pi.lbeta = w[(3 + DIM) * p.Nh + r];
+    double acc[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) acc[f] = 0.0;
+    double Gr[DIM * DIM];
+    {
+        const double* G = p.geo + e * p.geo_stride;
+#pragma unroll
+        for (int q = 0; q < DIM * DIM; ++q) Gr[q] = G[q];
+    }
+    const bool curved = DIM == 3 && p.curved;
+    const double* Ge = curved ? p.geoG + (size_t)e * (DIM * DIM) * p.Nh : nullptr;
+    double Gi[DIM * DIM];
+    if (curved) {
+#pragma unroll
+        for (int q = 0; q < DIM * DIM; ++q) Gi[q] = Ge[q * p.Nh + r];
+    }
+    double* qf = s.QF + (size_t)eb * NF * p.Nh;
+    for (int t = 0; t < p.sym_rounds; ++t) {
+        const int j = act ? p.sym_dst[t * p.Nh + r] : -1;
+        if (j >= 0) {
+            const double* cq = p.sym_c + (size_t)(t * p.Nh + r) * 3;
+            if (curved) {
+#pragma unroll
+                for (int q = 0; q < DIM * DIM; ++q) Gr[q] = .5 * (Gi[q] + Ge[q * p.Nh + j]);
+            }
+            double c[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+                double a = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < DIM; ++kk) a = fma(Gr[d * DIM + kk], cq[kk], a);
+                c[d] = a;
+            }
+            Prim<DIM> Pj;
+            Pj.rho = w[j];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) Pj.vel[d] = w[(1 + d) * p.Nh + j];
+            Pj.beta = w[(1 + DIM) * p.Nh + j];
+            Pj.lrho = w[(2 + DIM) * p.Nh + j];
+            Pj.lbeta = w[(3 + DIM) * p.Nh + j];
+            double F[NF];
+            ec_flux_dot<DIM>(Pi, Pj, c, p.igm1x2, F);
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                acc[f] += F[f];
+                qf[f * p.Nh + j] -= F[f];
+            }
+        }
+        __syncthreads();
+    }
+    if (act) {
+#pragma unroll
+        for (int f = 0; f < NF; ++f) qf[f * p.Nh + r] += acc[f];
+    }
+}
+
 // Kernel A: face traces of the (projected) conservative variables.
 template <int DIM>
 __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_traces(const __grid_constant__ GenericParams pin) {
@@ -296,7 +375,9 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_rhs(const 
         for (int f = 0; f < NF; ++f) s.Fl[(eb * NF + f) * p.Nfq + k] = F[f];
     }
 
-    // phase 4: Hadamard sum, one hybridized row per item
+    // phase 4: Hadamard sum -- symmetric schedule when the host built one, else one hybridized row per item
+    if (p.sym_rounds > 0) hadamard_sym<DIM>(p, s, e0, nb);
+    else
     for (int i = tid; i < nb * p.Nh; i += nt) {
         const int eb = i / p.Nh, r = i - eb * p.Nh;
         const long long e = e0 + eb;
