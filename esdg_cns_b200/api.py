@@ -120,6 +120,13 @@ class Solver:
             if getattr(cns, "mapB", None) is not None:
                 mb = np.ascontiguousarray(np.asarray(cns.mapB, dtype=np.int64) + shift)
                 self._ck(lib.esdg_set_boundary_nodes(self._ctx, mb.ctypes.data, mb.size))
+            if getattr(cns, "inflow", None) is not None:
+                # shock-tube node sets `leftwall` / `rightwall` and the inflow state (dg2D_CNS_modalESDG.jl:161-218)
+                fin = np.ascontiguousarray(np.asarray(cns.inflow, dtype=np.int64) + shift)
+                fout = np.ascontiguousarray(np.asarray(cns.outflow, dtype=np.int64) + shift)
+                st = np.ascontiguousarray(np.asarray(cns.inflow_state, dtype=np.float64))
+                self._ck(lib.esdg_set_inflow_outflow_bc(self._ctx, fin.ctypes.data, fin.size, st.ctypes.data,
+                                                        fout.ctypes.data, fout.size))
         self._ck(lib.esdg_finalize(self._ctx))
 
     # -- helpers ---------------------------------------------------------------

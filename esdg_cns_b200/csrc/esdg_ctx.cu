@@ -100,6 +100,19 @@ void fill_cns(esdg_ctx* ctx, CnsParams& P, const double* Qsrc) {
     P.dPq = c.dPq; P.dVf = c.dVf; P.dDr = c.dDr; P.dDs = c.dDs;
     P.bc = c.bc;
     P.vlid = c.vlid_dev;
+    {
+        const double g = ctx->d.gamma, rho = c.inflow_state[0], u = c.inflow_state[1], v = c.inflow_state[2], pr = c.inflow_state[3];
+        const double beta = rho / (2.0 * pr);
+        P.in_prim[0] = rho; P.in_prim[1] = u; P.in_prim[2] = v; P.in_prim[3] = beta;
+        P.in_prim[4] = std::log(rho); P.in_prim[5] = std::log(beta);
+        // v_ufun (euler_variables.jl:79-92)
+        const double rhoe = pr / (g - 1.0), E = rhoe + .5 * rho * (u * u + v * v);
+        const double sU = std::log((g - 1.0) * rhoe / std::pow(rho, g));
+        P.in_v[0] = (-E + rhoe * (g + 1.0 - sU)) / rhoe;
+        P.in_v[1] = rho * u / rhoe;
+        P.in_v[2] = rho * v / rhoe;
+        P.in_v[3] = -rho / rhoe;
+    }
     P.bctype = c.bctype;
     P.viscous_dissp = c.viscous_dissp;
     P.lam = -c.lambda;                                  // `let lambda=-lambda` (dg2D_CNS_cavity_optimized.jl:614)
@@ -368,6 +381,22 @@ int esdg_set_wall_bc(esdg_ctx* ctx, int bctype, const int64_t* wall_idx, int64_t
     return ESDG_OK;
 }
 
+int esdg_set_inflow_outflow_bc(esdg_ctx* ctx, const int64_t* inflow_idx, int64_t n_in, const double* state, const int64_t* outflow_idx,
+                               int64_t n_out) {
+    if (!ctx) return ESDG_EINVAL;
+    if (n_in < 0 || n_out < 0 || (n_in > 0 && (!inflow_idx || !state)) || (n_out > 0 && !outflow_idx))
+        return fail(ctx, ESDG_EINVAL, "esdg_set_inflow_outflow_bc: bad argument");
+    if (ctx->finalized) return fail(ctx, ESDG_EINVAL, "esdg_set_inflow_outflow_bc: call before esdg_finalize");
+    CnsState& c = ctx->cns;
+    if (n_in > 0) {
+        if (!(state[0] > 0.0) || !(state[3] > 0.0)) return fail(ctx, ESDG_EINVAL, "esdg_set_inflow_outflow_bc: inflow density and pressure must be positive");
+        for (int k = 0; k < 4; ++k) c.inflow_state[k] = state[k];
+    }
+    c.inflow.assign(inflow_idx, inflow_idx + n_in);
+    c.outflow.assign(outflow_idx, outflow_idx + n_out);
+    return ESDG_OK;
+}
+
 int esdg_set_boundary_nodes(esdg_ctx* ctx, const int64_t* mapB, int64_t nB) {
     if (!ctx || nB < 0 || (nB > 0 && !mapB)) return fail(ctx, ESDG_EINVAL, "esdg_set_boundary_nodes: bad argument");
     ctx->cns.mapB.assign(mapB, mapB + nB);
@@ -399,25 +428,26 @@ static int finalize_cns(esdg_ctx* ctx) {
         for (int64_t v1 : idx) {
             const int64_t v = v1 - 1;
             if (v < 0 || v >= ntr) return false;
-            if (exclusive && (bc[(size_t)v] & 3)) return false;
+            if (exclusive && (bc[(size_t)v] & 7)) return false;
             bc[(size_t)v] |= bits;
         }
         return true;
     };
-    if (!mark(c.wall, 1, true) || !mark(c.lid, 2, true))
-        return fail(ctx, ESDG_EINVAL, "esdg_finalize: wall/lid index out of range or listed twice");
+    if (!mark(c.wall, 1, true) || !mark(c.lid, 2, true) || !mark(c.inflow, 3, true) || !mark(c.outflow, 4, true))
+        return fail(ctx, ESDG_EINVAL, "esdg_finalize: wall/lid/inflow/outflow index out of range or listed twice");
     if (!c.lid.empty()) {
         vl.assign((size_t)ntr, 0.0);
         for (size_t i = 0; i < c.lid.size(); ++i) vl[(size_t)(c.lid[i] - 1)] = c.vlid[i];
     }
     if (c.have_mapB) {
-        if (!mark(c.mapB, 4, false)) return fail(ctx, ESDG_EINVAL, "esdg_finalize: mapB index out of range");
+        if (!mark(c.mapB, 8, false)) return fail(ctx, ESDG_EINVAL, "esdg_finalize: mapB index out of range");
     } else {
-        for (auto& b : bc) if (b & 3) b |= 4;           // default: md.mapB = wall + lid (cavity, :139-147)
+        for (auto& b : bc) if ((b & 7) == 1 || (b & 7) == 2) b |= 8;   // default: md.mapB = wall + lid (cavity, :139-147)
     }
-    // a wall/lid node must be a boundary node of the mesh: mapP == mapM there (SetupDG.jl:294-298)
+    // a wall/lid node must be a boundary node of the mesh: mapP == mapM there (SetupDG.jl:294-298); inflow / outflow
+    // nodes may be connected to anything (the shock-tube script makes the box periodic first)
     for (int64_t i = 0; i < ntr; ++i)
-        if ((bc[(size_t)i] & 3) && ctx->mapP_host[(size_t)i] - 1 != i)
+        if (((bc[(size_t)i] & 7) == 1 || (bc[(size_t)i] & 7) == 2) && ctx->mapP_host[(size_t)i] - 1 != i)
             return fail(ctx, ESDG_EINVAL, "esdg_finalize: wall/lid node is not a boundary node (mapP != mapM)");
     if ((rc = dev_upload(ctx, &c.bc, bc))) return rc;
     if (!vl.empty() && (rc = dev_upload(ctx, &c.vlid_dev, vl))) return rc;
@@ -758,7 +788,7 @@ int esdg_finalize(esdg_ctx* ctx) {
     CK(cudaMemset(ctx->rhstest_dev, 0, 2 * sizeof(double)));
     if (ctx->cns.on) {
         if ((rc = finalize_cns(ctx))) return rc;
-    } else if (!ctx->cns.wall.empty() || !ctx->cns.lid.empty()) {
+    } else if (!ctx->cns.wall.empty() || !ctx->cns.lid.empty() || !ctx->cns.inflow.empty() || !ctx->cns.outflow.empty()) {
         return fail(ctx, ESDG_EINVAL, "esdg_finalize: wall BCs need the CNS path (call esdg_set_viscosity; mu = 0 gives Euler with walls)");
     }
     if (!ctx->cns.on && (rc = hexfast_try_create(ctx))) return rc;

@@ -36,6 +36,8 @@ struct CnsState {
     int viscous_dissp = 0, bctype = 1;
     std::vector<int64_t> wall, lid, mapB; // 1-based linear indices into Nfq x K (Julia)
     std::vector<double> vlid;
+    std::vector<int64_t> inflow, outflow; // shock-tube boundary nodes (dg2D_CNS_modalESDG.jl:165-166)
+    double inflow_state[4] = {1, 0, 0, 1}; // rho, u, v, p of the inflow
     bool have_mapB = false;
     DevEll Pq, Vf, Dr, Ds;
     esdg::Dense dPq{}, dVf{}, dDr{}, dDs{};

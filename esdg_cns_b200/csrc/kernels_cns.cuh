@@ -28,7 +28,9 @@ struct CnsParams {
     GenericParams g;
     Ell Pq, Vf, Dr, Ds;          // Np x Nq, Nfq x Np, Np x Np, Np x Np
     Dense dPq, dVf, dDr, dDs;    // the same, dense + padded for the tensor-core GEMMs
-    const unsigned char* bc;     // [Nfq*K] bits 0-1: 0 interior, 1 wall, 2 lid ; bit 2: member of md.mapB
+    const unsigned char* bc;     // [Nfq*K] bits 0-2: 0 interior, 1 wall, 2 lid, 3 inflow, 4 outflow ; bit 3: member of md.mapB
+    double in_prim[6];           // inflow state: rho, u, v, beta, log rho, log beta   (dg2D_CNS_modalESDG.jl:172-175)
+    double in_v[4];              // its entropy variables v_ufun(rhoL, rhoL uL, rhoL vL, EL)  (:191-197)
     const double* vlid;          // [Nfq*K] lid speed (read only where kind == 2) or nullptr
     int bctype;                  // 1 adiabatic no-slip, 2 isothermal, 3 slip   (:27)
     int viscous_dissp;           // :30
@@ -219,9 +221,16 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_sigma(const __
             for (int f = 0; f < 4; ++f) VP[f] = p.traces[f * p.trace_stride + ip];
         }
         const int code = P.bc[self];
-        if (code & 3) {
+        const int kind = code & 7;
+        if (kind == 1 || kind == 2) {
             const double isJ = fast_rcp(sJ);
-            bc_entropy_vars(P, code & 3, (code & 3) == 2 ? P.vlid[self] : 0.0, nxJ * isJ, nyJ * isJ, Vf, VP);
+            bc_entropy_vars(P, kind, kind == 2 ? P.vlid[self] : 0.0, nxJ * isJ, nyJ * isJ, Vf, VP);
+        } else if (kind == 3) {            // inflow: entropy variables of the prescribed state (dg2D_CNS_modalESDG.jl:191-197)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) VP[f] = P.in_v[f];
+        } else if (kind == 4) {            // outflow: exterior = interior (:199-202)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) VP[f] = Vf[f];
         }
         c.Jx[(eb * 4) * Nfq + k] = 0.0;
         c.Jy[(eb * 4) * Nfq + k] = 0.0;
@@ -374,7 +383,7 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_rhs(const __gr
         const long long self = e * Nfq + k;
         const long long ip = p.mapP[self];
         const int code = P.bc[self];
-        const int kind = code & 3;
+        const int kind = code & 7;
         const double vlid = kind == 2 ? P.vlid[self] : 0.0;
         double UM[NF], UP[NF], VM[NF], VPv[NF];
         Prim<2> PM, PP;
@@ -396,16 +405,21 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_rhs(const __gr
             u_of_v<2>(VPv, p.gamma, p.lg1, UP);
             prim_of_u<2>(UP, p.gamma, PP);
         }
-        if (kind) {
+        if (kind == 1 || kind == 2) {
             // impose_BCs_inviscid! (:157-176): rho+ = rho, beta+ = beta, u+ = u - 2 (u.n) n
             const double Un = PM.vel[0] * nx + PM.vel[1] * ny;
             PP.rho = PM.rho; PP.beta = PM.beta; PP.lrho = PM.lrho; PP.lbeta = PM.lbeta;
             PP.vel[0] = PM.vel[0] - 2 * Un * nx;
             PP.vel[1] = PM.vel[1] - 2 * Un * ny;
+        } else if (kind == 3) {            // shock-tube inflow: prescribed primitive state (dg2D_CNS_modalESDG.jl:172-175)
+            PP.rho = P.in_prim[0]; PP.vel[0] = P.in_prim[1]; PP.vel[1] = P.in_prim[2];
+            PP.beta = P.in_prim[3]; PP.lrho = P.in_prim[4]; PP.lbeta = P.in_prim[5];
+        } else if (kind == 4) {            // outflow: exterior = interior (:177-180)
+            PP = PM;
         }
         double F[NF];
         ec_flux_dot<2>(PP, PM, nJ, p.igm1x2, F);          // update_flux! evaluates (QP, QM) (:311)
-        if (p.lf_scale != 0.0) {
+        if (p.lf_scale != 0.0 && kind < 3) {   // impose_BCs_lam! zeroes the penalty at inflow / outflow nodes (:183-188)
             const double unM = (UM[1] * nJ[0] + UM[2] * nJ[1]) * isJ;
             const double unP = (UP[1] * nJ[0] + UP[2] * nJ[1]) * isJ;
             const double lamM = wavespeed_1d(UM[0], unM, UM[3], p.gamma);
@@ -425,19 +439,30 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_rhs(const __gr
             sxP[f] = P.sig_tr[f * p.trace_stride + ip];
             syP[f] = P.sig_tr[(3 + f) * p.trace_stride + ip];
         }
-        if (kind) bc_stress(P, kind, vlid, nx, ny, sxf, syf, sxP, syP);
+        if (kind == 1 || kind == 2) bc_stress(P, kind, vlid, nx, ny, sxf, syf, sxP, syP);
+        else if (kind >= 3) {              // sigma+ = sigma on `vwall` (dg2D_CNS_modalESDG.jl:205-215)
+#pragma unroll
+            for (int f = 0; f < 3; ++f) { sxP[f] = sxf[f]; syP[f] = syf[f]; }
+        }
         // viscous face term of this point: surf + J * pen, so that (vol + LIFT surf)/J + LIFT pen (:843-846) is one lift
         double sv[3], pen[3] = {0.0, 0.0, 0.0};
 #pragma unroll
         for (int f = 0; f < 3; ++f) sv[f] = .5 * ((sxP[f] - sxf[f]) * nJ[0] + (syP[f] - syf[f]) * nJ[1]);
         // penalisation tau*[[v]] (:817-840)
         if (P.viscous_dissp) {
-            if (kind) bc_entropy_vars(P, kind, vlid, nx, ny, VM, VPv);
+            if (kind == 1 || kind == 2) bc_entropy_vars(P, kind, vlid, nx, ny, VM, VPv);
+            else if (kind == 3) {
+#pragma unroll
+                for (int f = 0; f < 4; ++f) VPv[f] = P.in_v[f];
+            } else if (kind == 4) {
+#pragma unroll
+                for (int f = 0; f < 4; ++f) VPv[f] = VM[f];
+            }
             const double iv4 = fast_rcp(VM[3]);
             const double tau = -iv4 / P.Re;
             const double d1 = VPv[1] - VM[1], d2 = VPv[2] - VM[2], d3 = VPv[3] - VM[3];
             double p3 = tau * d3;
-            if (code & 4) {
+            if (code & 8) {
                 const double a1 = .5 * (VPv[1] + VM[1]), a2 = .5 * (VPv[2] + VM[2]);
                 p3 = P.bctype == 1 ? -tau * (a1 * d1 + a2 * d2) * iv4
                                    : -tau * (a1 * d1 + a2 * d2 + d3 * d3 * .5) * iv4;

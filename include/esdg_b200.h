@@ -115,6 +115,14 @@ int esdg_set_viscosity(esdg_ctx* ctx, double lambda, double mu, double Pr, doubl
  * (:218-262) are applied at these nodes. */
 int esdg_set_wall_bc(esdg_ctx* ctx, int bctype, const int64_t* wall_idx, int64_t nwall, const int64_t* lid_idx,
                      const double* vlid, int64_t nlid);
+/* Inflow / outflow nodes of the viscous shock tube (examples/CompressibleNS/dg2D_CNS_modalESDG.jl, init_BC_funs
+ * :161-218).  inflow_idx = `leftwall`: exterior primitive state fixed to state = (rho, u, v, p) (:172-175), exterior
+ * entropy variables v_ufun of it (:191-197).  outflow_idx = `rightwall`: exterior = interior (:177-180, :199-202).
+ * On both sets the Lax-Friedrichs coefficient is zero (impose_BCs_lam!, :183-188) and the exterior stress equals the
+ * interior one (:205-215).  1-based linear indices into the Nfq x K face arrays; mapP may connect these nodes to
+ * anything (the script makes the box periodic first, :80-86).  Can be combined with esdg_set_wall_bc. */
+int esdg_set_inflow_outflow_bc(esdg_ctx* ctx, const int64_t* inflow_idx, int64_t n_in, const double* state /* [4] */,
+                               const int64_t* outflow_idx, int64_t n_out);
 /* md.mapB (src/node_map_functions.jl:53): nodes where the penalisation switches to its wall form
  * (:829-839).  Default when not called: wall + lid. */
 int esdg_set_boundary_nodes(esdg_ctx* ctx, const int64_t* mapB, int64_t nB);

@@ -76,6 +76,12 @@ def impose_BCs_inviscid(QP, Qf, bc):  # :157-176
     QP[3][b] = Qf[3][b]
     QP[1][b] = Qf[1][b] - 2 * Un * bc.nx
     QP[2][b] = Qf[2][b] - 2 * Un * bc.ny
+    if getattr(bc, "inflow", None) is not None:             # dg2D_CNS_modalESDG.jl:171-181
+        rho, u, v, p = bc.inflow_state
+        i, o = bc.inflow, bc.outflow
+        QP[0][i], QP[1][i], QP[2][i], QP[3][i] = rho, u, v, rho / (2 * p)
+        for k in range(4):
+            QP[k][o] = Qf[k][o]
     return QP
 
 
@@ -99,6 +105,13 @@ def impose_BCs_entropyvars(VUP, VUf, bc, bctype):  # :178-216
         VUP[3][b] = VUf[3][b]
         VUP[1][b] = VUf[1][b] - 2 * VUn * bc.nx
         VUP[2][b] = VUf[2][b] - 2 * VUn * bc.ny
+    if getattr(bc, "inflow", None) is not None:             # dg2D_CNS_modalESDG.jl:190-203
+        rho, u, v, p = bc.inflow_state
+        E = p / (GAMMA - 1) + .5 * rho * (u * u + v * v)
+        VL = P.v_of_u((np.array([rho]), np.array([rho * u]), np.array([rho * v]), np.array([E])))
+        for k in range(4):
+            VUP[k][bc.inflow] = VL[k][0]
+            VUP[k][bc.outflow] = VUf[k][bc.outflow]
     return VUP
 
 
@@ -123,6 +136,10 @@ def impose_BCs_stress(sxP, syP, sxf, syf, bc, bctype):  # :218-262
         sxP[2][b] = -sxf[2][b] + 2 * bc.ny * snx
         syP[2][b] = -syf[2][b] + 2 * bc.ny * sny
         sxP[3][b], syP[3][b] = -sxf[3][b], -syf[3][b]
+    if getattr(bc, "inflow", None) is not None:             # dg2D_CNS_modalESDG.jl:205-215: sigma+ = sigma on `vwall`
+        vw = np.concatenate([bc.inflow, bc.outflow])
+        for k in range(4):
+            sxP[k][vw], syP[k][vw] = sxf[k][vw], syf[k][vw]
     return sxP, syP
 
 
@@ -140,7 +157,14 @@ def rhs_inviscid(Q, md, ops, bc, inviscid_dissp=True):
     Uf = tuple(u[Nq:, :] for u in Uh)
     rhoUn = (Uf[1] * md.nxJ + Uf[2] * md.nyJ) / md.sJ
     lam = np.abs(np.sqrt(np.abs(rhoUn / Uf[0])) + np.sqrt(1.4 * 0.4 * (Uf[3] - .5 * rhoUn ** 2 / Uf[0]) / Uf[0]))
-    LFc = .25 * np.maximum(lam, _gather(lam, md.mapP)) * md.sJ
+    lamP = _gather(lam, md.mapP)
+    if getattr(bc, "inflow", None) is not None:             # impose_BCs_lam! (dg2D_CNS_modalESDG.jl:183-188, :320-323)
+        vw = np.concatenate([bc.inflow, bc.outflow])
+        lam_f, lamP_f = _flat(lam).copy(), _flat(lamP).copy()
+        lam_f[vw] = 0.0
+        lamP_f[vw] = 0.0
+        lam, lamP = lam_f.reshape(shape_f, order="F"), lamP_f.reshape(shape_f, order="F")
+    LFc = .25 * np.maximum(lam, lamP) * md.sJ
     UP = tuple(_gather(u, md.mapP) for u in Uf)
     fx, fy = P.euler_fluxes_2d(tuple(QP), QM)                 # update_flux! evaluates (QP, QM)  (:311)
     rhsQ = []
@@ -357,3 +381,92 @@ def dopri45(Q, rhs_fun, T, dt, err_tol=1e-5, max_attempts=10 ** 9):
         hist["t"].append(t); hist["dt"].append(dt); hist["err"].append(err)
         hist["rhstest"].append(rt); hist["rhstest_visc"].append(rtv); hist["accepted"].append(bool(ok))
     return Q, hist
+
+
+# ---------------------------------------------------------------- viscous shock tube (Becker)
+# examples/CompressibleNS/dg2D_CNS_modalESDG.jl: parameters :31-58, mesh :70-86, BCs :161-218,
+# exact solution :545-578.
+def shocktube_params(viscous_dissp=False):
+    g = GAMMA
+    M0, mu, v_inf, m0, v0 = 3.0, 0.01, 0.2, 1.0, 1.0
+    pr = SimpleNamespace(Re=10000.0, mu=mu, lam=2 / 3 * mu, Pr=3 / 4, bctype=1, inviscid_dissp=True,
+                         viscous_dissp=viscous_dissp, M0=M0, v_inf=v_inf, m0=m0, v0=v0)
+    pr.v1 = (g - 1 + 2 / M0 ** 2) / (g + 1)
+    pr.v01 = np.sqrt(v0 * pr.v1)
+    pr.kappa = mu * (g / (g - 1)) / pr.Pr
+    pr.cv = 1 / (g - 1)
+    uL, uR = v0 + v_inf, pr.v1 + v_inf
+    rhoL, rhoR = m0 / v0, m0 / pr.v1
+    eL = 1 / (2 * g) * ((g + 1) / (g - 1) * pr.v01 ** 2 - v0 ** 2)
+    eR = 1 / (2 * g) * ((g + 1) / (g - 1) * pr.v01 ** 2 - pr.v1 ** 2)
+    pr.left = (rhoL, uL, 0.0, (g - 1) * rhoL * eL)        # rho, u, v, p
+    pr.right = (rhoR, uR, 0.0, (g - 1) * rhoR * eR)
+    return pr
+
+
+def becker_velocity(x, pr, max_iter=100, tol=1e-14):
+    """``bisection_solve_velocity`` (:545-567), vectorised over x."""
+    g = GAMMA
+    x = np.asarray(x, dtype=float)
+    Lk = pr.kappa / pr.m0 / pr.cv
+    v0, v1, v01 = pr.v0, pr.v1, pr.v01
+
+    def f(v):
+        return -x + 2 * Lk / (g + 1) * (v0 / (v0 - v1) * np.log((v0 - v) / (v0 - v01)) - v1 / (v0 - v1) * np.log((v - v1) / (v01 - v1)))
+    vL = np.full(x.shape, v1)
+    vR = np.full(x.shape, v0)
+    vn = .5 * (vL + vR)
+    done = np.zeros(x.shape, dtype=bool)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for _ in range(max_iter):
+            vn = np.where(done, vn, .5 * (vL + vR))
+            fn = f(vn)
+            done |= np.abs(fn) < tol
+            same = np.sign(f(vL)) == np.sign(fn)
+            vL = np.where(~done & same, vn, vL)
+            vR = np.where(~done & ~same, vn, vR)
+    return vn
+
+
+def becker_exact(x, t, pr):
+    """``exact_sol_viscous_shocktube`` (:573-578): conservative state of the travelling viscous shock."""
+    g = GAMMA
+    u = becker_velocity(x - pr.v_inf * t, pr)
+    rho = pr.m0 / u
+    e = 1 / (2 * g) * ((g + 1) / (g - 1) * pr.v01 ** 2 - u ** 2)
+    return [rho, rho * (pr.v_inf + u), np.zeros_like(rho), rho * (e + .5 * (pr.v_inf + u) ** 2)]
+
+
+def shocktube_bc_sets(md, pr):
+    """``leftwall`` (inflow) / ``rightwall`` (outflow) of init_BC_funs (:161-169) on [-1/2, 1] x [0, 1]; the mesh is
+    made periodic first (:80-86), the top / bottom walls stay periodic."""
+    xb = md.xf.flatten(order="F")[md.mapB]
+    bc = SimpleNamespace()
+    bc.inflow = md.mapB[np.abs(xb + .5) < 1e-12]
+    bc.outflow = md.mapB[np.abs(xb - 1.0) < 1e-12]
+    bc.inflow_state = pr.left
+    e = np.zeros(0, dtype=np.int64)
+    bc.wall, bc.lid, bc.boundary, bc.vlid, bc.nx, bc.ny = e, e, e, np.zeros(0), np.zeros(0), np.zeros(0)
+    bc.mapB = e                                            # penalisation: interior form everywhere (the script's is commented out)
+    return bc
+
+
+def setup_shocktube(elem="tri", N=2, K1D=8):
+    """Mesh, operators, BC sets and the exact initial state of the Becker shock tube (:20-30, :70-117, :580-581)."""
+    pr = shocktube_params()
+    if elem == "tri":
+        VX, VY, EToV = M.uniform_tri_mesh(K1D // 2 * 3, K1D)
+        rd = S.init_reference_tri(N)
+    else:
+        VX, VY, EToV = M.uniform_quad_mesh(K1D // 2 * 3, K1D)
+        rd = S.init_reference_quad(N)
+    VX = VX / 4 * 3 + 1 / 4
+    VY = (VY + 1) / 2
+    md = S.init_mesh((VX, VY), EToV, rd)
+    bc = shocktube_bc_sets(md, pr)                         # node sets from the ORIGINAL mapB, before the periodic patch
+    S.make_periodic(md, rd, (VX.max() - VX.min(), VY.max() - VY.min()))
+    ops = build_cns_ops(rd)
+    for name in ("rxJ", "sxJ", "ryJ", "syJ"):
+        setattr(md, name, ops.Vh @ getattr(md, name))
+    Q = becker_exact(md.x, 0.0, pr)
+    return rd, md, ops, bc, Q, pr

@@ -260,3 +260,64 @@ def test_cns_slabs_with_halo_exchange_match_single_context(nslabs, periodic):
     # a stage without the sigma pass is refused
     with pytest.raises(Exception):
         sol[0].stage_update(0, dt, False, 0)
+
+
+def _shocktube_settings(pr, bc):
+    return SimpleNamespace(Re=pr.Re, mu=pr.mu, lam=pr.lam, Pr=pr.Pr, bctype=1, inviscid_dissp=True,
+                           viscous_dissp=pr.viscous_dissp, wall=bc.wall, lid=bc.lid, vlid=bc.vlid, mapB=bc.mapB,
+                           inflow=bc.inflow, outflow=bc.outflow, inflow_state=bc.inflow_state)
+
+
+@pytest.mark.parametrize("elem,N,K1D", [("tri", 2, 8), ("tri", 3, 4), ("quad", 3, 4)])
+@pytest.mark.parametrize("viscous_dissp", [False, True])
+def test_shocktube_rhs_matches_oracle(elem, N, K1D, viscous_dissp):
+    """inflow / outflow BCs of the viscous shock tube (dg2D_CNS_modalESDG.jl:161-218) on the
+    Becker profile; the script itself runs with viscous_dissp = false."""
+    from oracle import cns
+    from esdg_cns_b200 import api
+    rd, md, ops, bc, Q, pr = cns.setup_shocktube(elem, N, K1D)
+    pr.mu, pr.lam = .05, 2 / 3 * .05                          # a profile the small meshes can carry
+    pr.kappa = pr.mu * (1.4 / .4) / pr.Pr
+    pr.viscous_dissp = viscous_dissp
+    Q = cns.becker_exact(md.x, 0.0, pr)
+    # The exact profile has v = 0, so u.n vanishes up to round-off on the horizontal faces and the reference's
+    # sqrt(|u_n|) in `wavespeed` (euler_variables.jl:9, SURVEY H4) turns 1e-17 into 3e-9: the Lax-Friedrichs penalty of
+    # the reference is then defined only to ~1e-9 (measured: 2e-12 with the penalty off, 1e-9 with it on).  A transverse
+    # velocity keeps the comparison away from that square-root singularity; the boundary treatment is what is tested.
+    vt = .1 * (1 + .3 * np.sin(2 * np.pi * md.y))
+    Q[3] = Q[3] + .5 * Q[0] * vt ** 2
+    Q[2] = Q[0] * vt
+    ref, rt_ref, rtv_ref = cns.rhsRK(Q, md, ops, bc, pr)
+    s = api.Solver(md, ops, cns=_shocktube_settings(pr, bc))
+    out, rt, rtv = s.rhs(Q, True)
+    tol = parity_tol(lambda: cns.rhsRK(Q, md, ops, bc, pr)[0], ref)
+    err = relerr(out, ref)
+    print(f"shock tube {elem} N={N} K1D={K1D} dissp={viscous_dissp}: relerr {err:.2e} tol {tol:.2e}; rhstest {rt:.6e} vs {rt_ref:.6e}; "
+          f"visc {rtv:.3e} vs {rtv_ref:.3e}")
+    assert err < tol
+    assert abs(rt - rt_ref) < 1e-10 * max(1.0, abs(rt_ref)) and abs(rtv - rtv_ref) < 1e-10 * max(1.0, abs(rtv_ref))
+
+
+def test_shocktube_tracks_the_becker_solution():
+    """The reference experiment at reduced size: start from the exact travelling viscous shock, integrate with the
+    script's DOPRI45 loop, compare with exact_sol_viscous_shocktube(x, T) in the L2 norm (dg2D_CNS_modalESDG.jl:745-774)."""
+    from oracle import cns
+    from esdg_cns_b200 import api
+    errs = []
+    for K1D in (8, 16):
+        rd, md, ops, bc, Q, pr = cns.setup_shocktube("tri", 3, K1D)
+        pr.mu, pr.lam = .02, 2 / 3 * .02
+        pr.kappa = pr.mu * (1.4 / .4) / pr.Pr
+        Q = cns.becker_exact(md.x, 0.0, pr)
+        s = api.Solver(md, ops, cns=_shocktube_settings(pr, bc))
+        s.upload(Q)
+        T = .05
+        hist = s.dopri45(T, dt=1e-4, err_tol=1e-6)
+        Q1 = s.download()
+        Qe = cns.becker_exact(md.x, hist["t"][-1], pr)
+        num = np.sqrt(sum(np.sum(md.wJq * (ops.Vq @ (a - b)) ** 2) for a, b in zip(Q1, Qe)))
+        den = np.sqrt(sum(np.sum(md.wJq * (ops.Vq @ b) ** 2) for b in Qe))
+        errs.append(num / den)
+        print(f"shock tube K1D={K1D}: t={hist['t'][-1]:.4f} after {len(hist['accepted'])} attempts, L2 error vs Becker {num / den:.3e}")
+        assert all(np.isfinite(q).all() for q in Q1)
+    assert errs[1] < 5e-3 and errs[1] < .6 * errs[0]

@@ -430,3 +430,29 @@ def test_persistent_line_kernel_is_bitwise_the_one_shot_kernel(monkeypatch):
         s.close()
     assert all(np.array_equal(a, b) for a, b in zip(out[0][0], out[1][0]))
     assert out[0][1] == out[1][1]
+
+
+@pytest.mark.parametrize("case", ["quad", "hex_generic", "curved"])
+def test_symmetric_pair_schedule_matches_row_wise_sum(case, monkeypatch):
+    """ESDG_SYM_PAIRS=2 forces the symmetric schedule (each unordered pair once) on operators where it is not the
+    default; it must agree with the row-wise Hadamard sum to round-off and keep the entropy residual."""
+    from oracle import solvers as SV
+    from esdg_cns_b200 import api
+    if case == "quad":
+        rd, md, ops, Q = SV.setup_quad_vortex(3, 6, 5)
+    elif case == "hex_generic":
+        monkeypatch.setenv("ESDG_FORCE_GENERIC", "1")
+        rd, md, ops, Q = _hex_case(2, 3, "rand", generic_velocity=True)
+    else:
+        rd, md, ops, Q = _curved_case(2, 3)
+    ops.lf_scale = 0.0
+    res = []
+    for flag in ("0", "2"):
+        monkeypatch.setenv("ESDG_SYM_PAIRS", flag)
+        s = api.Solver(md, ops)
+        res.append(s.rhs(Q, True))
+        s.close()
+    err = _relerr(res[1][0], res[0][0])
+    print(f"{case}: symmetric vs row-wise relerr {err:.2e}; rhstest {res[0][1]:.2e} / {res[1][1]:.2e}")
+    assert err < 1e-13
+    assert abs(res[1][1]) < 1e-11

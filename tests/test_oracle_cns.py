@@ -141,3 +141,40 @@ def test_dopri45_coefficients_and_controller():
     for _ in range(n):
         Qr, res, _ = SV.lsrk45_step(Qr, res, T / n, lambda q, w: cns.rhsRK(q, md, ops, bc, par)[:2])
     assert max(np.abs(x - y).max() for x, y in zip(Q1, Qr)) < 1e-5
+
+
+def test_shocktube_becker_solution_is_consistent_with_the_rhs():
+    """Viscous shock tube (dg2D_CNS_modalESDG.jl): the Becker profile travels with v_inf, so the CNS rhs of the exact
+    state must approach its time derivative as the mesh resolves the shock (mu = .02: thickness ~ .04)."""
+    errs = []
+    for K1D in (8, 16, 32):
+        rd, md, ops, bc, Q, pr = cns.setup_shocktube("tri", 3, K1D)
+        pr.mu, pr.lam = .02, 2 / 3 * .02
+        pr.kappa = pr.mu * (1.4 / .4) / pr.Pr
+        Q = cns.becker_exact(md.x, 0.0, pr)
+        r, rt, _ = cns.rhsRK(Q, md, ops, bc, pr)
+        d = 1e-5
+        dQ = [(a - b) / (2 * d) for a, b in zip(cns.becker_exact(md.x, d, pr), cns.becker_exact(md.x, -d, pr))]
+        num = np.sqrt(sum(np.sum(md.wJq * (ops.Vq @ (a - b)) ** 2) for a, b in zip(r, dQ)))
+        den = np.sqrt(sum(np.sum(md.wJq * (ops.Vq @ b) ** 2) for b in dQ))
+        errs.append(num / den)
+        assert rt < 0                                       # entropy is dissipated
+    assert errs[2] < .15 and errs[2] < .5 * errs[1] < .25 * errs[0]
+
+
+def test_shocktube_states_and_node_sets():
+    rd, md, ops, bc, Q, pr = cns.setup_shocktube("tri", 2, 4)
+    # Rankine-Hugoniot: mass, momentum and energy fluxes of the two end states agree in the shock frame
+    (rL, uL, _, pL), (rR, uR, _, pR) = pr.left, pr.right
+    wL, wR = uL - pr.v_inf, uR - pr.v_inf
+    assert abs(rL * wL - rR * wR) < 1e-14
+    assert abs(rL * wL ** 2 + pL - rR * wR ** 2 - pR) < 1e-14
+    hL, hR = 3.5 * pL / rL + .5 * wL ** 2, 3.5 * pR / rR + .5 * wR ** 2
+    assert abs(hL - hR) < 1e-14
+    xf = md.xf.flatten(order="F")
+    assert np.allclose(xf[bc.inflow], -.5) and np.allclose(xf[bc.outflow], 1.0)
+    assert bc.inflow.size == bc.outflow.size == 4 * 3        # K1D faces x (N+1) points
+    # the exact profile connects the two states
+    Ql = cns.becker_exact(np.array([-.5]), 0.0, pr)
+    Qr = cns.becker_exact(np.array([1.0]), 0.0, pr)
+    assert abs(Ql[0][0] - rL) < 1e-10 and abs(Qr[0][0] - rR) < 1e-10
