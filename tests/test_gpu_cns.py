@@ -321,3 +321,21 @@ def test_shocktube_tracks_the_becker_solution():
         print(f"shock tube K1D={K1D}: t={hist['t'][-1]:.4f} after {len(hist['accepted'])} attempts, L2 error vs Becker {num / den:.3e}")
         assert all(np.isfinite(q).all() for q in Q1)
     assert errs[1] < 5e-3 and errs[1] < .6 * errs[0]
+
+
+def test_convergence_sweep_harness_boundary_error_decreases():
+    """examples/cns_convergence_sweep.py (the harness of dg2D_CNS_convergence_test.jl:841-1088) at reduced size: the weakly
+    imposed no-slip condition converges under p- and h-refinement, and the run stays entropy stable."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("sweep", os.path.join(os.path.dirname(GOLD), "..", "examples", "cns_convergence_sweep.py"))
+    sweep = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sweep)
+    errs = {}
+    for N, K1D in ((1, 8), (2, 8), (3, 8), (2, 16)):
+        e, hist = sweep.run_case(N, K1D, 100.0, T=.2)
+        errs[(N, K1D)] = e
+        print(f"sweep N={N} K1D={K1D}: boundary error {e:.3e}, {len(hist['accepted'])} DOPRI attempts, last rhstest {hist['rhstest'][-1]:.2e}")
+        assert hist["t"][-1] >= .2 and hist["rhstest"][-1] <= 1e-10
+    assert errs[(3, 8)] < errs[(2, 8)] < errs[(1, 8)]
+    assert errs[(2, 16)] < errs[(2, 8)]
