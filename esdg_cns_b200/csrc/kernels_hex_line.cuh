@@ -74,12 +74,18 @@ struct LineDims {
 #ifndef ESDG_LINE_EB5
 #define ESDG_LINE_EB5 2
 #endif
-    static constexpr int EB = n == 5 ? ESDG_LINE_EB5 : (n == 4 ? 2 : (n == 3 ? 4 : 8));
+#ifndef ESDG_LINE_EB4
+#define ESDG_LINE_EB4 2
+#endif
+    static constexpr int EB = n == 5 ? ESDG_LINE_EB5 : (n == 4 ? ESDG_LINE_EB4 : (n == 3 ? 4 : 8));
     static constexpr int THREADS = ((EB * NL + 31) / 32) * 32;
 #ifndef ESDG_LINE_MINB5
 #define ESDG_LINE_MINB5 2
 #endif
-    static constexpr int MINB = (n == 5 && ESDG_LINE_EB5 == 2) ? ESDG_LINE_MINB5 : 4;   // CTAs per SM the register budget is sized for
+#ifndef ESDG_LINE_MINB4
+#define ESDG_LINE_MINB4 4
+#endif
+    static constexpr int MINB = (n == 5 && ESDG_LINE_EB5 == 2) ? ESDG_LINE_MINB5 : (n == 4 ? ESDG_LINE_MINB4 : 4);   // CTAs per SM the register budget is sized for
     static constexpr int EN = EB * Nq, EF = EB * Nfq;
     static constexpr int TAB = 5 * n + EB * 34;
     // WV[7][EN] WF[7][EF] P[7][EF] A[15][EN] Q[5][EN] R[5][EN]
