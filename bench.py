@@ -123,6 +123,7 @@ def run_reference(args):
     x, y, z = SD.hex_node_coords(prd, pmd)
     rho, u, v, w, p = SD.taylor_green(x, y, z)
     Q = SD.primitive_to_conservative(rho, (u, v, w), p)
+    _all_host_threads(c_oracle)
     co = c_oracle.COracle(pmd, pops)
     dt = tgv_dt(N, 128)
     dof = co.nf * co.Nq * co.K
@@ -147,9 +148,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _all_host_threads(c_oracle):
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host thread it can."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    c_oracle.load().esdg_oracle_set_threads(int(n))
+
+
 def cpu_baseline_leg(seconds_budget=25.0):
     from oracle import c_oracle
     from esdg_cns_b200 import setup_dg as SD
+    _all_host_threads(c_oracle)
     N, mesh = N_DEG, CPU_SAMPLE_MESH
     prd, pops = SD.reference_hex(N)
     pmd = SD.uniform_hex_mesh_md(prd, mesh, domain=((-np.pi, np.pi),) * 3)
@@ -185,6 +193,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=device)
     N = N_DEG
     Kx, Ky, Kzl = LOCAL_MESH
@@ -318,7 +328,7 @@ def run_ours(args):
             "gpu_launches": launches, "clocks": clocks,
             "kernels_ms": {k: {"total_ms": v[0], "launches": v[1]} for k, v in ktimes.items() if v[1]},
         }
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:      # reported on rank 0 at N = 1 only
             line["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -42,6 +42,15 @@ typedef struct {
     double lf_scale, volume_scale;
 } oracle_desc;
 
+/* bench.py --impl reference under torchrun inherits OMP_NUM_THREADS=1: let the caller ask for all host threads */
+void esdg_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int esdg_oracle_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -29,6 +29,8 @@ def load(build=True):
             subprocess.check_call(["make", "-C", os.path.join(_HERE, "c")])
         lib = C.CDLL(_SO)
         lib.esdg_oracle_threads.restype = C.c_int
+        lib.esdg_oracle_set_threads.argtypes = [C.c_int]
+        lib.esdg_oracle_set_threads.restype = None
         lib.esdg_oracle_work_doubles.restype = C.c_int64
         lib.esdg_oracle_work_doubles.argtypes = [C.POINTER(oracle_desc)]
         lib.esdg_oracle_rhs.restype = C.c_double
