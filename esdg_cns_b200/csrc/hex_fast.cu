@@ -122,7 +122,7 @@ int set_attrs(esdg_ctx* ctx) {
     h->smem_traces = (size_t)(D::EB * 5 * D::Nq + 2 * n) * sizeof(double);
     if (h->line) {
         h->EB = LD::EB;
-        h->threads = LD::THREADS;
+        h->threads = LD::THREADS_LAUNCH;
         h->smem_stage = (size_t)LD::SMEM_DOUBLES * sizeof(double);
         if (const char* ex = getenv("ESDG_HEX_EXTRA_SMEM_KB")) h->smem_stage += (size_t)atoi(ex) * 1024;   // occupancy experiments
         CK(cudaFuncSetAttribute(k_hex_stage_line<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage));

@@ -68,6 +68,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     } while (!done);
 }
 
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(unsigned long long* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
 template <int n>
 struct LineDims {
     static constexpr int Nq = n * n * n, nfp = n * n, Nfq = 6 * nfp, Nh = Nq + Nfq, NL = 3 * nfp;
@@ -78,7 +85,19 @@ struct LineDims {
 #define ESDG_LINE_EB4 2
 #endif
     static constexpr int EB = n == 5 ? ESDG_LINE_EB5 : (n == 4 ? ESDG_LINE_EB4 : (n == 3 ? 4 : 8));
-    static constexpr int THREADS = ((EB * NL + 31) / 32) * 32;
+    static constexpr int THREADS = ((EB * NL + 31) / 32) * 32;   // line threads
+#ifndef ESDG_LINE_HELPER
+#define ESDG_LINE_HELPER 0
+#endif
+    // N = 3, 4: an odd number of line warps leaves one warp slot of the register file unused (warps are allocated in
+    // pairs); with ESDG_LINE_HELPER=1 a helper warp in that slot computes the surface flux concurrently with the pair
+    // loops (mbarrier hand-over).  Measured on B200: N=4 5.11 ms against 5.02 ms without it, N=3 2.57 against 2.34 --
+    // one warp needs as long for all the face points as the line warps for their pairs, so it stays off.
+#ifndef ESDG_LINE_HELPER4
+#define ESDG_LINE_HELPER4 1
+#endif
+    static constexpr bool HELPER = ESDG_LINE_HELPER && ((THREADS / 32) % 2 == 1) && (n == 5 || ESDG_LINE_HELPER4);
+    static constexpr int THREADS_LAUNCH = THREADS + (HELPER ? 32 : 0);
 #ifndef ESDG_LINE_MINB5
 #define ESDG_LINE_MINB5 2
 #endif
@@ -328,9 +347,9 @@ __device__ __forceinline__ void line_vf_all(const Node (&nd)[n], const Node (&fn
 }
 
 #ifdef ESDG_LINE_MAXNREG   // register-budget experiments (n = 5 only): explicit cap instead of the CTAs-per-SM hint
-#define ESDG_LINE_BOUNDS(n) __launch_bounds__(LineDims<n>::THREADS) __maxnreg__(n == 5 ? ESDG_LINE_MAXNREG : 128)
+#define ESDG_LINE_BOUNDS(n) __launch_bounds__(LineDims<n>::THREADS_LAUNCH) __maxnreg__(n == 5 ? ESDG_LINE_MAXNREG : 128)
 #else
-#define ESDG_LINE_BOUNDS(n) __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB)
+#define ESDG_LINE_BOUNDS(n) __launch_bounds__(LineDims<n>::THREADS_LAUNCH, LineDims<n>::MINB)
 #endif
 
 template <int n, bool DIAG>
@@ -343,8 +362,9 @@ __global__ void ESDG_LINE_BOUNDS(n) k_hex_stage_line(
 #define ESDG_LINE_WI 1
 #endif
     constexpr int W = ESDG_LINE_WI;   // items per thread interleaved in the per-node / per-face-point phases (2 measured no faster)
+    constexpr int NTP = D::THREADS_LAUNCH;   // all threads share the per-point phases and the loads
     extern __shared__ __align__(16) double sm[];
-    __shared__ unsigned long long mbar;
+    __shared__ unsigned long long mbar, bbar;
     double* sWV = sm;                   // [7][EN]  rho, u/2, v/2, w/2, beta, log rho, log beta at volume nodes
     double* sWF = sWV + 7 * EN;         // [7][EF]  the same at the face points (own traces)
     double* sP = sWF + 7 * EF;          // [7][EF]  exterior traces, overwritten by the surface flux (5 planes)
@@ -363,14 +383,14 @@ __global__ void ESDG_LINE_BOUNDS(n) k_hex_stage_line(
 #endif
     const long long e0 = p.e_begin + (long long)blockIdx.x * EB;
     const int nb = (int)min((long long)EB, p.e_begin + p.e_count - e0);
-    constexpr int MAXF = (EF + NT - 1) / NT, MAXV = (EN + NT - 1) / NT;
+    constexpr int MAXF = (EF + NTP - 1) / NTP, MAXV = (EN + NTP - 1) / NTP;
     constexpr int GF = (MAXF + W - 1) / W, GV = (MAXV + W - 1) / W;   // item groups of W per thread
     const long long gq0 = e0 * Nq, gf0 = e0 * Nfq;
     // exterior-trace indices first: their (L2) latency overlaps everything up to the gather below
     int ipv[MAXF];
 #pragma unroll
     for (int r = 0; r < MAXF; ++r) {
-        const int it = tid + r * NT;
+        const int it = tid + r * NTP;
 #ifndef ESDG_LINE_NOLOAD
         ipv[r] = it < nb * Nfq ? p.mapP[gf0 + it] : -1;
 #else
@@ -378,7 +398,10 @@ __global__ void ESDG_LINE_BOUNDS(n) k_hex_stage_line(
 #endif
     }
     PHASE_MARK(12);
-    if (tid == 0) mbar_init(&mbar, 1);
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        mbar_init(&bbar, 32);   // helper warp -> line threads: surface flux ready
+    }
     PHASE_MARK(13);
     if (tid < n) {
         s_lm[tid] = p.lm[tid];
@@ -406,7 +429,7 @@ __global__ void ESDG_LINE_BOUNDS(n) k_hex_stage_line(
         if (tid == 0) mbar_expect_tx(&mbar, (p.mode == 1 ? 12u : 7u) * bq + 7u * bf);
         if ((tid & 31) == 0) {
             const int wv = tid >> 5;
-            constexpr int NW = NT / 32;
+            constexpr int NW = NTP / 32;
             for (int c = wv; c < 19; c += NW) {
                 if (c < 5) bulk_g2s(sQ + c * EN, p.Q + c * p.q_stride + gq0, bq, &mbar);
                 else if (c < 7) bulk_g2s(sWV + c * EN, p.Lcur + (c - 5) * p.q_stride + gq0, bq, &mbar);
@@ -415,7 +438,7 @@ __global__ void ESDG_LINE_BOUNDS(n) k_hex_stage_line(
             }
         }
     } else {
-        for (int it = tid; it < nb * Nq; it += NT) {
+        for (int it = tid; it < nb * Nq; it += NTP) {
             const long long g = gq0 + it;
 #pragma unroll
             for (int f = 0; f < 5; ++f) cp_async8(sQ + f * EN + it, p.Q + f * p.q_stride + g);
@@ -426,7 +449,7 @@ __global__ void ESDG_LINE_BOUNDS(n) k_hex_stage_line(
                 for (int f = 0; f < 5; ++f) cp_async8(sR + f * EN + it, p.res + f * p.q_stride + g);
             }
         }
-        for (int it = tid; it < nb * Nfq; it += NT) {
+        for (int it = tid; it < nb * Nfq; it += NTP) {
 #pragma unroll
             for (int q = 0; q < HEX_TP; ++q) cp_async8(sWF + q * EF + it, p.Tcur + q * p.t_stride + gf0 + it);
         }
@@ -434,13 +457,13 @@ __global__ void ESDG_LINE_BOUNDS(n) k_hex_stage_line(
     PHASE_MARK(10);
 #pragma unroll
     for (int r = 0; r < MAXF; ++r) {
-        const int it = tid + r * NT;
+        const int it = tid + r * NTP;
         if (it < nb * Nfq) {
 #pragma unroll
             for (int q = 0; q < HEX_TP; ++q) cp_async8(sP + q * EF + it, p.Tcur + q * p.t_stride + ipv[r]);
         }
     }
-    for (int it = tid; it < nb * 34; it += NT) cp_async8(sGeo + it, p.geo + e0 * 34 + it);
+    for (int it = tid; it < nb * 34; it += NTP) cp_async8(sGeo + it, p.geo + e0 * 34 + it);
     cp_async_commit();
     PHASE_MARK(11);
     // warm L2 for the CTA that starts when this one retires (one grid wave ahead)
@@ -448,7 +471,7 @@ __global__ void ESDG_LINE_BOUNDS(n) k_hex_stage_line(
         constexpr int PF_DIST = 148 * D::MINB;
         const long long e1 = e0 + (long long)PF_DIST * EB;
         if (e1 + EB <= p.e_begin + p.e_count) {
-            for (int it = tid * 16; it < EN; it += NT * 16) {   // one 128-byte line per 16 doubles
+            for (int it = tid * 16; it < EN; it += NTP * 16) {   // one 128-byte line per 16 doubles
                 const long long g1 = e1 * Nq + it;
 #pragma unroll
                 for (int f = 0; f < 5; ++f) prefetch_l2(p.Q + f * p.q_stride + g1);
@@ -459,7 +482,7 @@ __global__ void ESDG_LINE_BOUNDS(n) k_hex_stage_line(
                     for (int f = 0; f < 5; ++f) prefetch_l2(p.res + f * p.q_stride + g1);
                 }
             }
-            for (int it = tid * 16; it < EF; it += NT * 16) {
+            for (int it = tid * 16; it < EF; it += NTP * 16) {
                 prefetch_l2(p.mapP + e1 * Nfq + it);
 #pragma unroll
                 for (int q = 0; q < HEX_TP; ++q) prefetch_l2(p.Tcur + q * p.t_stride + e1 * Nfq + it);
@@ -480,12 +503,18 @@ __global__ void ESDG_LINE_BOUNDS(n) k_hex_stage_line(
 #define LINE_PARTIAL_IDX blockIdx.x
 #define LINE_AFTER_C()
 #define LINE_AFTER_E()
+#define LINE_NTP NTP
+#define LINE_HELPER D::HELPER
+#define LINE_B_PARITY 0
 #include "hex_line_phases.inc"
 #undef LINE_CSYNC
 #undef LINE_SGEO
 #undef LINE_PARTIAL_IDX
 #undef LINE_AFTER_C
 #undef LINE_AFTER_E
+#undef LINE_NTP
+#undef LINE_HELPER
+#undef LINE_B_PARITY
 #ifndef ESDG_LINE_NOLOAD
     if (bad) atomicOr(p.bad, 1);
 #endif
@@ -501,12 +530,6 @@ __global__ void ESDG_LINE_BOUNDS(n) k_hex_stage_line(
 //   empty_T : compute threads arrive after the line phase (traces, exterior traces / flux*, stash consumed)
 //   empty_Q : compute threads arrive after the update phase
 // Full batches with 16-byte aligned runs only (the host sends a ragged tail to the one-shot kernel).
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void cp_async_mbar_arrive(unsigned long long* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
 
 template <int n>
 struct LineDimsP {
@@ -523,6 +546,7 @@ __global__ void __launch_bounds__(LineDimsP<n>::THREADS, LineDims<n>::MINB) k_he
     constexpr int W = ESDG_LINE_WI;
     extern __shared__ __align__(16) double sm[];
     __shared__ unsigned long long pbar[4];   // full_T, full_Q, empty_T, empty_Q
+    __shared__ unsigned long long bbar;      // (helper-warp hand-over of the one-shot kernel: unused here)
     double* sWV = sm;
     double* sWF = sWV + 7 * EN;
     double* sP = sWF + 7 * EF;
@@ -634,12 +658,18 @@ __global__ void __launch_bounds__(LineDimsP<n>::THREADS, LineDims<n>::MINB) k_he
 #define LINE_PARTIAL_IDX bi
 #define LINE_AFTER_C() do { if (!p.want_rhstest) mbar_arrive(&pbar[2]); } while (0)
 #define LINE_AFTER_E() do { if (p.want_rhstest) mbar_arrive(&pbar[2]); mbar_arrive(&pbar[3]); } while (0)
+#define LINE_NTP NT
+#define LINE_HELPER false
+#define LINE_B_PARITY 0
 #include "hex_line_phases.inc"
 #undef LINE_CSYNC
 #undef LINE_SGEO
 #undef LINE_PARTIAL_IDX
 #undef LINE_AFTER_C
 #undef LINE_AFTER_E
+#undef LINE_NTP
+#undef LINE_HELPER
+#undef LINE_B_PARITY
     }
     if (bad) atomicOr(p.bad, 1);
 }
