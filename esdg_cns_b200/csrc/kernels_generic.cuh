@@ -320,6 +320,14 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_rhs(const 
     const long long e0 = (long long)blockIdx.x * p.EB;
     const int nb = (int)min((long long)p.EB, p.K - e0);
     bool bad = false;
+    // LSRK register of this thread's first output item: requested now, consumed in phase 6
+    double res_pre[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) res_pre[f] = 0.0;
+    if (p.mode == 1 && tid < nb * p.Ns) {
+#pragma unroll
+        for (int f = 0; f < NF; ++f) res_pre[f] = p.res[f * p.q_stride + e0 * p.Ns + tid];
+    }
     project_batch<DIM>(p, s, e0, nb, bad);
 
     // phase 3: surface flux at face points
@@ -494,7 +502,7 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_rhs(const 
         } else {
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
-                const double res = p.rk_a * p.res[f * p.q_stride + g] + p.dt * rr[f];
+                const double res = p.rk_a * (i == tid ? res_pre[f] : p.res[f * p.q_stride + g]) + p.dt * rr[f];
                 p.res[f * p.q_stride + g] = res;
                 p.Qout[f * p.q_stride + g] = s.U[(eb * NF + f) * p.Ns + r] + p.rk_b * res;
             }
