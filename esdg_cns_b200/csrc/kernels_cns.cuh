@@ -343,7 +343,8 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_sigma(const __
 }
 
 // Kernel 3: inviscid rhs + BR1 divergence + penalisation -> rhs or LSRK stage.
-__global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_rhs(const __grid_constant__ CnsParams P) {
+// 128 registers keep four 128-thread CTAs per SM (quad N=3: 2.1 ms per launch; at 134 registers three CTAs, 2.8 ms)
+__global__ void __maxnreg__(128) k_cns_rhs(const __grid_constant__ CnsParams P) {
     const GenericParams& p = P.g;
     constexpr int NF = 4;
     extern __shared__ double smem[];
