@@ -130,7 +130,7 @@ int cns_traces(esdg_ctx* ctx, const double* Qsrc) {
     CnsParams P;
     fill_cns(ctx, P, Qsrc);
     tick(ctx, "cns_traces");
-    k_cns_traces<<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(P);
+    k_cns_traces<<<grid_blocks(ctx), ctx->threads, ctx->smem_cns_traces, ctx->stream>>>(P);
     tock(ctx);
     CK(cudaGetLastError());
     return ESDG_OK;
@@ -142,7 +142,7 @@ int cns_sigma_pass(esdg_ctx* ctx, const double* Qsrc, int want) {
     fill_cns(ctx, P, Qsrc);
     P.g.want_rhstest = want;
     tick(ctx, "cns_sigma");
-    k_cns_sigma<<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(P);
+    k_cns_sigma<<<grid_blocks(ctx), ctx->threads, ctx->smem_cns_sigma, ctx->stream>>>(P);
     tock(ctx);
     CK(cudaGetLastError());
     return ESDG_OK;
@@ -477,8 +477,10 @@ static int finalize_cns(esdg_ctx* ctx) {
     ctx->smem_bytes = bytes(EB) + tbl;
     ctx->threads = std::min(ESDG_GENERIC_MAX_THREADS, ((EB * Nh + 31) / 32) * 32);
     if (const char* tv = getenv("ESDG_CNS_THREADS")) ctx->threads = std::max(32, (atoi(tv) / 32) * 32);   // launch-shape experiments
-    CK(cudaFuncSetAttribute(k_cns_traces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
-    CK(cudaFuncSetAttribute(k_cns_sigma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+    ctx->smem_cns_sigma = ctx->stage_tables ? ctx->smem_bytes : cns_sigma_smem_bytes(EB, d.Ns, d.Nq, d.Nfq);
+    ctx->smem_cns_traces = ctx->stage_tables ? ctx->smem_bytes : cns_traces_smem_bytes(EB, d.Ns, d.Nq, d.Nfq);
+    CK(cudaFuncSetAttribute(k_cns_traces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_cns_traces));
+    CK(cudaFuncSetAttribute(k_cns_sigma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_cns_sigma));
     CK(cudaFuncSetAttribute(k_cns_rhs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
     const size_t nb = (size_t)grid_blocks(ctx);
     if ((rc = dev_alloc(ctx, &c.partial_visc, nb))) return rc;

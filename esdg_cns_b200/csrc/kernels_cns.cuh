@@ -61,6 +61,13 @@ struct CnsSmem {
 inline size_t cns_extra_doubles(int EB, int Np, int Nq, int Nfq) {
     return (size_t)EB * 4 * (3 * Nfq + 6 * Np + 2 * Nq);
 }
+// k_cns_sigma: U, V of the generic block + the CNS arrays; k_cns_traces: U, V + one face array
+inline size_t cns_sigma_smem_bytes(int EB, int Np, int Nq, int Nfq) {
+    return ((size_t)EB * 4 * (Np + Nq) + cns_extra_doubles(EB, Np, Nq, Nfq)) * sizeof(double);
+}
+inline size_t cns_traces_smem_bytes(int EB, int Np, int Nq, int Nfq) {
+    return (size_t)EB * 4 * (Np + Nq + Nfq) * sizeof(double);
+}
 
 __device__ __forceinline__ CnsSmem cns_carve(double* base, const GenericParams& p) {
     CnsSmem c;
@@ -165,6 +172,7 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_traces(const _
     extern __shared__ double smem[];
     const GenericParams& p = Pin.g;
     GenericSmem<2> s(smem, p);
+    s.Uf = s.W;   // compact layout (cns_traces_smem_bytes): only U, V and one face array are used here
     const long long e0 = (long long)blockIdx.x * p.EB;
     const int nb = (int)min((long long)p.EB, p.K - e0);
     bool bad = false;
@@ -188,7 +196,9 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_sigma(const __
     extern __shared__ double smem[];
     const GenericParams& p = P.g;
     GenericSmem<2> s(smem, p);
-    CnsSmem c = cns_carve(s.R + p.EB * 4 * p.Ns, p);
+    // compact layout: this kernel touches only U and V of the generic block, so the CNS arrays start where W would
+    // (cns_sigma_smem_bytes: 27 KB instead of 45 KB per 4-element CTA on quads N=3 -> 8 instead of 5 CTAs per SM)
+    CnsSmem c = cns_carve(s.W, p);
     const int tid = threadIdx.x, nt = blockDim.x;
     const int Np = p.Ns, Nq = p.Nq, Nfq = p.Nfq;
     const long long e0 = (long long)blockIdx.x * p.EB;
