@@ -60,9 +60,9 @@ int launch_traces(esdg_ctx* ctx, const double* Qsrc) {
     p.Q = Qsrc;
     tick(ctx, "generic_traces");
     if (ctx->d.dim == 2)
-        k_generic_traces<2><<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(p);
+        k_generic_traces<2><<<grid_blocks(ctx), ctx->threads, ctx->smem_generic_traces, ctx->stream>>>(p);
     else
-        k_generic_traces<3><<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(p);
+        k_generic_traces<3><<<grid_blocks(ctx), ctx->threads, ctx->smem_generic_traces, ctx->stream>>>(p);
     tock(ctx);
     CK(cudaGetLastError());
     return ESDG_OK;
@@ -765,11 +765,12 @@ int esdg_finalize(esdg_ctx* ctx) {
     ctx->smem_bytes = ctx->table_off + tbl;
     if (ctx->smem_bytes > (size_t)maxsm) return fail(ctx, ESDG_EINVAL, "esdg_finalize: element too large for shared memory");
     ctx->threads = std::min(ESDG_GENERIC_MAX_THREADS, ((EB * Nh + 31) / 32) * 32);
+    ctx->smem_generic_traces = generic_traces_smem_bytes(DIM, EB, d.Ns, d.Nq, d.Nfq);
     if (DIM == 2) {
-        CK(cudaFuncSetAttribute(k_generic_traces<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+        CK(cudaFuncSetAttribute(k_generic_traces<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_generic_traces));
         CK(cudaFuncSetAttribute(k_generic_rhs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
     } else {
-        CK(cudaFuncSetAttribute(k_generic_traces<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+        CK(cudaFuncSetAttribute(k_generic_traces<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_generic_traces));
         CK(cudaFuncSetAttribute(k_generic_rhs<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
     }
     // ---- state -------------------------------------------------------------------

@@ -286,24 +286,74 @@ __device__ __forceinline__ void hadamard_sym(const GenericParams& p, GenericSmem
     }
 }
 
-// Kernel A: face traces of the (projected) conservative variables.
+// Kernel A: face traces of the (projected) conservative variables, Uf = u_vfun(face rows of the projection of
+// v_ufun) (dg2D_euler_quad.jl:149-150 / dg2D_euler_tri.jl:138-140).  Only the face rows are evaluated (the volume rows,
+// primitive variables and logs of project_batch are not needed here), with a compact shared-memory layout
+// (generic_traces_smem_bytes: U, V and one face array).
+inline size_t generic_traces_smem_bytes(int DIM, int EB, int Ns, int Nq, int Nfq) {
+    return (size_t)EB * (DIM + 2) * (Ns + Nq + Nfq) * sizeof(double);
+}
+
 template <int DIM>
 __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_traces(const __grid_constant__ GenericParams pin) {
     constexpr int NF = DIM + 2;
     extern __shared__ double smem[];
-    GenericParams p = pin;
-    stage_generic_tables(p, smem, ST_VQ | ST_PROJ);   // visible after the first barrier of project_batch
-    GenericSmem<DIM> s(smem, p);
+    const GenericParams& p = pin;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double* sU = smem;                          // [EB][NF][Ns]
+    double* sV = sU + p.EB * NF * p.Ns;         // [EB][NF][Nq]
+    double* sF = sV + p.EB * NF * p.Nq;         // [EB][NF][Nfq]  (modal: projected entropy variables at the face points)
     const long long e0 = (long long)blockIdx.x * p.EB;
     const int nb = (int)min((long long)p.EB, p.K - e0);
     bool bad = false;
-    project_batch<DIM>(p, s, e0, nb, bad);
     for (int f = 0; f < NF; ++f) {
-        double* dst = p.traces + f * p.trace_stride + e0 * p.Nfq;
-        for (int i = threadIdx.x; i < nb * p.Nfq; i += blockDim.x) {
-            const int eb = i / p.Nfq, k = i - eb * p.Nfq;
-            dst[i] = s.Uf[(eb * NF + f) * p.Nfq + k];
+        const double* src = p.Q + f * p.q_stride + e0 * p.Ns;
+        for (int i = tid; i < nb * p.Ns; i += nt) {
+            const int eb = i / p.Ns, k = i - eb * p.Ns;
+            sU[(eb * NF + f) * p.Ns + k] = src[i];
         }
+    }
+    __syncthreads();
+    if (!p.collocated) {
+        mma_apply<false>(p.dVq, sU, p.Ns, sV, p.Nq, nb * NF);
+        __syncthreads();
+    }
+    const double* Uq = p.collocated ? sU : sV;  // state at the quadrature points
+    const int ldq = p.collocated ? p.Ns : p.Nq;
+    for (int i = tid; i < nb * p.Nq; i += nt) {
+        const int eb = i / p.Nq, q = i - eb * p.Nq;
+        double U[NF], V[NF];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) U[f] = Uq[(eb * NF + f) * ldq + q];
+        v_of_u<DIM>(U, p.gamma, p.lg1, V, bad);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) sV[(eb * NF + f) * p.Nq + q] = V[f];
+    }
+    __syncthreads();
+    if (!p.collocated) {
+        mma_apply<false>(p.dProjF, sV, p.Nq, sF, p.Nfq, nb * NF);
+        __syncthreads();
+    }
+    for (int i = tid; i < nb * p.Nfq; i += nt) {
+        const int eb = i / p.Nfq, k = i - eb * p.Nfq;
+        double U[NF], V[NF];
+        if (!p.collocated) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) V[f] = sF[(eb * NF + f) * p.Nfq + k];
+        } else {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) V[f] = 0.0;
+            const int n = p.Proj.cnt[k];
+            for (int j = 0; j < n; ++j) {
+                const int c = p.Proj.col[k * p.Proj.width + j];
+                const double a = p.Proj.val[k * p.Proj.width + j];
+#pragma unroll
+                for (int f = 0; f < NF; ++f) V[f] = fma(a, sV[(eb * NF + f) * p.Nq + c], V[f]);
+            }
+        }
+        u_of_v<DIM>(V, p.gamma, p.lg1, U);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) p.traces[f * p.trace_stride + e0 * p.Nfq + i] = U[f];
     }
     if (bad) atomicOr(p.bad_flag, 1);
 }
