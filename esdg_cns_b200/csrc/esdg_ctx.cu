@@ -648,7 +648,7 @@ int esdg_finalize(esdg_ctx* ctx) {
                 // the dense triangle operators (config 2, 15 rounds against 30 entries per row: 1.04 -> 0.98 ms) and loses
                 // on the sparse quad operators (4.97 -> 5.36 ms), so it is used only when it really halves the row length
                 const bool force = ev && atoi(ev) == 2;
-                if (force || 10 * rounds <= 6 * width) {
+                if (force || 2 * rounds <= width) {
                     ctx->sym_rounds = rounds;
                     if ((rc = dev_upload(ctx, &ctx->sym_dst, sd))) return rc;
                     if ((rc = dev_upload(ctx, &ctx->sym_c, sc))) return rc;
@@ -757,7 +757,15 @@ int esdg_finalize(esdg_ctx* ctx) {
     ctx->stage_tables = tbl <= 48 * 1024 && getenv("ESDG_STAGE_TABLES") != nullptr;
     if (!ctx->stage_tables) tbl = 0;
     int EB = std::max(1, ESDG_GENERIC_MAX_THREADS / Nh);
-    EB = std::min<int64_t>(EB, d.collocated ? 16 : 4);   // modal: see finalize_cns
+    if (d.collocated) {
+        // two full rounds of items per phase for the CTA's threads: same residency (two 320-thread CTAs per SM by
+        // registers) with half the barriers and per-CTA set-up per element -- quads N=3, 1024^2: 4.78 ms (EB=10)
+        // -> 3.85 ms (EB=20) per rhs launch, 16 / 24 / 32 are slower (profiles/r1_generic_launch_shapes.txt).
+        // The symmetric schedule needs one thread per row, so a forced schedule keeps one round.
+        if (ctx->sym_rounds == 0) EB *= 2;
+    } else {
+        EB = std::min(EB, 4);                            // modal: see finalize_cns
+    }
     if (const char* ev = getenv("ESDG_GENERIC_EB")) EB = std::max(1, atoi(ev));   // launch-shape experiments
     while (EB > 1 && generic_smem_bytes(DIM, EB, d.Ns, d.Nq, d.Nfq, Nh, d.collocated) + tbl > (size_t)maxsm / 2) --EB;
     ctx->EB = EB;
