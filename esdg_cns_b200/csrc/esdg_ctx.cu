@@ -76,10 +76,12 @@ int launch_rhs(esdg_ctx* ctx, const double* Qsrc, int mode, double a, double b, 
     p.rk_a = a; p.rk_b = b; p.dt = dt;
     p.want_rhstest = want_rhstest;
     tick(ctx, "generic_rhs");
-    if (ctx->d.dim == 2)
-        k_generic_rhs<2><<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(p);
+    if (ctx->d.dim == 2 && !ctx->d.collocated)
+        k_generic_rhs<2, 64><<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(p);
+    else if (ctx->d.dim == 2)
+        k_generic_rhs<2, 96><<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(p);
     else
-        k_generic_rhs<3><<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(p);
+        k_generic_rhs<3, 128><<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(p);
     tock(ctx);
     CK(cudaGetLastError());
     if (want_rhstest) {
@@ -156,7 +158,7 @@ int cns_rhs_pass(esdg_ctx* ctx, const double* Qsrc, int mode, double a, double b
     P.g.rk_a = a; P.g.rk_b = b; P.g.dt = dt;
     P.g.want_rhstest = want;
     tick(ctx, "cns_rhs");
-    k_cns_rhs<<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(P);
+    k_cns_rhs<<<grid_blocks(ctx), ctx->threads, ctx->smem_cns_rhs, ctx->stream>>>(P);
     tock(ctx);
     CK(cudaGetLastError());
     if (want) {
@@ -481,7 +483,9 @@ static int finalize_cns(esdg_ctx* ctx) {
     ctx->smem_cns_traces = ctx->stage_tables ? ctx->smem_bytes : cns_traces_smem_bytes(EB, d.Ns, d.Nq, d.Nfq);
     CK(cudaFuncSetAttribute(k_cns_traces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_cns_traces));
     CK(cudaFuncSetAttribute(k_cns_sigma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_cns_sigma));
-    CK(cudaFuncSetAttribute(k_cns_rhs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+    ctx->smem_cns_rhs = ctx->stage_tables ? ctx->smem_bytes
+                                          : generic_smem_bytes(2, EB, d.Ns, d.Nq, d.Nfq, Nh, 0) + cns_rhs_extra_doubles(EB, d.Ns, d.Nq, d.Nfq) * sizeof(double);
+    CK(cudaFuncSetAttribute(k_cns_rhs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_cns_rhs));
     const size_t nb = (size_t)grid_blocks(ctx);
     if ((rc = dev_alloc(ctx, &c.partial_visc, nb))) return rc;
     if ((rc = dev_alloc(ctx, &c.partial_vrhs, nb))) return rc;
@@ -776,10 +780,11 @@ int esdg_finalize(esdg_ctx* ctx) {
     ctx->smem_generic_traces = generic_traces_smem_bytes(DIM, EB, d.Ns, d.Nq, d.Nfq);
     if (DIM == 2) {
         CK(cudaFuncSetAttribute(k_generic_traces<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_generic_traces));
-        CK(cudaFuncSetAttribute(k_generic_rhs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+        CK(cudaFuncSetAttribute(k_generic_rhs<2, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+        CK(cudaFuncSetAttribute(k_generic_rhs<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
     } else {
         CK(cudaFuncSetAttribute(k_generic_traces<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_generic_traces));
-        CK(cudaFuncSetAttribute(k_generic_rhs<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+        CK(cudaFuncSetAttribute(k_generic_rhs<3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
     }
     // ---- state -------------------------------------------------------------------
     const size_t nstate = (size_t)NF * d.Ns * d.K;

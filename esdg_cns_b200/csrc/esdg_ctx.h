@@ -73,7 +73,7 @@ struct esdg_ctx {
     // derived sizes
     int Nh = 0, Nfp = 0, NF = 0, EB = 1, threads = 256, geo_stride = 0;
     size_t smem_bytes = 0;
-    size_t smem_cns_sigma = 0, smem_cns_traces = 0;   // compact per-kernel layouts (kernels_cns.cuh)
+    size_t smem_cns_sigma = 0, smem_cns_traces = 0, smem_cns_rhs = 0;   // compact per-kernel layouts (kernels_cns.cuh)
     size_t smem_generic_traces = 0;                   // k_generic_traces: U, V and one face array
     int stage_tables = 0;          // operator tables copied to shared memory by the kernels
     unsigned table_off = 0;        // byte offset of the table region in dynamic shared memory

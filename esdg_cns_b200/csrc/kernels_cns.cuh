@@ -142,6 +142,23 @@ __device__ __forceinline__ void bc_stress(const CnsParams& p, int kind, double v
     }
 }
 
+// k_cns_rhs uses Vfc, B1, B2, Jx, Q1, Rv of the CNS arrays only: compact carve behind the generic block
+inline size_t cns_rhs_extra_doubles(int EB, int Np, int Nq, int Nfq) {
+    return (size_t)EB * 4 * (2 * Nfq + 3 * Np + Nq);
+}
+__device__ __forceinline__ CnsSmem cns_carve_rhs(double* base, const GenericParams& p) {
+    CnsSmem c;
+    const int EB = p.EB;
+    c.Vfc = base;
+    c.B1 = c.Vfc + EB * 4 * p.Nfq;
+    c.B2 = c.B1 + EB * 4 * p.Ns;
+    c.Jx = c.B2 + EB * 4 * p.Ns;
+    c.Q1 = c.Jx + EB * 4 * p.Nfq;
+    c.Rv = c.Q1 + EB * 4 * p.Nq;
+    c.A = c.Tx = c.Ty = c.Jy = c.Q2 = nullptr;
+    return c;
+}
+
 // Stage Q, evaluate v_ufun(Vq*Q) at the quadrature points (:763-771).  Fills s.U, s.V.
 __device__ __forceinline__ void cns_entropy_vars(const GenericParams& p, GenericSmem<2>& s, long long e0, int nb, bool& bad) {
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -353,13 +370,18 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_cns_sigma(const __
 }
 
 // Kernel 3: inviscid rhs + BR1 divergence + penalisation -> rhs or LSRK stage.
-// 128 registers keep four 128-thread CTAs per SM (quad N=3: 2.1 ms per launch; at 134 registers three CTAs, 2.8 ms)
-__global__ void __maxnreg__(128) k_cns_rhs(const __grid_constant__ CnsParams P) {
+// Residency is the lever on this path (profiles/r1_cns_register_caps.txt, quad N=3, 128-thread CTAs, compact shared
+// memory of 35 KB): 134 registers = 3 CTAs per SM 2.8 ms, 128 = 4 CTAs 2.12 ms, 96 = 5 CTAs 1.91 ms, 80 = 6 CTAs 1.76 ms
+// per launch (20 bytes of spills)
+#ifndef ESDG_CNS_RHS_REGS
+#define ESDG_CNS_RHS_REGS 80
+#endif
+__global__ void __maxnreg__(ESDG_CNS_RHS_REGS) k_cns_rhs(const __grid_constant__ CnsParams P) {
     const GenericParams& p = P.g;
     constexpr int NF = 4;
     extern __shared__ double smem[];
     GenericSmem<2> s(smem, p);
-    CnsSmem c = cns_carve(s.R + p.EB * 4 * p.Ns, p);
+    CnsSmem c = cns_carve_rhs(s.R + p.EB * 4 * p.Ns, p);
     s.Vface = c.Vfc;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int Np = p.Ns, Nq = p.Nq, Nfq = p.Nfq;

@@ -359,8 +359,11 @@ __global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_traces(con
 }
 
 // Kernel B: surface + volume + lift + (rhs | LSRK stage).
-template <int DIM>
-__global__ void __launch_bounds__(ESDG_GENERIC_MAX_THREADS) k_generic_rhs(const __grid_constant__ GenericParams pin) {
+// RCAP: register cap.  Residency decides on these table-driven kernels (profiles/r1_generic_register_caps.txt):
+// collocated elements run 320-thread CTAs and are best at 96 registers (quads N=3: 3.88 ms against 4.28 ms at 80 / 64);
+// modal elements run 128-thread CTAs and gain from 64 registers = 8 CTAs per SM (triangles N=4: 0.93 -> 0.84 ms).
+template <int DIM, int RCAP>
+__global__ void __maxnreg__(RCAP) k_generic_rhs(const __grid_constant__ GenericParams pin) {
     constexpr int NF = DIM + 2;
     extern __shared__ double smem[];
     GenericParams p = pin;
