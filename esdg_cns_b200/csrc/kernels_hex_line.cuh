@@ -349,7 +349,11 @@ __device__ __forceinline__ void line_vf_all(const Node (&nd)[n], const Node (&fn
 #ifdef ESDG_LINE_MAXNREG   // register-budget experiments (n = 5 only): explicit cap instead of the CTAs-per-SM hint
 #define ESDG_LINE_BOUNDS(n) __launch_bounds__(LineDims<n>::THREADS_LAUNCH) __maxnreg__(n == 5 ? ESDG_LINE_MAXNREG : 128)
 #else
-#define ESDG_LINE_BOUNDS(n) __launch_bounds__(LineDims<n>::THREADS_LAUNCH, LineDims<n>::MINB)
+#ifndef ESDG_LINE_REGTHREADS4
+#define ESDG_LINE_REGTHREADS4 0   // N = 3: thread count the register budget is computed for (0 = the launch size)
+#endif
+#define ESDG_LINE_BOUNDS(n) \
+    __launch_bounds__((n == 4 && ESDG_LINE_REGTHREADS4) ? ESDG_LINE_REGTHREADS4 : LineDims<n>::THREADS_LAUNCH, LineDims<n>::MINB)
 #endif
 
 template <int n, bool DIAG>
