@@ -901,15 +901,18 @@ int esdg_lsrk45_step(esdg_ctx* ctx, double dt, int nsteps, double* rhstest_last)
 }
 
 // ---- pipelined host step -----------------------------------------------------------------------------
-// upload -> nsteps x 5 stages -> download with the PCIe copies overlapped: the state travels in element
-// chunks; the traces of a chunk are computed as soon as it has landed and the first stage runs on every
-// chunk whose neighbours (through mapP) have landed too, while later chunks are still in flight; the
-// last stage runs chunk by chunk with the device->host copy of each finished chunk behind it.
+// upload -> nsteps x 5 stages -> download as a WAVEFRONT over element chunks, so that the host->device and the
+// device->host copies overlap the stages AND each other (PCIe is full duplex).  Stage s of a chunk needs stage s-1 of the
+// chunks its mapP touches (their new traces; the same condition protects the double-buffered trace arrays against
+// overwriting), so after 5 stages a chunk depends on a cone of +-4 neighbour layers only: chunks are uploaded outward
+// from chunk 0, every (chunk, stage) task is issued to the one compute stream as soon as its predecessors have been
+// issued, and a chunk's device->host copy starts behind its last stage while later chunks are still uploading.
 static int build_chunks(esdg_ctx* ctx) {
     const esdg_desc& d = ctx->d;
     const long long K = d.K;
     const int EB = ctx->hex ? 2 * ctx->hex->EB : 1;               // even element offsets keep the TMA path aligned
-    int nchunk = (int)std::min<long long>(8, K / std::max<long long>(4096, EB));
+    int nchunk = (int)std::min<long long>(16, K / std::max<long long>(4096, EB));
+    if (const char* ev = getenv("ESDG_HOST_CHUNKS")) nchunk = std::max(1, std::min(32, atoi(ev)));   // experiments
     if (nchunk < 2) nchunk = 1;
     long long per = ((K + nchunk - 1) / nchunk + EB - 1) / EB * EB;
     ctx->chunk_begin.clear();
@@ -953,55 +956,82 @@ int esdg_lsrk45_host(esdg_ctx* ctx, const double* const* Q_in, double* const* Q_
     const int nchunk = (int)ctx->chunk_begin.size() - 1;
     const size_t n = (size_t)ctx->d.Ns * ctx->d.K;
     const int Ns = ctx->d.Ns;
+    const int nstage = 5 * nsteps;
     ctx->dopri.ready = false;
     // order the copy stream after everything already queued on the main stream
     cudaEvent_t fence = ctx->chunk_done[0];
     CK(cudaEventRecord(fence, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->h2d_stream, fence, 0));
+    CK(cudaStreamWaitEvent(ctx->d2h_stream, fence, 0));
     CK(cudaMemsetAsync(ctx->res, 0, ctx->NF * n * sizeof(double), ctx->stream));
     h->prod ^= 1;                                                 // fresh trace / log buffers for the uploaded state
-    h->cons = h->prod ^ 1;
-    const int bufU = h->prod;
-    unsigned landed = 0, started = 0;
-    auto first_stage = [&](int c) -> int {
-        h->cons = bufU;
-        h->prod = bufU ^ 1;
-        started |= 1u << c;
-        return hexfast_stage_range(ctx, ctx->Q, 1, RK4A[0], RK4B[0], dt, ctx->chunk_begin[c],
-                                   ctx->chunk_begin[c + 1] - ctx->chunk_begin[c]);
+    const int bufU = h->prod;                                     // buffer of the traces of the uploaded state
+    // upload order: breadth first from chunk 0 over the chunk graph (periodic slabs: 0, 1, C-1, 2, C-2, ...)
+    std::vector<int> order;
+    {
+        std::vector<char> seen(nchunk, 0);
+        order.push_back(0);
+        seen[0] = 1;
+        for (size_t i = 0; i < order.size() || (int)order.size() < nchunk; ++i) {
+            if (i == order.size()) {                              // disconnected remainder
+                for (int c = 0; c < nchunk; ++c)
+                    if (!seen[c]) { order.push_back(c); seen[c] = 1; break; }
+            }
+            const int c = order[i];
+            for (int q = 0; q < nchunk; ++q)
+                if (!seen[q] && (ctx->chunk_dep[c] >> q & 1u)) { order.push_back(q); seen[q] = 1; }
+        }
+    }
+    std::vector<int> done(nchunk, 0);     // stages issued per chunk
+    std::vector<char> up(nchunk, 0);      // uploaded and traces issued
+    auto ready = [&](int c) {
+        const int st = done[c];
+        if (!up[c] || st >= nstage) return false;
+        for (int q = 0; q < nchunk; ++q)
+            if ((ctx->chunk_dep[c] >> q & 1u) && (st == 0 ? !up[q] : done[q] < st)) return false;
+        return true;
     };
-    for (int c = 0; c < nchunk; ++c) {
-        const long long b = ctx->chunk_begin[c], len = ctx->chunk_begin[c + 1] - b;
+    for (int idx = 0; idx < nchunk; ++idx) {
+        const int u = order[idx];
+        const long long b = ctx->chunk_begin[u], len = ctx->chunk_begin[u + 1] - b;
         for (int f = 0; f < ctx->NF; ++f)
             CK(cudaMemcpyAsync(ctx->Q + f * n + b * Ns, Q_in[f] + b * Ns, (size_t)len * Ns * sizeof(double),
                                cudaMemcpyHostToDevice, ctx->h2d_stream));
-        CK(cudaEventRecord(ctx->chunk_up[c], ctx->h2d_stream));
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_up[c], 0));
+        CK(cudaEventRecord(ctx->chunk_up[u], ctx->h2d_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_up[u], 0));
         h->prod = bufU;
         h->cons = bufU ^ 1;
         if ((rc = hexfast_traces_range(ctx, ctx->Q, b, len))) return rc;
-        landed |= 1u << c;
-        for (int q = 0; q < nchunk; ++q)
-            if (!(started & (1u << q)) && (ctx->chunk_dep[q] & ~landed) == 0 && (rc = first_stage(q))) return rc;
+        up[u] = 1;
+        // issue every task that has become ready, deepest stage first (ties: upload order): chunks near chunk 0 finish
+        // all their stages -- and start their download -- while the outer chunks are still on the bus
+        for (;;) {
+            int best = -1;
+            for (int k = 0; k < nchunk; ++k) {
+                const int c = order[k];
+                if (ready(c) && (best < 0 || done[c] > done[best])) best = c;
+            }
+            if (best < 0) break;
+            const int c = best, st = done[c];
+            const long long cb = ctx->chunk_begin[c], cl = ctx->chunk_begin[c + 1] - cb;
+            h->cons = bufU ^ (st & 1);                            // stage st reads the traces stage st-1 wrote
+            h->prod = h->cons ^ 1;
+            if ((rc = hexfast_stage_range(ctx, ctx->Q, 1, RK4A[st % 5], RK4B[st % 5], dt, cb, cl))) return rc;
+            done[c] = st + 1;
+            if (done[c] == nstage) {                              // finished: its download goes behind it
+                CK(cudaEventRecord(ctx->chunk_done[c], ctx->stream));
+                CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->chunk_done[c], 0));
+                for (int f = 0; f < ctx->NF; ++f)
+                    CK(cudaMemcpyAsync(Q_out[f] + cb * Ns, ctx->Q + f * n + cb * Ns, (size_t)cl * Ns * sizeof(double),
+                                       cudaMemcpyDeviceToHost, ctx->d2h_stream));
+            }
+        }
     }
-    h->cons = bufU;
-    h->prod = bufU ^ 1;
+    for (int c = 0; c < nchunk; ++c)
+        if (done[c] != nstage) return fail(ctx, ESDG_EINVAL, "esdg_lsrk45_host: internal scheduling error");
+    h->prod = bufU ^ (nstage & 1);                                // traces of the final state
+    h->cons = h->prod ^ 1;
     ctx->traces_valid = true;
-    const int nstage = 5 * nsteps;
-    for (int sidx = 1; sidx < nstage - 1; ++sidx)
-        if ((rc = do_stage(ctx, ctx->Q, 1, RK4A[sidx % 5], RK4B[sidx % 5], dt, 0, ESDG_PART_ALL))) return rc;
-    // last stage, chunk by chunk, each followed by its download
-    h->cons = h->prod;
-    h->prod = h->cons ^ 1;
-    for (int c = 0; c < nchunk; ++c) {
-        const long long b = ctx->chunk_begin[c], len = ctx->chunk_begin[c + 1] - b;
-        if ((rc = hexfast_stage_range(ctx, ctx->Q, 1, RK4A[4], RK4B[4], dt, b, len))) return rc;
-        CK(cudaEventRecord(ctx->chunk_done[c], ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->chunk_done[c], 0));
-        for (int f = 0; f < ctx->NF; ++f)
-            CK(cudaMemcpyAsync(Q_out[f] + b * Ns, ctx->Q + f * n + b * Ns, (size_t)len * Ns * sizeof(double),
-                               cudaMemcpyDeviceToHost, ctx->d2h_stream));
-    }
     CK(cudaStreamSynchronize(ctx->d2h_stream));
     return check_bad(ctx);
 }

@@ -312,10 +312,15 @@ def test_hex_line_kernel_matches_generic_kernels(monkeypatch):
     assert _relerr(Qa, Qb) < 1e-12
 
 
-@pytest.mark.parametrize("N,mesh,nsteps", [(4, (32, 32, 10), 1), (3, (40, 40, 6), 2), (2, (5, 4, 3), 1)])
-def test_pipelined_host_step_is_bitwise_the_resident_loop(N, mesh, nsteps):
-    """esdg_lsrk45_host (chunked upload / first stage / last stage / download) == upload + lsrk45 + download."""
+@pytest.mark.parametrize("N,mesh,nsteps,chunks", [(4, (32, 32, 10), 1, None), (3, (40, 40, 6), 2, None), (2, (5, 4, 3), 1, None),
+                                                  (4, (16, 16, 24), 1, 12), (4, (16, 16, 24), 1, 7), (3, (12, 10, 22), 3, 11),
+                                                  (2, (8, 8, 32), 1, 32)])
+def test_pipelined_host_step_is_bitwise_the_resident_loop(N, mesh, nsteps, chunks, monkeypatch):
+    """esdg_lsrk45_host (wavefront of (chunk, stage) tasks behind the chunked upload, downloads behind the finished
+    chunks) == upload + lsrk45 + download, for chunk counts that split layers evenly, unevenly and one layer per chunk."""
     import torch
+    if chunks is not None:
+        monkeypatch.setenv("ESDG_HOST_CHUNKS", str(chunks))
     from esdg_cns_b200 import api, setup_dg as SD
     prd, pops = SD.reference_hex(N)
     pmd = SD.uniform_hex_mesh_md(prd, mesh, domain=((-np.pi, np.pi),) * 3)
