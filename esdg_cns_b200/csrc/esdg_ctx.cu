@@ -912,22 +912,22 @@ static int build_chunks(esdg_ctx* ctx) {
     const long long K = d.K;
     const int EB = ctx->hex ? 2 * ctx->hex->EB : 1;               // even element offsets keep the TMA path aligned
     int nchunk = (int)std::min<long long>(16, K / std::max<long long>(4096, EB));
-    if (const char* ev = getenv("ESDG_HOST_CHUNKS")) nchunk = std::max(1, std::min(32, atoi(ev)));   // experiments
+    if (const char* ev = getenv("ESDG_HOST_CHUNKS")) nchunk = std::max(1, std::min(64, atoi(ev)));   // experiments
     if (nchunk < 2) nchunk = 1;
     long long per = ((K + nchunk - 1) / nchunk + EB - 1) / EB * EB;
     ctx->chunk_begin.clear();
     for (long long b = 0; b < K; b += per) ctx->chunk_begin.push_back(b);
     ctx->chunk_begin.push_back(K);
     nchunk = (int)ctx->chunk_begin.size() - 1;
-    ctx->chunk_dep.assign(nchunk, 0u);
+    ctx->chunk_dep.assign(nchunk, 0ull);
     auto chunk_of = [&](long long e) {
         int c = (int)(e / per);
         return c < nchunk ? c : nchunk - 1;
     };
     for (int c = 0; c < nchunk; ++c) {
-        unsigned m = 1u << c;
+        unsigned long long m = 1ull << c;
         for (long long e = ctx->chunk_begin[c]; e < ctx->chunk_begin[c + 1]; ++e)
-            for (int k = 0; k < d.Nfq; ++k) m |= 1u << chunk_of((ctx->mapP_host[(size_t)(e * d.Nfq + k)] - 1) / d.Nfq);
+            for (int k = 0; k < d.Nfq; ++k) m |= 1ull << chunk_of((ctx->mapP_host[(size_t)(e * d.Nfq + k)] - 1) / d.Nfq);
         ctx->chunk_dep[c] = m;
     }
     CK(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
@@ -979,7 +979,7 @@ int esdg_lsrk45_host(esdg_ctx* ctx, const double* const* Q_in, double* const* Q_
             }
             const int c = order[i];
             for (int q = 0; q < nchunk; ++q)
-                if (!seen[q] && (ctx->chunk_dep[c] >> q & 1u)) { order.push_back(q); seen[q] = 1; }
+                if (!seen[q] && (ctx->chunk_dep[c] >> q & 1ull)) { order.push_back(q); seen[q] = 1; }
         }
     }
     std::vector<int> done(nchunk, 0);     // stages issued per chunk
@@ -988,7 +988,7 @@ int esdg_lsrk45_host(esdg_ctx* ctx, const double* const* Q_in, double* const* Q_
         const int st = done[c];
         if (!up[c] || st >= nstage) return false;
         for (int q = 0; q < nchunk; ++q)
-            if ((ctx->chunk_dep[c] >> q & 1u) && (st == 0 ? !up[q] : done[q] < st)) return false;
+            if ((ctx->chunk_dep[c] >> q & 1ull) && (st == 0 ? !up[q] : done[q] < st)) return false;
         return true;
     };
     for (int idx = 0; idx < nchunk; ++idx) {

@@ -111,7 +111,7 @@ struct esdg_ctx {
     // pipelined host step (esdg_lsrk45_host): copy streams, per-chunk events, chunk dependency masks
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     std::vector<cudaEvent_t> chunk_up, chunk_done;
-    std::vector<unsigned> chunk_dep;    // bit c' set: the stage of this chunk reads traces of chunk c'
+    std::vector<unsigned long long> chunk_dep;   // bit c' set: the stage of this chunk reads traces of chunk c'
     std::vector<long long> chunk_begin; // nchunk + 1 element offsets
     long long bnd_lo = 0, bnd_hi = 0;   // leading / trailing elements whose traces are sent to neighbours
     bool res_zero = true;
