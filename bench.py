@@ -179,6 +179,25 @@ def cpu_baseline_leg(seconds_budget=25.0):
                       f"{steps} LSRK45 steps, {el:.1f} s, C/OpenMP restatement of dg3D_euler_hex.jl (Julia unavailable)"}
 
 
+def bind_to_gpu_cpus(index):
+    """Multi-GPU runs: keep this rank (and the pinned host buffers it first-touches) on the CPUs NVML reports as local to
+    its GPU, so that the host<->device copies of the end-to-end leg do not cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -192,6 +211,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_cpus(local_rank) if world > 1 else None   # pinned host buffers on the GPU's own NUMA node
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line (NCCL prints its version there)
@@ -312,7 +332,7 @@ def run_ours(args):
             "config": {"workload": f"tgv_hex_N{N}_{Kx}x{Ky}x{Kzl}_per_gpu", "N": N, "elements_per_gpu": K,
                        "global_mesh": [Kx, Ky, Kz], "dof_per_gpu": dof, "stages_per_step": 5, "dt": dt,
                        "l2_policy": f"state {dof * 8 * 2 / 1e9:.2f} GB/GPU streamed every stage (>> 126 MB L2), no flush needed",
-                       "parallelism": f"z-slab x{world}", "finite": finite},
+                       "parallelism": f"z-slab x{world}", "finite": finite, "cpus_bound_per_rank": numa},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(dom_name, K), "kernel": dom_name, "kernel_ms_per_launch": per_launch_s * 1e3,
                          "kernel_launches_timed": dom_n, "kernel_share_of_step": dom_ms / ms,
