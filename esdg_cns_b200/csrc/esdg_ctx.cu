@@ -8,6 +8,9 @@
 using namespace esdg;
 
 #define ESDG_VERSION "esdg_b200 0.1 (sm_100a)"
+#ifndef ESDG_GENERIC_COLL_REGS
+#define ESDG_GENERIC_COLL_REGS 96   // register cap of the generic rhs kernel on collocated 2-D elements (kernels_generic.cuh)
+#endif
 
 using namespace esdg_host;
 
@@ -79,7 +82,7 @@ int launch_rhs(esdg_ctx* ctx, const double* Qsrc, int mode, double a, double b, 
     if (ctx->d.dim == 2 && !ctx->d.collocated)
         k_generic_rhs<2, 64><<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(p);
     else if (ctx->d.dim == 2)
-        k_generic_rhs<2, 96><<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(p);
+        k_generic_rhs<2, ESDG_GENERIC_COLL_REGS><<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(p);
     else
         k_generic_rhs<3, 128><<<grid_blocks(ctx), ctx->threads, ctx->smem_bytes, ctx->stream>>>(p);
     tock(ctx);
@@ -777,10 +780,11 @@ int esdg_finalize(esdg_ctx* ctx) {
     ctx->smem_bytes = ctx->table_off + tbl;
     if (ctx->smem_bytes > (size_t)maxsm) return fail(ctx, ESDG_EINVAL, "esdg_finalize: element too large for shared memory");
     ctx->threads = std::min(ESDG_GENERIC_MAX_THREADS, ((EB * Nh + 31) / 32) * 32);
+    if (const char* tv = getenv("ESDG_GENERIC_THREADS")) ctx->threads = std::max(32, (atoi(tv) / 32) * 32);   // launch-shape experiments
     ctx->smem_generic_traces = generic_traces_smem_bytes(DIM, EB, d.Ns, d.Nq, d.Nfq);
     if (DIM == 2) {
         CK(cudaFuncSetAttribute(k_generic_traces<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_generic_traces));
-        CK(cudaFuncSetAttribute(k_generic_rhs<2, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+        CK(cudaFuncSetAttribute(k_generic_rhs<2, ESDG_GENERIC_COLL_REGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
         CK(cudaFuncSetAttribute(k_generic_rhs<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
     } else {
         CK(cudaFuncSetAttribute(k_generic_traces<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_generic_traces));
