@@ -283,7 +283,8 @@ def run_ours(args):
     def e2e_step():
         if stepper is None:
             # one call of the host-buffer API: H2D of this step's input from pinned memory, 5 stages, D2H of the
-            # result -- all inside the timed region; the library pipelines the copies against the first / last stage
+            # result -- all inside the timed region; the library runs the stages as a wavefront over element chunks
+            # behind the upload and starts each chunk's download behind its last stage
             s.lsrk45_host(host, dt, 1)
             return
         s.upload(host)           # H2D of this step's input from pinned memory (+ sync)

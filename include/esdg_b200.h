@@ -149,8 +149,11 @@ int esdg_download_state(esdg_ctx* ctx, double* const* Q);
 int esdg_lsrk45_step(esdg_ctx* ctx, double dt, int nsteps, double* rhstest_last);
 
 /* The same loop for HOST state (the Julia `Q`, `Vector{Matrix{Float64}}`): Q_in -> nsteps LSRK45 steps ->
- * Q_out (may alias Q_in), with the host<->device copies pipelined against the first and last stage
- * (chunks of elements; pinned host memory is needed for the copies to overlap).  Synchronous. */
+ * Q_out (may alias Q_in).  On the tensor-product hex path the state travels in element chunks and the stages run as
+ * a wavefront behind the upload (stage s of a chunk needs stage s-1 of the chunks its mapP touches), with each
+ * chunk's download behind its last stage, so both copy directions and the kernels overlap; the result is bitwise
+ * that of esdg_upload_state + esdg_lsrk45_step + esdg_download_state.  Pinned host memory is needed for the copies
+ * to overlap.  Other paths: plain upload / steps / download.  Synchronous. */
 int esdg_lsrk45_host(esdg_ctx* ctx, const double* const* Q_in, double* const* Q_out, double dt, int nsteps);
 
 /* DOPRI45 adaptive driver of the CNS scripts (dg2D_CNS_cavity_optimized.jl:919-934 coefficients,
