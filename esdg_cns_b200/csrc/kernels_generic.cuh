@@ -219,8 +219,11 @@ __device__ __forceinline__ void hadamard_sym(const GenericParams& p, GenericSmem
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int i = tid; i < nb * NF * p.Nh; i += nt) s.QF[i] = 0.0;
     __syncthreads();
-    const bool act = tid < nb * p.Nh;
-    const int eb = act ? tid / p.Nh : 0, r = act ? tid - eb * p.Nh : 0;
+    // elements with at most 32 hybridized rows (triangles up to N = 4): one WARP per element, so the rounds need a
+    // warp barrier only (a row and its partner's slot belong to the same element)
+    const bool warp_elems = p.Nh <= 32 && nt >= 32 * nb;
+    const bool act = warp_elems ? ((tid >> 5) < nb && (tid & 31) < p.Nh) : tid < nb * p.Nh;
+    const int eb = !act ? 0 : (warp_elems ? tid >> 5 : tid / p.Nh), r = !act ? 0 : (warp_elems ? tid & 31 : tid - eb * p.Nh);
     const long long e = e0 + eb;
     const double* w = s.W + (size_t)eb * (NF + 2) * p.Nh;
     Prim<DIM> Pi;
@@ -278,7 +281,7 @@ __device__ __forceinline__ void hadamard_sym(const GenericParams& p, GenericSmem
                 qf[f * p.Nh + j] -= F[f];
             }
         }
-        __syncthreads();
+        if (warp_elems) __syncwarp(); else __syncthreads();
     }
     if (act) {
 #pragma unroll
