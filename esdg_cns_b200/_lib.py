@@ -78,6 +78,7 @@ _SIGNATURES = {
     "esdg_kernel_time_ms": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "esdg_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "esdg_debug_log_exp": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "esdg_debug_pair_flux": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p]),
     "esdg_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "esdg_version": (C.c_char_p, []),
 }

@@ -437,6 +437,51 @@ extern "C" int esdg_debug_log_exp(int device, const double* x, int64_t n, double
     return cudaGetLastError() == cudaSuccess ? ESDG_OK : ESDG_ECUDA;
 }
 
+
+// ---- diagnostic entry point: the line kernel's own two-point flux (pair_flux_v) on caller-supplied pairs -----
+namespace {
+__global__ void k_debug_pair_flux(const double* L, const double* R, long long n, double gamma, double* F) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    NodeV<1> A, B;
+    const double* S[2] = {L, R};
+    NodeV<1>* N2[2] = {&A, &B};
+    for (int s = 0; s < 2; ++s) {
+        N2[s]->rho[0] = S[s][i];
+        for (int c = 0; c < 3; ++c) N2[s]->u[c][0] = .5 * S[s][(1 + c) * n + i];   // the kernels keep HALF velocities
+        N2[s]->beta[0] = S[s][4 * n + i];
+        N2[s]->lr[0] = S[s][5 * n + i];
+        N2[s]->lb[0] = S[s][6 * n + i];
+    }
+    const double c_igm = 1.0 / (2.0 * (gamma - 1.0));
+    VD<1> Fv[5];
+    {   // axis-aligned form: flux / g0 along the first component
+        const VD<1> g[3] = {vset<1>(1.0), vset<1>(0.0), vset<1>(0.0)};
+        pair_flux_v<1, true>(A, B, g, c_igm, Fv);
+        for (int f = 0; f < 5; ++f) F[(0 * 5 + f) * n + i] = Fv[f][0];
+    }
+    for (int d = 0; d < 3; ++d) {   // general form contracted with e_d
+        const VD<1> g[3] = {vset<1>(d == 0 ? 1.0 : 0.0), vset<1>(d == 1 ? 1.0 : 0.0), vset<1>(d == 2 ? 1.0 : 0.0)};
+        pair_flux_v<1, false>(A, B, g, c_igm, Fv);
+        for (int f = 0; f < 5; ++f) F[((1 + d) * 5 + f) * n + i] = Fv[f][0];
+    }
+}
+}  // namespace
+
+extern "C" int esdg_debug_pair_flux(int device, const double* UL, const double* UR, int64_t n, double gamma, double* F_out) {
+    if (!UL || !UR || !F_out || n <= 0) return ESDG_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return ESDG_ECUDA;
+    double *dl = nullptr, *dr = nullptr, *df = nullptr;
+    if (cudaMalloc(&dl, n * 56) != cudaSuccess || cudaMalloc(&dr, n * 56) != cudaSuccess || cudaMalloc(&df, n * 160) != cudaSuccess)
+        return ESDG_ENOMEM;
+    cudaMemcpy(dl, UL, n * 56, cudaMemcpyHostToDevice);
+    cudaMemcpy(dr, UR, n * 56, cudaMemcpyHostToDevice);
+    k_debug_pair_flux<<<(unsigned)((n + 127) / 128), 128>>>(dl, dr, n, gamma, df);
+    cudaMemcpy(F_out, df, n * 160, cudaMemcpyDeviceToHost);
+    cudaFree(dl); cudaFree(dr); cudaFree(df);
+    return cudaGetLastError() == cudaSuccess ? ESDG_OK : ESDG_ECUDA;
+}
+
 #ifdef ESDG_PHASE_TIMING
 // debug build: read and clear the per-phase cycle counters of k_hex_stage_line
 extern "C" int esdg_debug_phase_cycles(unsigned long long* out16) {

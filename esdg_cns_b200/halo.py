@@ -191,3 +191,49 @@ class LocalSlabsCNS:
             for s in self.s:
                 s.stage_update(k, dt, want, s.PART_ALL)
             self._exchange_v()
+
+
+class LocalSlabs:
+    """GpuSlabStepper for several z-slabs of an Euler mesh held by one process: the same per-stage call sequence
+    (boundary layers -> pack -> exchange -> interior -> unpack, or the plain one), with device-to-device copies
+    for the exchange.  Single-GPU coverage of the distributed hex path (esdg_stage_update parts 1/2, the
+    7-plane halo, pack / unpack)."""
+
+    def __init__(self, solvers, mds, torch, device, overlap=True):
+        self.s = solvers
+        self.h = [SlabHalo(md, s.trace_planes(), None, torch, device) for s, md in zip(solvers, mds)]
+        for s, h in zip(solvers, self.h):
+            s.set_send_list(h.send_list)
+        self.overlap = overlap
+        self.fresh = True
+
+    def _pack(self):
+        for s, h in zip(self.s, self.h):
+            s.pack_send(h.send.data_ptr())
+
+    def _unpack(self):
+        exchange_in_process(self.h)
+        for s, h in zip(self.s, self.h):
+            s.unpack_halo(h.recv.data_ptr())
+
+    def step(self, dt, want_rhstest=False):
+        if self.fresh:
+            for s in self.s:
+                s.compute_traces()
+            self._pack()
+            self._unpack()
+            self.fresh = False
+        for k in range(5):
+            want = want_rhstest and k == 4
+            if self.overlap:
+                for s in self.s:
+                    s.stage_update(k, dt, want, s.PART_BOUNDARY)
+                self._pack()
+                for s in self.s:
+                    s.stage_update(k, dt, want, s.PART_INTERIOR)
+                self._unpack()
+            else:
+                for s in self.s:
+                    s.stage_update(k, dt, want, s.PART_ALL)
+                self._pack()
+                self._unpack()

@@ -211,6 +211,10 @@ int esdg_kernel_time_ms(esdg_ctx* ctx, const char* kernel, double* total_ms, int
 int esdg_enable_timing(esdg_ctx* ctx, int on);              /* CUDA-event timing per kernel */
 /* diagnostic: the kernels' own log (x > 0, normal) and exp (|x| < 700) evaluated on n host values */
 int esdg_debug_log_exp(int device, const double* x, int64_t n, double* log_out, double* exp_out);
+/* diagnostic: the tensor-product kernels' own two-point flux (logmean.jl:14-28 + euler_fluxes.jl:51-89) on n
+ * caller-supplied pairs.  UL, UR: [7][n] host doubles (rho, u, v, w, beta, log rho, log beta); F_out: [4][5][n] =
+ * the axis-aligned form (x flux) followed by the general form contracted with e_x, e_y, e_z */
+int esdg_debug_pair_flux(int device, const double* UL, const double* UR, int64_t n, double gamma, double* F_out);
 /* DFMA micro-benchmark: non-tensor FP64 peak of the device in TFLOP/s (roofline denominator) */
 int esdg_measure_fp64_peak(int device, double* tflops);
 const char* esdg_version(void);

@@ -33,8 +33,11 @@ def _pow(x, y):
 # --------------------------------------------------------------------------
 # logmean.jl:14-28
 def logmean(aL, aR, logL=None, logR=None):
-    aL = np.asarray(aL, dtype=np.float64)
-    aR = np.asarray(aR, dtype=np.float64)
+    aL = np.asarray(aL)
+    aR = np.asarray(aR)
+    if aL.dtype != np.longdouble:      # extended-precision arbiter (oracle/extended.py) keeps its dtype
+        aL = aL.astype(np.float64)
+        aR = aR.astype(np.float64)
     if logL is None:
         logL = _log(aL)  # logmean.jl:5-7
         logR = _log(aR)

@@ -129,12 +129,13 @@ def sparse_hadamard_sum(Qh, ops, vgeo, dim):
     nf = len(Qh)
     Nh, K = Qh[0].shape
     Qlog = (P._log(Qh[0]), P._log(Qh[-1]))
-    out = [np.zeros((Nh, K)) for _ in range(nf)]
+    dt = Qh[0].dtype
+    out = [np.zeros((Nh, K), dtype=dt) for _ in range(nf)]
     Qs = ops.Qsparse
     for i in range(Nh):
         Qi = tuple(q[i] for q in Qh)
         Li = tuple(q[i] for q in Qlog)
-        acc = [np.zeros(K) for _ in range(nf)]
+        acc = [np.zeros(K, dtype=dt) for _ in range(nf)]
         for j in ops.Qnzids[i]:
             Qj = tuple(q[j] for q in Qh)
             Lj = tuple(q[j] for q in Qlog)
