@@ -236,6 +236,12 @@ class Solver:
     def trace_planes(self):
         return int(self._lib.esdg_trace_planes(self._ctx))
 
+    def kernel_path(self):
+        return self._lib.esdg_kernel_path(self._ctx).decode()
+
+    def hex_diag(self):
+        return self.kernel_path() == "hex_line_diag"
+
     # CNS across GPUs: the sigma traces are the second exchange of a stage (include/esdg_b200.h)
     SIGMA_PLANES = 6
 

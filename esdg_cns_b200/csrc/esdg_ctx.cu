@@ -183,16 +183,16 @@ int cns_stage(esdg_ctx* ctx, const double* Qsrc, int mode, double a, double b, d
 
 // ---- path selection: tensor-product hex kernels when the operators allow, else generic ----
 int total_partials(const esdg_ctx* ctx) {
-    if (!ctx->hex) return grid_blocks(ctx);
-    const long long EB = ctx->hex->EB, lo = ctx->bnd_lo, hi = ctx->bnd_hi;
-    return (int)((lo + EB - 1) / EB + (hi + EB - 1) / EB + (ctx->d.K - lo - hi + EB - 1) / EB);
+    // hex path: one slot per element (a batch writes the slot of its first element, the rest stay zero), so the
+    // deterministic reduction does not depend on which stage kernel / batch size / element split produced them
+    return ctx->hex ? (int)ctx->d.K : grid_blocks(ctx);
 }
 
 int reduce_rhstest(esdg_ctx* ctx, bool split) {
     // a split stage (boundary + interior launches) lays its partials out per range; an unsplit one
     // uses ceil(K/EB) slots
-    const int n = ctx->hex ? (split ? total_partials(ctx) : (int)((ctx->d.K + ctx->hex->EB - 1) / ctx->hex->EB))
-                           : grid_blocks(ctx);
+    (void)split;
+    const int n = total_partials(ctx);
     tick(ctx, "reduce_partials");
     k_reduce_partials<<<1, 256, 0, ctx->stream>>>(ctx->partials, n, ctx->rhstest_dev);
     tock(ctx);
@@ -492,10 +492,10 @@ static int finalize_cns(esdg_ctx* ctx) {
     const size_t nb = (size_t)grid_blocks(ctx);
     if ((rc = dev_alloc(ctx, &c.partial_visc, nb))) return rc;
     if ((rc = dev_alloc(ctx, &c.partial_vrhs, nb))) return rc;
-    CK(cudaMemset(c.partial_visc, 0, nb * sizeof(double)));
-    CK(cudaMemset(c.partial_vrhs, 0, nb * sizeof(double)));
-    CK(cudaMemset(c.sig, 0, (size_t)6 * d.Ns * d.K * sizeof(double)));
-    CK(cudaMemset(c.sig_tr, 0, (size_t)6 * ctx->trace_stride * sizeof(double)));
+    CK(cudaMemsetAsync(c.partial_visc, 0, nb * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(c.partial_vrhs, 0, nb * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(c.sig, 0, (size_t)6 * d.Ns * d.K * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(c.sig_tr, 0, (size_t)6 * ctx->trace_stride * sizeof(double), ctx->stream));
     return ESDG_OK;
 }
 
@@ -799,13 +799,13 @@ int esdg_finalize(esdg_ctx* ctx) {
     if ((rc = dev_alloc(ctx, &ctx->traces, (size_t)NF * ctx->trace_stride))) return rc;
     ctx->n_partials = (int)std::max<long long>(grid_blocks(ctx), d.K + 4);   // >= blocks of either path, any split
     if ((rc = dev_alloc(ctx, &ctx->partials, (size_t)ctx->n_partials))) return rc;
-    CK(cudaMemset(ctx->partials, 0, (size_t)ctx->n_partials * sizeof(double)));
+    CK(cudaMemsetAsync(ctx->partials, 0, (size_t)ctx->n_partials * sizeof(double), ctx->stream));
     if ((rc = dev_alloc(ctx, &ctx->rhstest_dev, 2))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->bad_flag, 1))) return rc;
-    CK(cudaMemset(ctx->bad_flag, 0, sizeof(int)));
-    CK(cudaMemset(ctx->res, 0, nstate * sizeof(double)));
-    CK(cudaMemset(ctx->traces, 0, (size_t)NF * ctx->trace_stride * sizeof(double)));
-    CK(cudaMemset(ctx->rhstest_dev, 0, 2 * sizeof(double)));
+    CK(cudaMemsetAsync(ctx->bad_flag, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->res, 0, nstate * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->traces, 0, (size_t)NF * ctx->trace_stride * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->rhstest_dev, 0, 2 * sizeof(double), ctx->stream));
     if (ctx->cns.on) {
         if ((rc = finalize_cns(ctx))) return rc;
     } else if (!ctx->cns.wall.empty() || !ctx->cns.lid.empty() || !ctx->cns.inflow.empty() || !ctx->cns.outflow.empty()) {
@@ -914,7 +914,7 @@ int esdg_lsrk45_step(esdg_ctx* ctx, double dt, int nsteps, double* rhstest_last)
 static int build_chunks(esdg_ctx* ctx) {
     const esdg_desc& d = ctx->d;
     const long long K = d.K;
-    const int EB = ctx->hex ? 2 * ctx->hex->EB : 1;               // even element offsets keep the TMA path aligned
+    const int EB = ctx->hex ? 6 * ctx->hex->EB_ws : 1;            // whole batches of either stage kernel per chunk
     int nchunk = (int)std::min<long long>(16, K / std::max<long long>(4096, EB));
     if (const char* ev = getenv("ESDG_HOST_CHUNKS")) nchunk = std::max(1, std::min(64, atoi(ev)));   // experiments
     if (nchunk < 2) nchunk = 1;
@@ -1051,6 +1051,13 @@ static double* cur_traces(esdg_ctx* ctx) { return ctx->hex ? ctx->hex->trace[ctx
 static int cur_planes(const esdg_ctx* ctx) { return ctx->hex ? ESDG_HEX_TRACE_PLANES : ctx->NF; }
 
 int esdg_trace_planes(esdg_ctx* ctx) { return ctx ? cur_planes(ctx) : 0; }
+
+const char* esdg_kernel_path(const esdg_ctx* ctx) {
+    if (!ctx || !ctx->finalized) return "";
+    if (ctx->cns.on) return "cns";
+    if (ctx->hex) return ctx->hex->diag ? "hex_line_diag" : "hex_line";
+    return "generic";
+}
 
 int esdg_set_send_list(esdg_ctx* ctx, const int64_t* idx, int64_t n) {
     int rc = require_ready(ctx, "esdg_set_send_list");

@@ -2,8 +2,7 @@
 #include "hex_fast.h"
 
 #include "ctx_util.h"
-#include "kernels_hex.cuh"
-#include "kernels_hex_line.cuh"
+#include "kernels_hex_ws.cuh"
 
 using namespace esdg;
 using namespace esdg_host;
@@ -112,41 +111,30 @@ void fill_hex_params(esdg_ctx* ctx, HexParams& p) {
 
 template <int n>
 int set_attrs(esdg_ctx* ctx) {
-    using D = HexDims<n>;
+    using TD = TraceDims<n>;
     using LD = LineDims<n>;
+    using WD = WsDims<n>;
     HexFast* h = ctx->hex;
-    const char* kv = getenv("ESDG_HEX_KERNEL");          // "node": the node-per-thread kernel (comparison runs)
-    h->line = !(kv && !strcmp(kv, "node"));
-    h->EB_tr = D::EB;
-    h->threads_tr = D::THREADS;
-    h->smem_traces = (size_t)(D::EB * 5 * D::Nq + 2 * n) * sizeof(double);
-    if (h->line) {
-        h->EB = LD::EB;
-        h->threads = LD::THREADS_LAUNCH;
-        h->smem_stage = (size_t)LD::SMEM_DOUBLES * sizeof(double);
-        if (const char* ex = getenv("ESDG_HEX_EXTRA_SMEM_KB")) h->smem_stage += (size_t)atoi(ex) * 1024;   // occupancy experiments
-        CK(cudaFuncSetAttribute(k_hex_stage_line<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage));
-        CK(cudaFuncSetAttribute(k_hex_stage_line<n, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage));
-        // persistent producer-warp variant (kernels_hex_line.cuh): measured 5.40 ms against 5.27 ms per stage for the
-        // one-shot kernel on 128x128x16 N=4 (the two resident CTAs already hide each other's loads), so it is opt-in:
-        // ESDG_HEX_PERSIST=1
-        const char* pv = getenv("ESDG_HEX_PERSIST");
-        h->persist = pv && atoi(pv) != 0;
-        h->smem_stage_p = (size_t)LineDimsP<n>::SMEM_DOUBLES * sizeof(double);
-        h->threads_p = LineDimsP<n>::THREADS;
-        CK(cudaFuncSetAttribute(k_hex_stage_line_p<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage_p));
-        CK(cudaFuncSetAttribute(k_hex_stage_line_p<n, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage_p));
-        int sms = 0;
-        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-        h->grid_p = sms * LD::MINB;
-    } else {
-        h->EB = D::EB;
-        h->threads = D::THREADS;
-        h->smem_stage = (size_t)D::SMEM_DOUBLES * sizeof(double);
-        CK(cudaFuncSetAttribute(k_hex_stage<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage));
-        CK(cudaFuncSetAttribute(k_hex_stage<n, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage));
-    }
+    // ESDG_HEX_KERNEL = "line": the one-shot kernel everywhere; "ws": the warp-specialised persistent kernel everywhere;
+    // default: persistent kernel for element ranges that fill the GPU, one-shot kernel for small ones
+    const char* kv = getenv("ESDG_HEX_KERNEL");
+    h->kernel_choice = kv && !strcmp(kv, "line") ? 1 : (kv && !strcmp(kv, "ws") ? 2 : 0);
+    h->EB_tr = TD::EB;
+    h->threads_tr = TD::THREADS;
+    h->smem_traces = (size_t)TD::SMEM_DOUBLES * sizeof(double);
+    h->EB = LD::EB;
+    h->threads = LD::THREADS;
+    h->smem_stage = (size_t)LD::SMEM_DOUBLES * sizeof(double);
+    h->EB_ws = WD::EB;
+    h->threads_ws = WD::THREADS;
+    h->smem_ws = (size_t)WD::SMEM_DOUBLES * sizeof(double);
+    CK(cudaFuncSetAttribute(k_hex_stage_line<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage));
+    CK(cudaFuncSetAttribute(k_hex_stage_line<n, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_stage));
+    CK(cudaFuncSetAttribute(k_hex_stage_ws<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_ws));
+    CK(cudaFuncSetAttribute(k_hex_stage_ws<n, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_ws));
     CK(cudaFuncSetAttribute(k_hex_traces<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_traces));
+    CK(cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    if (const char* gv = getenv("ESDG_WS_GRID")) h->sms = std::max(1, atoi(gv));   // experiments
     return ESDG_OK;
 }
 
@@ -166,45 +154,25 @@ int launch_traces_n(esdg_ctx* ctx, const double* Q, long long e_begin = 0, long 
 }
 
 template <int n>
-int launch_stage_n(esdg_ctx* ctx, const HexParams& p, int blocks) {
+int launch_stage_n(esdg_ctx* ctx, const HexParams& p) {
     HexFast* h = ctx->hex;
     tick(ctx, "hex_stage");
-    if (h->line && h->persist) {
-        // full batches with 16-byte aligned runs go to the persistent kernel, a ragged tail to the one-shot kernel
-        using LD = LineDims<n>;
-        const bool aligned = (((p.q_stride | (p.e_begin * LD::Nq) | p.t_stride | (p.e_begin * LD::Nfq)) & 1) == 0) &&
-                             ((((size_t)p.Q | (size_t)p.res | (size_t)p.Lcur | (size_t)p.Tcur) & 15) == 0);
-        const long long nbatch = aligned ? p.e_count / LD::EB : 0;
-        if (nbatch > 0) {
-            HexParams pp = p;
-            pp.e_count = nbatch * LD::EB;
-            const int grid = (int)std::min<long long>(nbatch, h->grid_p);
-            if (h->diag)
-                k_hex_stage_line_p<n, true><<<grid, h->threads_p, h->smem_stage_p, ctx->stream>>>(pp);
-            else
-                k_hex_stage_line_p<n, false><<<grid, h->threads_p, h->smem_stage_p, ctx->stream>>>(pp);
-        }
-        const long long done = nbatch * LD::EB;
-        if (done < p.e_count) {
-            HexParams pt = p;
-            pt.e_begin = p.e_begin + done;
-            pt.e_count = p.e_count - done;
-            pt.partial = p.partial + nbatch;
-            const int tb = (int)((pt.e_count + h->EB - 1) / h->EB);
-            if (h->diag)
-                k_hex_stage_line<n, true><<<tb, h->threads, h->smem_stage, ctx->stream>>>(pt);
-            else
-                k_hex_stage_line<n, false><<<tb, h->threads, h->smem_stage, ctx->stream>>>(pt);
-        }
-    } else if (h->line) {
+    // the persistent kernel wants at least two batches per SM (its pipeline overlaps batch i with i +- 1)
+    const long long nbatch_ws = (p.e_count + h->EB_ws - 1) / h->EB_ws;
+    const bool ws = h->kernel_choice == 2 || (h->kernel_choice == 0 && nbatch_ws >= 2LL * h->sms);
+    if (ws) {
+        const int grid = (int)std::min<long long>(nbatch_ws, h->sms);
+        if (h->diag)
+            k_hex_stage_ws<n, true><<<grid, h->threads_ws, h->smem_ws, ctx->stream>>>(p);
+        else
+            k_hex_stage_ws<n, false><<<grid, h->threads_ws, h->smem_ws, ctx->stream>>>(p);
+    } else {
+        const int blocks = (int)((p.e_count + h->EB - 1) / h->EB);
         if (h->diag)
             k_hex_stage_line<n, true><<<blocks, h->threads, h->smem_stage, ctx->stream>>>(p);
         else
             k_hex_stage_line<n, false><<<blocks, h->threads, h->smem_stage, ctx->stream>>>(p);
-    } else if (h->diag)
-        k_hex_stage<n, true><<<blocks, h->threads, h->smem_stage, ctx->stream>>>(p);
-    else
-        k_hex_stage<n, false><<<blocks, h->threads, h->smem_stage, ctx->stream>>>(p);
+    }
     tock(ctx);
     CK(cudaGetLastError());
     return ESDG_OK;
@@ -308,7 +276,7 @@ int hexfast_try_create(esdg_ctx* ctx) {
     for (int q = 0; q < 2; ++q) {
         if ((rc = dev_alloc(ctx, &h->trace[q], (size_t)HEX_TP * ctx->trace_stride))) return rc;
         if ((rc = dev_alloc(ctx, &h->logs[q], (size_t)2 * d.Nq * d.K))) return rc;
-        CK(cudaMemset(h->trace[q], 0, (size_t)HEX_TP * ctx->trace_stride * sizeof(double)));
+        CK(cudaMemsetAsync(h->trace[q], 0, (size_t)HEX_TP * ctx->trace_stride * sizeof(double), ctx->stream));
     }
     return ESDG_OK;
 }
@@ -355,12 +323,11 @@ int hexfast_stage_range(esdg_ctx* ctx, const double* Q, int mode, double a, doub
     p.e_count = e_count;
     p.mode = mode;
     p.rk_a = a; p.rk_b = b; p.dt = dt;
-    const int blocks = (int)((e_count + h->EB - 1) / h->EB);
     switch (h->n) {
-        case 2: return launch_stage_n<2>(ctx, p, blocks);
-        case 3: return launch_stage_n<3>(ctx, p, blocks);
-        case 4: return launch_stage_n<4>(ctx, p, blocks);
-        default: return launch_stage_n<5>(ctx, p, blocks);
+        case 2: return launch_stage_n<2>(ctx, p);
+        case 3: return launch_stage_n<3>(ctx, p);
+        case 4: return launch_stage_n<4>(ctx, p);
+        default: return launch_stage_n<5>(ctx, p);
     }
 }
 
@@ -381,7 +348,8 @@ int hexfast_stage(esdg_ctx* ctx, const double* Q, int mode, double a, double b, 
     } else if (part == ESDG_PART_INTERIOR) {
         begin[0] = lo; count[0] = d.K - lo - hi;
     }
-    int block_off = part == ESDG_PART_INTERIOR ? (int)((lo + h->EB - 1) / h->EB + (hi + h->EB - 1) / h->EB) : 0;
+    if (want_rhstest && part != ESDG_PART_INTERIOR)   // one slot per element; batches write the slot of their first element
+        CK(cudaMemsetAsync(ctx->partials, 0, (size_t)d.K * sizeof(double), ctx->stream));
     for (int r = 0; r < nr; ++r) {
         if (count[r] <= 0) continue;
         HexParams p;
@@ -397,15 +365,12 @@ int hexfast_stage(esdg_ctx* ctx, const double* Q, int mode, double a, double b, 
         p.mode = mode;
         p.rk_a = a; p.rk_b = b; p.dt = dt;
         p.want_rhstest = want_rhstest;
-        p.partial = ctx->partials + block_off;
-        const int blocks = (int)((count[r] + h->EB - 1) / h->EB);
-        block_off += blocks;
         int rc;
         switch (h->n) {
-            case 2: rc = launch_stage_n<2>(ctx, p, blocks); break;
-            case 3: rc = launch_stage_n<3>(ctx, p, blocks); break;
-            case 4: rc = launch_stage_n<4>(ctx, p, blocks); break;
-            default: rc = launch_stage_n<5>(ctx, p, blocks); break;
+            case 2: rc = launch_stage_n<2>(ctx, p); break;
+            case 3: rc = launch_stage_n<3>(ctx, p); break;
+            case 4: rc = launch_stage_n<4>(ctx, p); break;
+            default: rc = launch_stage_n<5>(ctx, p); break;
         }
         if (rc) return rc;
     }
@@ -483,7 +448,7 @@ extern "C" int esdg_debug_pair_flux(int device, const double* UL, const double* 
 }
 
 #ifdef ESDG_PHASE_TIMING
-// debug build: read and clear the per-phase cycle counters of k_hex_stage_line
+// debug build: read and clear the per-activity cycle counters of k_hex_stage_ws
 extern "C" int esdg_debug_phase_cycles(unsigned long long* out16) {
     unsigned long long z[16] = {0};
     if (cudaMemcpyFromSymbol(out16, g_phase_cycles, sizeof z) != cudaSuccess) return ESDG_ECUDA;

@@ -1,24 +1,24 @@
-// Host side of the tensor-product hex path (kernels_hex.cuh).
+// Host side of the tensor-product hex path (hex_common.cuh, kernels_hex_line.cuh, kernels_hex_ws.cuh).
 #pragma once
 #include "esdg_ctx.h"
 
-constexpr int ESDG_HEX_TRACE_PLANES = 7;   // == esdg::HEX_TP (kernels_hex.cuh)
+constexpr int ESDG_HEX_TRACE_PLANES = 8;   // == esdg::HEX_TP (hex_common.cuh)
 
 struct HexFast {
     int n = 0;                 // N + 1
     bool diag = false;         // axis-aligned elements: only rxJ, syJ, tzJ non-zero
     double T[64], lm[8], lp[8], w[8];
-    double* trace[2] = {nullptr, nullptr};   // 7 planes x trace_stride each
+    double* trace[2] = {nullptr, nullptr};   // 8 planes x trace_stride each
     double* logs[2] = {nullptr, nullptr};    // 2 planes x Nq*K each (log rho, log beta at volume nodes)
     int prod = 0;              // buffer most recently produced (pack/unpack act on it)
     int cons = 0;              // buffer the running stage consumes
     size_t smem_stage = 0, smem_traces = 0;
-    int threads = 0, EB = 1;           // stage kernel launch shape
+    int threads = 0, EB = 1;           // one-shot stage kernel launch shape (kernels_hex_line.cuh)
     int threads_tr = 0, EB_tr = 1;     // k_hex_traces launch shape
-    bool line = true;                  // line-per-thread stage kernel (kernels_hex_line.cuh); false: node-per-thread
-    bool persist = false;              // persistent producer-warp variant of the line kernel
-    size_t smem_stage_p = 0;
-    int threads_p = 0, grid_p = 0;
+    int threads_ws = 0, EB_ws = 1;     // warp-specialised persistent stage kernel (kernels_hex_ws.cuh)
+    size_t smem_ws = 0;
+    int sms = 0;                       // persistent grid size
+    int kernel_choice = 0;             // 0: by range size, 1: one-shot, 2: persistent (ESDG_HEX_KERNEL)
 };
 
 enum { ESDG_PART_ALL = 0, ESDG_PART_BOUNDARY = 1, ESDG_PART_INTERIOR = 2 };

@@ -200,8 +200,11 @@ int esdg_cns_sigma_pass(esdg_ctx* ctx, int compute_rhstest);
 int esdg_pack_send_sigma(esdg_ctx* ctx, void* send_dev /* 6*n doubles, device */);
 int esdg_unpack_halo_sigma(esdg_ctx* ctx, const void* recv_dev /* 6*n_halo doubles, device */);
 /* number of double planes per trace point in the pack/unpack buffers (5 = Uf of the generic path,
- * 7 = rho,u,v,w,beta,log rho,log beta of the tensor-product hex path) */
+ * 8 = rho,u,v,w,beta,log rho,log beta,lambda of the tensor-product hex path) */
 int esdg_trace_planes(esdg_ctx* ctx);
+/* which kernel family a finalized context runs: "hex_line_diag" (tensor-product hexes, axis-aligned elements),
+ * "hex_line" (general affine hexes), "generic" (table-driven), "cns" */
+const char* esdg_kernel_path(const esdg_ctx* ctx);
 int esdg_read_rhstest(esdg_ctx* ctx, double* rhstest);
 int esdg_read_rhstest_visc(esdg_ctx* ctx, double* rhstest_visc);   /* CNS contexts */
 

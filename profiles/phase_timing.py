@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Per-phase cycle breakdown of k_hex_stage_line (debug build `make -C esdg_cns_b200/csrc timing`).
-usage (GPU box): ESDG_B200_LIB=esdg_cns_b200/libesdg_b200_timing.so python profiles/phase_timing.py"""
+"""Per-activity cycle breakdown of the warp-specialised hex stage kernel (debug build with -DESDG_PHASE_TIMING:
+`profiles/build_variant.sh timing -DESDG_PHASE_TIMING`).
+usage (GPU box): ESDG_B200_LIB=scratch/v/libesdg_b200_timing.so python profiles/phase_timing.py"""
 import ctypes, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -18,14 +19,19 @@ s.sync()
 lib = _lib.load()
 buf = (ctypes.c_ulonglong * 16)()
 lib.esdg_debug_phase_cycles(buf)
-s.lsrk45(1e-4, 2)
+nst = 10
+s.enable_timing(True)
+s.lsrk45(1e-4, nst // 5)
 s.sync()
 lib.esdg_debug_phase_cycles(buf)
-names = ["0 issue loads", "1 wait loads+sync", "2 A vol prims", "3 B surface", "4 sync", "5 C lines", "6 sync",
-         "7 E update", "8 sync", "9 F traces"]
-names += ["10 (bulk issue)", "11 (gather issue)", "12 (mapP ld issue)", "13 (mbar init)", "14 (tables+sync)"]
-tot = sum(buf[:15])
-ncta = 10 * (pmd.K // 2)
-for k, nm in enumerate(names):  # phase 0 = prefetch issue only when 10/11 are present
-    print(f"{nm:20s} {buf[k]/ncta:9.0f} cycles/CTA {100*buf[k]/tot:5.1f}%")
-print(f"total {tot/ncta:.0f} cycles per CTA (thread 0 timeline)")
+ms, nl = s.kernel_time_ms("hex_stage")
+names = {0: "L loop overhead", 1: "L wait full_wv (A done)", 2: "L wait full_tp (traces landed)", 3: "L line_compute", 4: "L wait empty_a3 (E done)",
+         5: "L line_store", 6: "P loop / lambda overhead", 7: "P wait full_a3 (lines done)", 8: "P E update", 9: "P bar", 10: "P F traces",
+         11: "P rhstest + bar", 12: "P wait empty_in", 13: "P issue loads + next mapP", 14: "P geo + A prims"}
+nbatch = nst * ((pmd.K + 2) // 3)
+L = sum(buf[k] for k in range(0, 6))
+P = sum(buf[k] for k in range(6, 15))
+for k in range(15):
+    tot = L if k < 6 else P
+    print(f"{k:2d} {names[k]:32s} {buf[k]/nbatch:9.0f} cycles/batch {100*buf[k]/tot:5.1f}% of the team's time")
+print(f"line team {L/nbatch:.0f}, point team {P/nbatch:.0f} cycles per batch of 3 elements (thread 0 of each team); {ms/nl:.3f} ms per stage (timing build)")
