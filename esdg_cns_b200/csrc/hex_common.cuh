@@ -387,7 +387,9 @@ __device__ __forceinline__ void line_vf_all(const Node (&nd)[n], const Node (&fn
 // all pairs, the surface flux at the line's two face points (dg3D_euler_hex.jl:182-197), the face rows
 // H = flux* -/+ sum_a l[a] F(a,face) and their lift onto the line's own nodes.  Result: acc[a][f] in the ROTATED
 // field order (rho, momentum d, c1, c2, E); line_store writes it back in physical order.
-template <int n, int EB, bool DIAG>
+// OWN_GATHER: the exterior traces of the line's two face points were fetched by THIS thread with cp.async
+// (line_gather below); they are awaited right before their first use.
+template <int n, int EB, bool DIAG, bool OWN_GATHER = false>
 __device__ __forceinline__ void line_compute(int l, const double* sWV, const double* sWF, const double* sP, const double* sGeo,
                                              const HexParams& p, double c_igm, double (&acc)[n][5]) {
     using G = HexGeom<n>;
@@ -433,6 +435,7 @@ __device__ __forceinline__ void line_compute(int l, const double* sWV, const dou
     }
     // surface flux at the two face points (lane = side): F_EC(M,P).nJ - LFc (U+ - U)
     VD<2> FS[5];
+    if (OWN_GATHER) cp_async_wait_all();
     {
         NodeV<2> M, P;
         VD<2> nJ[3], sJ, lamM, lamP;
@@ -473,6 +476,31 @@ __device__ __forceinline__ void line_compute(int l, const double* sWV, const dou
         const double Hm = FS[f][0] + h[0][f], Hp = FS[f][1] - h[1][f];
 #pragma unroll
         for (int a = 0; a < n; ++a) acc[a][f] = fma(p.lpw[a], Hp, fma(p.lmw[a], Hm, acc[a][f]));
+    }
+}
+
+// exterior-trace indices of the two face points of line l in the batch starting at element e0 ...
+template <int n, int EB>
+__device__ __forceinline__ void line_mapP(int l, long long e0, const HexParams& p, int (&ip)[2]) {
+    using G = HexGeom<n>;
+    const int eb = l / G::NL, ll = l - eb * G::NL;
+    const int d = ll / G::nfp, m = ll - d * G::nfp;
+    const int* mp = p.mapP + (e0 + eb) * G::Nfq + 2 * d * G::nfp + m;
+    ip[0] = mp[0];
+    ip[1] = mp[G::nfp];
+}
+// ... and the asynchronous copy of their 8 trace planes into this thread's own slots of sP
+template <int n, int EB>
+__device__ __forceinline__ void line_gather(int l, const int (&ip)[2], const HexParams& p, double* sP) {
+    using G = HexGeom<n>;
+    constexpr int EF = EB * G::Nfq;
+    const int eb = l / G::NL, ll = l - eb * G::NL;
+    const int d = ll / G::nfp, m = ll - d * G::nfp;
+    double* dst = sP + eb * G::Nfq + 2 * d * G::nfp + m;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+#pragma unroll
+        for (int q = 0; q < HEX_TP; ++q) cp_async8(dst + q * EF + side * G::nfp, p.Tcur + q * p.t_stride + ip[side]);
     }
 }
 

@@ -22,7 +22,7 @@ struct LineDims {
 // own traces (bulk copies when every run is 16-byte aligned, else 8-byte cp.async) and exterior traces (gather
 // through mapP) of the batch go in flight; `bar` must have been initialised for ONE arrival (the expect_tx)
 // plus the transaction bytes
-template <int n, int EB, int NT>
+template <int n, int EB, int NT, bool GATHER = true>
 __device__ __forceinline__ void issue_trace_loads(int t, int nb, long long e0, const HexParams& p, double* sWF, double* sP,
                                                   unsigned long long* bar, bool bulk, const int (&ipv)[(EB * HexGeom<n>::Nfq + NT - 1) / NT]) {
     using G = HexGeom<n>;
@@ -41,12 +41,14 @@ __device__ __forceinline__ void issue_trace_loads(int t, int nb, long long e0, c
             for (int q = 0; q < HEX_TP; ++q) cp_async8(sWF + q * EF + it, p.Tcur + q * p.t_stride + gf0 + it);
         }
     }
+    if (GATHER) {
 #pragma unroll
-    for (int r = 0; r < MAXF; ++r) {
-        const int it = t + r * NT;
-        if (it < nb * Nfq) {
+        for (int r = 0; r < MAXF; ++r) {
+            const int it = t + r * NT;
+            if (it < nb * Nfq) {
 #pragma unroll
-            for (int q = 0; q < HEX_TP; ++q) cp_async8(sP + q * EF + it, p.Tcur + q * p.t_stride + ipv[r]);
+                for (int q = 0; q < HEX_TP; ++q) cp_async8(sP + q * EF + it, p.Tcur + q * p.t_stride + ipv[r]);
+            }
         }
     }
 }

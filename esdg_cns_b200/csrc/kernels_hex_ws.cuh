@@ -41,9 +41,9 @@ struct WsDims {
     static constexpr int EN = EB * G::Nq, EF = EB * G::Nfq;
     static constexpr int ENP = wv_stride<n, EB>();                                 // plane stride of WV (even)
     static constexpr int WV_DOUBLES = 7 * ENP;
-    static constexpr int IN_DOUBLES = WV_DOUBLES + 2 * HEX_TP * EF;               // WV, WF, P of one buffer (even)
+    static constexpr int IN_DOUBLES = WV_DOUBLES + HEX_TP * EF;                   // WV, WF of one buffer (even)
     static constexpr int GEO_DOUBLES = EB * HEX_SGEO;                              // geometry records: ring of three batches
-    static constexpr int SMEM_DOUBLES = 2 * IN_DOUBLES + 3 * GEO_DOUBLES + 15 * EN + 5 * EN + 3 * n;
+    static constexpr int SMEM_DOUBLES = 2 * IN_DOUBLES + HEX_TP * EF + 3 * GEO_DOUBLES + 15 * EN + 5 * EN + 3 * n;
 };
 
 #ifdef ESDG_PHASE_TIMING   // debug build only: cycles per activity (thread 0 of each team), summed over CTAs at kernel end
@@ -70,8 +70,9 @@ __global__ void __launch_bounds__(WsDims<n>::THREADS, 1) k_hex_stage_ws(const __
     extern __shared__ __align__(16) double sm[];
     __shared__ unsigned long long full_tp[2], full_wv[2], empty_in[2], full_a3, empty_a3;
     __shared__ double red[NPT / 32];
-    double* sIn = sm;                           // 2 x { WV[7][EN], WF[8][EF], P[8][EF] }
-    double* sGeo3 = sIn + 2 * D::IN_DOUBLES;    // 3 x geo[EB][40]: batch j uses slot j % 3 (its update runs two steps after its loads)
+    double* sIn = sm;                           // 2 x { WV[7][ENP], WF[8][EF] }
+    double* sPx = sIn + 2 * D::IN_DOUBLES;      // P[8][EF] exterior traces: every line thread fetches and reads only its own two points
+    double* sGeo3 = sPx + HEX_TP * EF;    // 3 x geo[EB][40]: batch j uses slot j % 3 (its update runs two steps after its loads)
     double* sA3 = sGeo3 + 3 * D::GEO_DOUBLES;   // [3][5][EN]
     double* sV = sA3 + 15 * EN;                 // [5][EN]
     double* s_lm = sV + 5 * EN;
@@ -107,18 +108,31 @@ __global__ void __launch_bounds__(WsDims<n>::THREADS, 1) k_hex_stage_ws(const __
         // ================================ line warps ================================================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ESDG_WS_LREGS));
         const double c_igm = 1.0 / (2.0 * (p.gamma - 1.0));
+        // exterior traces of this thread's two face points: indices read one batch ahead, copies issued as soon as the
+        // thread is done with the previous ones (no other thread touches these shared-memory slots)
+        const long long stride_e = (long long)gridDim.x * EB;
+        int ipn[2] = {0, 0};
+        {
+            const long long e0 = p.e_begin + (long long)blockIdx.x * EB;
+            const int nb = (int)min((long long)EB, e_end - e0);
+            if (tid < nb * NL) {
+                line_mapP<n, EB>(tid, e0, p, ipn);
+                line_gather<n, EB>(tid, ipn, p, sPx);
+            }
+        }
         unsigned it = 0;
         for (long long bi = blockIdx.x; bi < nbatch; bi += gridDim.x, ++it) {
             const int b = it & 1;
             const long long e0 = p.e_begin + bi * EB;
             const int nb = (int)min((long long)EB, e_end - e0);
+            const int nb1 = (int)max(0LL, min((long long)EB, e_end - (e0 + stride_e)));
             const double* sWV0 = sIn + b * D::IN_DOUBLES;
             const double* sWV = sWV0 + ((e0 * Nq) & 1);       // batch stored with the parity of its first global node index
             const double* sWF = sWV0 + D::WV_DOUBLES;
-            const double* sP = sWF + HEX_TP * EF;
             const double* sGeo = sGeo3 + (it % 3) * D::GEO_DOUBLES;
-            const bool active = tid < nb * NL;
+            const bool active = tid < nb * NL, active1 = tid < nb1 * NL;
             double acc[n][5];
+            if (active1) line_mapP<n, EB>(tid, e0 + stride_e, p, ipn);
             WS_MARK(0);
             mbar_wait(&full_wv[b], (it >> 1) & 1);
             WS_MARK(1);
@@ -129,10 +143,12 @@ __global__ void __launch_bounds__(WsDims<n>::THREADS, 1) k_hex_stage_ws(const __
             for (int a = 0; a < n; ++a)
 #pragma unroll
                 for (int f = 0; f < 5; ++f) acc[a][f] = 0.0 * sWV[a * 5 + f];
+            cp_async_wait_all();
 #else
-            if (active) line_compute<n, EB, DIAG>(tid, sWV, sWF, sP, sGeo, p, c_igm, acc);
+            if (active) line_compute<n, EB, DIAG, true>(tid, sWV, sWF, sPx, sGeo, p, c_igm, acc);
 #endif
             mbar_arrive(&empty_in[b]);
+            if (active1) line_gather<n, EB>(tid, ipn, p, sPx);
             WS_MARK(3);
             if (it > 0) mbar_wait(&empty_a3, (it - 1) & 1);
             WS_MARK(4);
@@ -148,16 +164,7 @@ __global__ void __launch_bounds__(WsDims<n>::THREADS, 1) k_hex_stage_ws(const __
         const bool bulk = trace_runs_aligned(p);
         const bool bulkq = ((p.q_stride & 1) == 0) && ((((size_t)p.Q | (size_t)p.Lcur) & 15) == 0);
         bool bad = false;
-        int ipv[MAXF];
-        {
-            const long long e0 = p.e_begin + (long long)blockIdx.x * EB;
-            const int nb = (int)max(0LL, min((long long)EB, e_end - e0));
-#pragma unroll
-            for (int r = 0; r < MAXF; ++r) {
-                const int k = pt + r * NPT;
-                ipv[r] = k < nb * Nfq ? p.mapP[e0 * Nfq + k] : 0;
-            }
-        }
+        int ipv[MAXF] = {};   // (the exterior traces are gathered by the line threads)
         // E and F of a batch whose line results are (about to be) in A3
         auto finish = [&](long long e0, int nb, unsigned j) {
             const double* sGeo = sGeo3 + (j % 3) * D::GEO_DOUBLES;
@@ -202,8 +209,7 @@ __global__ void __launch_bounds__(WsDims<n>::THREADS, 1) k_hex_stage_ws(const __
             const int b = j & 1;
             double* sWV = sIn + b * D::IN_DOUBLES;
             double* sWF = sWV + D::WV_DOUBLES;
-            double* sP = sWF + HEX_TP * EF;
-            issue_trace_loads<n, EB, NPT>(pt, nb, e0, p, sWF, sP, &full_tp[b], bulk, ipv);
+            issue_trace_loads<n, EB, NPT, false>(pt, nb, e0, p, sWF, nullptr, &full_tp[b], bulk, ipv);
             // Q (5 planes) and the log stash (2) into the WV planes.  Node k of the batch lives at WV[f][off + k] with
             // off = parity of its global node index, so that the even-aligned middle of every run moves as ONE 16-byte
             // aligned bulk copy; at most one leading / trailing double per plane goes by cp.async
@@ -237,14 +243,6 @@ __global__ void __launch_bounds__(WsDims<n>::THREADS, 1) k_hex_stage_ws(const __
 #pragma unroll
                     for (int f = 0; f < 5; ++f) prefetch_l2(p.res + f * p.q_stride + e0 * Nq + k);
                 }
-            }
-            // exterior-trace indices of this CTA's next batch: a whole iteration of latency slack
-            const long long e1 = e0 + (long long)gridDim.x * EB;
-            const int nb1 = (int)max(0LL, min((long long)EB, e_end - e1));
-#pragma unroll
-            for (int r = 0; r < MAXF; ++r) {
-                const int k = pt + r * NPT;
-                ipv[r] = k < nb1 * Nfq ? p.mapP[e1 * Nfq + k] : 0;
             }
         };
         // A: geometry records + conservative -> primitive in place (each thread converts the nodes it copied itself)
