@@ -380,7 +380,10 @@ __device__ __forceinline__ void line_vf_all(const Node (&nd)[n], const Node (&fn
 }
 
 #ifndef ESDG_LINE_WC
-#define ESDG_LINE_WC 2   // pairs evaluated together in the line problem
+#define ESDG_LINE_WC 2   // pairs evaluated together in the line problem (one-shot kernel: 168 registers)
+#endif
+#ifndef ESDG_LINE_WC_WS
+#define ESDG_LINE_WC_WS 3   // ... in the persistent kernel, whose line warps own 184 registers (measured: 2 -> 3 = -6 %, 4 = -3 %, 5 = +29 %)
 #endif
 
 // Line l of a batch of EB elements (EN = EB*Nq, EF = EB*Nfq are the plane strides of the shared arrays):
@@ -389,7 +392,7 @@ __device__ __forceinline__ void line_vf_all(const Node (&nd)[n], const Node (&fn
 // field order (rho, momentum d, c1, c2, E); line_store writes it back in physical order.
 // OWN_GATHER: the exterior traces of the line's two face points were fetched by THIS thread with cp.async
 // (line_gather below); they are awaited right before their first use.
-template <int n, int EB, bool DIAG, bool OWN_GATHER = false>
+template <int n, int EB, bool DIAG, bool OWN_GATHER = false, int WC = ESDG_LINE_WC>
 __device__ __forceinline__ void line_compute(int l, const double* sWV, const double* sWF, const double* sP, const double* sGeo,
                                              const HexParams& p, double c_igm, double (&acc)[n][5]) {
     using G = HexGeom<n>;
@@ -411,7 +414,7 @@ __device__ __forceinline__ void line_compute(int l, const double* sWV, const dou
 #pragma unroll
         for (int f = 0; f < 5; ++f) acc[a][f] = 0.0;
     // volume-volume pairs: acc_a += T[a][b] F(a,b), acc_b += T[b][a] F(a,b)
-    line_vv_all<n, DIAG, 0, ESDG_LINE_WC>(nd, acc, g0, g1, g2, c_igm, p);
+    line_vv_all<n, DIAG, 0, WC>(nd, acc, g0, g1, g2, c_igm, p);
     // volume-face pairs: node a against the two face points its line ends in
     Node fn[2];
     int fidx[2];
@@ -423,7 +426,7 @@ __device__ __forceinline__ void line_compute(int l, const double* sWV, const dou
     double h[2][5];
 #pragma unroll
     for (int f = 0; f < 5; ++f) h[0][f] = h[1][f] = 0.0;
-    line_vf_all<n, DIAG, 0, ESDG_LINE_WC>(nd, fn, acc, h, g0, g1, g2, c_igm, p);
+    line_vf_all<n, DIAG, 0, WC>(nd, fn, acc, h, g0, g1, g2, c_igm, p);
     if (DIAG) {   // pair_flux_v<.., true> returns F / g0: the single metric term, once per accumulated sum
 #pragma unroll
         for (int f = 0; f < 5; ++f) {

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(WsDims<n>::THREADS, 1) k_hex_stage_ws(const __
                 for (int f = 0; f < 5; ++f) acc[a][f] = 0.0 * sWV[a * 5 + f];
             cp_async_wait_all();
 #else
-            if (active) line_compute<n, EB, DIAG, true>(tid, sWV, sWF, sPx, sGeo, p, c_igm, acc);
+            if (active) line_compute<n, EB, DIAG, true, ESDG_LINE_WC_WS>(tid, sWV, sWF, sPx, sGeo, p, c_igm, acc);
 #endif
             mbar_arrive(&empty_in[b]);
             if (active1) line_gather<n, EB>(tid, ipn, p, sPx);

@@ -17,8 +17,13 @@ s.upload(Q)
 s.lsrk45(1e-4, 3)
 s.sync()
 s.enable_timing(True)
-s.lsrk45(1e-4, 5)
-s.sync()
-ms, nl = s.kernel_time_ms("hex_stage")
+best, prev = 1e9, (0.0, 0)
+for rep in range(4):
+    s.lsrk45(1e-4, 4)
+    s.sync()
+    ms, nl = s.kernel_time_ms("hex_stage")
+    best = min(best, (ms - prev[0]) / (nl - prev[1]))
+    prev = (ms, nl)
+ms, nl = best, 1
 Q1 = s.download()
-print(f"{os.environ.get('ESDG_B200_LIB', 'default')} LF={os.environ.get('LF', '.25')}: {ms/nl:.3f} ms/stage  finite={all(np.isfinite(q).all() for q in Q1)}  chk={sum(float(q.sum()) for q in Q1):.12e}")
+print(f"{os.environ.get('ESDG_B200_LIB', 'default')} LF={os.environ.get('LF', '.25')}: {ms/nl:.3f} ms/stage (best of 4 x 20 stages)  finite={all(np.isfinite(q).all() for q in Q1)}  chk={sum(float(q.sum()) for q in Q1):.12e}")

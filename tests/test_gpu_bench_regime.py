@@ -120,8 +120,10 @@ def test_hex_rhs_at_bench_resolution(N, K1D, which, lf):
           f"vs 80-bit: gpu {e_gpu_t:.2e} numpy {e_np_t:.2e} C {e_c_t:.2e}")
     if which == "tgv":       # whole 128^3 field: 100 % / 90 %; this sub-box sits where the pressure gradient is large
         assert st["rho"][0] > .9 and st["beta"][0] > .5 and st["beta"][1] > .02
-    elif which == "taylor":
+    elif which == "taylor" and N == 4:
         assert st["rho"][0] == 1.0 and st["beta"][0] == 1.0       # nothing but the Taylor branch
+        # (N = 3: the entropy-projected face densities differ from the nodal ones by 3e-4, so a quarter of the
+        #  volume-face pairs sit just above the switch -- the well-conditioned LOG branch at rho ~ 1, see hex_common.cuh)
     else:
         assert st["rho"][1] + st["beta"][1] > .02                 # pairs next to the switch exist
     # float64 rounding cloud of the reference formulas on this state: the kernel must sit inside it
