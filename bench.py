@@ -243,7 +243,16 @@ def run_ours(args):
         h[...] = q
     del Q0
     s.upload(host)
-    stepper = H.GpuSlabStepper(s, md, dist, torch, device, overlap=not args.no_overlap) if world > 1 else None
+    # N > 1: the context owns its NCCL communicator (esdg_comm_init) and esdg_lsrk45_step does the halo exchange
+    # itself; --py-halo keeps the host-driven exchange (torch.distributed p2p + staging copies) for comparison
+    stepper = None
+    if world > 1:
+        if args.py_halo:
+            stepper = H.GpuSlabStepper(s, md, dist, torch, device, overlap=not args.no_overlap)
+        else:
+            if args.no_overlap:
+                os.environ["ESDG_COMM_NO_OVERLAP"] = "1"
+            H.attach_comm(s, md, dist, torch, device)
 
     def step():
         if stepper is None:
@@ -281,14 +290,15 @@ def run_ours(args):
     ktimes = {k: s.kernel_time_ms(k) for k in ("hex_stage", "hex_traces", "generic_rhs", "generic_traces", "pack_send")}
     # ---- end to end through the host-buffer API ---------------------------------------------
     def e2e_step():
-        if stepper is None:
+        if world == 1:
             # one call of the host-buffer API: H2D of this step's input from pinned memory, 5 stages, D2H of the
             # result -- all inside the timed region; the library runs the stages as a wavefront over element chunks
             # behind the upload and starts each chunk's download behind its last stage
             s.lsrk45_host(host, dt, 1)
             return
         s.upload(host)           # H2D of this step's input from pinned memory (+ sync)
-        stepper.mark_fresh()
+        if stepper is not None:
+            stepper.mark_fresh()
         step()
         s.download(host)         # D2H of the step's result (synchronous)
 
@@ -333,7 +343,7 @@ def run_ours(args):
             "config": {"workload": f"tgv_hex_N{N}_{Kx}x{Ky}x{Kzl}_per_gpu", "N": N, "elements_per_gpu": K,
                        "global_mesh": [Kx, Ky, Kz], "dof_per_gpu": dof, "stages_per_step": 5, "dt": dt,
                        "l2_policy": f"state {dof * 8 * 2 / 1e9:.2f} GB/GPU streamed every stage (>> 126 MB L2), no flush needed",
-                       "parallelism": f"z-slab x{world}", "finite": finite, "cpus_bound_per_rank": numa},
+                       "parallelism": f"z-slab x{world}", "halo_exchange": ("none" if world == 1 else "host-driven (torch.distributed)" if args.py_halo else "in-library NCCL (esdg_comm_init)"), "finite": finite, "cpus_bound_per_rank": numa},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(dom_name, K), "kernel": dom_name, "kernel_ms_per_launch": per_launch_s * 1e3,
                          "kernel_launches_timed": dom_n, "kernel_share_of_step": dom_ms / ms,
@@ -366,6 +376,7 @@ def main():
     ap.add_argument("--small", action="store_true", help="16x16x8 elements per GPU (debugging only; not a bench number)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange halos without overlapping interior work")
+    ap.add_argument("--py-halo", action="store_true", help="multi-GPU: host-driven halo exchange (torch.distributed) instead of the context's own NCCL communicator")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -72,6 +72,9 @@ _SIGNATURES = {
     "esdg_pack_send_sigma": (C.c_int, [C.c_void_p, C.c_void_p]),
     "esdg_unpack_halo_sigma": (C.c_int, [C.c_void_p, C.c_void_p]),
     "esdg_trace_planes": (C.c_int, [C.c_void_p]),
+    "esdg_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "esdg_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "esdg_comm_destroy": (C.c_int, [C.c_void_p]),
     "esdg_kernel_path": (C.c_char_p, [C.c_void_p]),
     "esdg_read_rhstest": (C.c_int, [C.c_void_p, C.c_void_p]),
     "esdg_read_rhstest_visc": (C.c_int, [C.c_void_p, C.c_void_p]),

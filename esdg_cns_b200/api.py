@@ -213,6 +213,16 @@ class Solver:
         idx = np.ascontiguousarray(np.asarray(idx0, dtype=np.int64) + 1)
         self._ck(self._lib.esdg_set_send_list(self._ctx, idx.ctypes.data, idx.size))
 
+    def comm_init(self, unique_id, nranks, rank, nb_rank, nb_send, nb_recv):
+        """Attach an NCCL communicator (esdg_comm_init): afterwards ``lsrk45`` steps the partitioned mesh by itself."""
+        r = np.ascontiguousarray(nb_rank, dtype=np.int32)
+        ns = np.ascontiguousarray(nb_send, dtype=np.int64)
+        nr = np.ascontiguousarray(nb_recv, dtype=np.int64)
+        uid = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+        assert uid.size == 128
+        self._ck(self._lib.esdg_comm_init(self._ctx, uid.ctypes.data, int(nranks), int(rank), int(r.size),
+                                          r.ctypes.data, ns.ctypes.data, nr.ctypes.data))
+
     def compute_traces(self):
         self._ck(self._lib.esdg_compute_traces(self._ctx))
 

@@ -255,6 +255,8 @@ const double RK4B[5] = {1432997174477.0 / 9575080441755.0, 5161836677717.0 / 136
 
 }  // namespace
 
+static void comm_destroy(esdg_ctx* ctx);
+
 extern "C" {
 
 const char* esdg_version(void) { return ESDG_VERSION; }
@@ -300,6 +302,7 @@ int esdg_destroy(esdg_ctx* ctx) {
     for (cudaEvent_t e : ctx->chunk_done) cudaEventDestroy(e);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    comm_destroy(ctx);
     for (void* p : ctx->allocs) cudaFree(p);
     hexfast_destroy(ctx);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -883,11 +886,17 @@ int esdg_rhs(esdg_ctx* ctx, const double* const* Q, double* const* rhs_out, int 
     return ESDG_OK;
 }
 
+static int comm_lsrk45(esdg_ctx* ctx, double dt, int nsteps, double* rhstest_last);
+
 int esdg_lsrk45_step(esdg_ctx* ctx, double dt, int nsteps, double* rhstest_last) {
     int rc = require_ready(ctx, "esdg_lsrk45_step");
     if (rc) return rc;
-    if (ctx->d.n_halo != 0)
-        return fail(ctx, ESDG_EINVAL, "esdg_lsrk45_step: context has halo points; drive stages with esdg_stage_update");
+    if (ctx->d.n_halo != 0 || ctx->comm) {
+        if (!ctx->comm)
+            return fail(ctx, ESDG_EINVAL, "esdg_lsrk45_step: context has halo points; attach a communicator (esdg_comm_init) or drive "
+                                          "stages with esdg_stage_update");
+        return comm_lsrk45(ctx, dt, nsteps, rhstest_last);
+    }
     for (int s = 0; s < nsteps; ++s)
         for (int k = 0; k < 5; ++k) {
             const int want = (rhstest_last != nullptr) && (s == nsteps - 1) && (k == 4);  // dg2D_euler_quad.jl:202
@@ -1346,6 +1355,262 @@ int esdg_kernel_time_ms(esdg_ctx* ctx, const char* kernel, double* total_ms, int
     auto it = ctx->time_acc.find(kernel);
     if (total_ms) *total_ms = it == ctx->time_acc.end() ? 0.0 : it->second.first;
     if (launches) *launches = it == ctx->time_acc.end() ? 0 : it->second.second;
+    return ESDG_OK;
+}
+
+// ---- multi-GPU inside the boundary: the context owns an NCCL communicator and a communication stream ------------------
+// (SURVEY 8b / 8e).  NCCL is resolved at run time (dlopen of libnccl.so.2 -- already in the process when the host is
+// PyTorch or NCCL.jl), so the library has no link-time dependency on it and loads on machines without NCCL.
+}  // extern "C"
+
+#include <dlfcn.h>
+
+namespace {
+typedef struct ncclComm* ncclComm_t;
+struct ncclUniqueId_t { char internal[128]; };
+enum { NCCL_DOUBLE = 8, NCCL_SUM = 0 };
+struct NcclApi {
+    int (*GetUniqueId)(ncclUniqueId_t*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId_t, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+
+const char* load_nccl() {
+    if (g_nccl.ok) return nullptr;
+    void* h = nullptr;
+    const char* names[] = {getenv("ESDG_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names)
+        if (nm && !h) h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return "libnccl.so.2 not found (set ESDG_NCCL_LIB or load NCCL in the host process first)";
+#define ESDG_NCCL_SYM(field, sym)                                         \
+    *(void**)(&g_nccl.field) = dlsym(h, sym);                             \
+    if (!g_nccl.field) return "libnccl: missing symbol " sym;
+    ESDG_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    ESDG_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    ESDG_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    ESDG_NCCL_SYM(GroupStart, "ncclGroupStart")
+    ESDG_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    ESDG_NCCL_SYM(Send, "ncclSend")
+    ESDG_NCCL_SYM(Recv, "ncclRecv")
+    ESDG_NCCL_SYM(AllReduce, "ncclAllReduce")
+    ESDG_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef ESDG_NCCL_SYM
+    g_nccl.ok = true;
+    return nullptr;
+}
+}  // namespace
+
+struct EsdgComm {
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+    std::vector<int> nb_rank;               // neighbours in send-list order
+    std::vector<long long> send_off, send_cnt, recv_off, recv_cnt;   // per neighbour, in trace points
+    cudaStream_t stream = nullptr;          // communication stream
+    cudaEvent_t packed = nullptr, landed = nullptr;
+    double* sendbuf = nullptr;              // [neighbour][plane][count]
+    int* send_slot = nullptr;               // send-list entry -> first entry of its neighbour's block
+    int* send_cntv = nullptr;               // send-list entry -> size of its neighbour's block
+    int max_planes = 0;
+    bool pending = false;                   // an exchange is in flight on the communication stream
+    bool fresh = true;                      // state uploaded, traces not yet computed / exchanged
+};
+
+#define NCK(call)                                                                                        \
+    do {                                                                                                 \
+        int r_ = (call);                                                                                 \
+        if (r_ != 0) return fail(ctx, ESDG_ENCCL, std::string(#call ": ") + g_nccl.GetErrorString(r_));  \
+    } while (0)
+
+static void comm_destroy(esdg_ctx* ctx) {
+    EsdgComm* c = ctx->comm;
+    if (!c) return;
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
+    if (c->packed) cudaEventDestroy(c->packed);
+    if (c->landed) cudaEventDestroy(c->landed);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    ctx->comm = nullptr;
+}
+
+namespace {
+// send-list entry i of neighbour b goes to sendbuf[planes*off_b + f*cnt_b + (i - off_b)]: one contiguous message per
+// (neighbour, plane), no staging copy between the gather and ncclSend
+__global__ void k_pack_send_nb(const double* __restrict__ traces, long long stride, const int* __restrict__ idx,
+                               const int* __restrict__ slot, const int* __restrict__ cntv, long long n, int nf,
+                               double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int j = idx[i], c = cntv[i];
+    const long long ob = slot[i], local = i - ob;   // slot[i] = first send-list entry of the neighbour the entry belongs to
+    for (int f = 0; f < nf; ++f) out[ob * nf + (long long)f * c + local] = traces[f * stride + j];
+}
+
+// start the exchange of `planes` trace planes of `tr` (halo tail after Nfq*K): pack on the compute stream, NCCL
+// send / recv on the communication stream behind it
+int comm_exchange_start(esdg_ctx* ctx, double* tr, int planes) {
+    EsdgComm* c = ctx->comm;
+    if (planes > c->max_planes) return fail(ctx, ESDG_EINVAL, "comm: too many trace planes");
+    if (ctx->n_send > 0) {
+        tick(ctx, "pack_send");
+        k_pack_send_nb<<<(unsigned)((ctx->n_send + 255) / 256), 256, 0, ctx->stream>>>(tr, ctx->trace_stride, ctx->send_idx, c->send_slot,
+                                                                                      c->send_cntv, ctx->n_send, planes, c->sendbuf);
+        tock(ctx);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(c->packed, ctx->stream));
+    CK(cudaStreamWaitEvent(c->stream, c->packed, 0));
+    const long long tail = (long long)ctx->d.Nfq * ctx->d.K;
+    const int nnb = (int)c->nb_rank.size();
+    NCK(g_nccl.GroupStart());
+    for (int b = 0; b < nnb; ++b)
+        for (int f = 0; f < planes; ++f)
+            if (c->send_cnt[b] > 0 && c->nb_rank[b] >= 0)
+                NCK(g_nccl.Send(c->sendbuf + c->send_off[b] * planes + (long long)f * c->send_cnt[b], (size_t)c->send_cnt[b], NCCL_DOUBLE,
+                                c->nb_rank[b], c->comm, c->stream));
+    // receives in reverse neighbour order: with two ranks and a periodic direction both messages of a plane travel
+    // between the same pair, and the peer's "to its lower neighbour" block is my "from my upper neighbour" block
+    for (int b = nnb - 1; b >= 0; --b)
+        for (int f = 0; f < planes; ++f)
+            if (c->recv_cnt[b] > 0 && c->nb_rank[b] >= 0)
+                NCK(g_nccl.Recv(tr + (long long)f * ctx->trace_stride + tail + c->recv_off[b], (size_t)c->recv_cnt[b], NCCL_DOUBLE,
+                                c->nb_rank[b], c->comm, c->stream));
+    NCK(g_nccl.GroupEnd());
+    CK(cudaEventRecord(c->landed, c->stream));
+    c->pending = true;
+    return ESDG_OK;
+}
+
+int comm_exchange_finish(esdg_ctx* ctx) {
+    EsdgComm* c = ctx->comm;
+    if (c->pending) {
+        CK(cudaStreamWaitEvent(ctx->stream, c->landed, 0));
+        c->pending = false;
+    }
+    return ESDG_OK;
+}
+}  // namespace
+
+// LSRK45 on a partitioned mesh (one context per rank).  Euler, tensor-product hexes: per stage the boundary-layer
+// elements first, their new traces packed and sent while the interior elements are updated, the halo received straight
+// into the tail of the trace planes the NEXT stage reads.  Other paths: stage, then exchange.  CNS: two exchanges per
+// stage (sigma traces, entropy-variable traces).
+static int comm_lsrk45(esdg_ctx* ctx, double dt, int nsteps, double* rhstest_last) {
+    EsdgComm* c = ctx->comm;
+    int rc;
+    const int planes = cur_planes(ctx);
+    if (c->fresh || !ctx->traces_valid) {
+        if ((rc = do_traces(ctx, ctx->Q))) return rc;
+        ctx->traces_valid = true;
+        if ((rc = comm_exchange_start(ctx, cur_traces(ctx), planes))) return rc;
+        if ((rc = comm_exchange_finish(ctx))) return rc;
+        c->fresh = false;
+    }
+    const bool overlap = ctx->hex != nullptr && !getenv("ESDG_COMM_NO_OVERLAP");
+    for (int s = 0; s < nsteps; ++s)
+        for (int k = 0; k < 5; ++k) {
+            const int want = (rhstest_last != nullptr) && (s == nsteps - 1) && (k == 4);
+            if (ctx->cns.on) {
+                if ((rc = cns_sigma_pass(ctx, ctx->Q, want))) return rc;
+                ctx->cns.sigma_valid = true;
+                if ((rc = comm_exchange_start(ctx, ctx->cns.sig_tr, 6))) return rc;
+                if ((rc = comm_exchange_finish(ctx))) return rc;
+                if ((rc = do_stage(ctx, ctx->Q, 1, RK4A[k], RK4B[k], dt, want, ESDG_PART_ALL))) return rc;
+                if ((rc = comm_exchange_start(ctx, cur_traces(ctx), planes))) return rc;
+                if ((rc = comm_exchange_finish(ctx))) return rc;
+            } else if (overlap) {
+                if ((rc = do_stage(ctx, ctx->Q, 1, RK4A[k], RK4B[k], dt, want, ESDG_PART_BOUNDARY))) return rc;
+                if ((rc = comm_exchange_start(ctx, cur_traces(ctx), planes))) return rc;
+                if ((rc = do_stage(ctx, ctx->Q, 1, RK4A[k], RK4B[k], dt, want, ESDG_PART_INTERIOR))) return rc;
+                if ((rc = comm_exchange_finish(ctx))) return rc;
+            } else {
+                if ((rc = do_stage(ctx, ctx->Q, 1, RK4A[k], RK4B[k], dt, want, ESDG_PART_ALL))) return rc;
+                if ((rc = comm_exchange_start(ctx, cur_traces(ctx), planes))) return rc;
+                if ((rc = comm_exchange_finish(ctx))) return rc;
+            }
+        }
+    if (rhstest_last) {
+        // entropy residual of the whole mesh: sum of the ranks' partials (2 doubles: total, viscous)
+        NCK(g_nccl.AllReduce(ctx->rhstest_dev, ctx->rhstest_dev, 2, NCCL_DOUBLE, NCCL_SUM, c->comm, ctx->stream));
+        CK(cudaMemcpyAsync(rhstest_last, ctx->rhstest_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        return check_bad(ctx);
+    }
+    return ESDG_OK;
+}
+
+extern "C" {
+
+int esdg_comm_unique_id(void* id128) {
+    if (!id128) return ESDG_EINVAL;
+    if (load_nccl()) return ESDG_ENCCL;
+    ncclUniqueId_t id;
+    if (g_nccl.GetUniqueId(&id) != 0) return ESDG_ENCCL;
+    std::memcpy(id128, &id, sizeof id);
+    return ESDG_OK;
+}
+
+int esdg_comm_init(esdg_ctx* ctx, const void* id128, int nranks, int rank, int n_neighbours, const int* nb_rank,
+                   const int64_t* nb_send, const int64_t* nb_recv) {
+    int rc = require_ready(ctx, "esdg_comm_init");
+    if (rc) return rc;
+    if (!id128 || nranks < 1 || rank < 0 || rank >= nranks || n_neighbours < 0 || (n_neighbours && (!nb_rank || !nb_send || !nb_recv)))
+        return fail(ctx, ESDG_EINVAL, "esdg_comm_init: bad argument");
+    if (const char* e = load_nccl()) return fail(ctx, ESDG_ENCCL, std::string("esdg_comm_init: ") + e);
+    long long ns = 0, nr = 0;
+    for (int b = 0; b < n_neighbours; ++b) {
+        if (nb_rank[b] < -1 || nb_rank[b] >= nranks || nb_send[b] < 0 || nb_recv[b] < 0) return fail(ctx, ESDG_EINVAL, "esdg_comm_init: bad neighbour entry");
+        ns += nb_send[b];
+        nr += nb_recv[b];
+    }
+    if (ns != ctx->n_send) return fail(ctx, ESDG_EINVAL, "esdg_comm_init: neighbour send counts do not add up to the send list (esdg_set_send_list)");
+    if (nr != ctx->d.n_halo) return fail(ctx, ESDG_EINVAL, "esdg_comm_init: neighbour receive counts do not add up to desc.n_halo");
+    comm_destroy(ctx);
+    EsdgComm* c = new EsdgComm();
+    ctx->comm = c;
+    c->nranks = nranks;
+    c->rank = rank;
+    std::vector<int> slot((size_t)ns), cntv((size_t)ns);
+    long long so = 0, ro = 0;
+    for (int b = 0; b < n_neighbours; ++b) {
+        c->nb_rank.push_back(nb_rank[b]);
+        c->send_off.push_back(so);
+        c->send_cnt.push_back(nb_send[b]);
+        c->recv_off.push_back(ro);
+        c->recv_cnt.push_back(nb_recv[b]);
+        for (long long i = 0; i < nb_send[b]; ++i) { slot[(size_t)(so + i)] = (int)so; cntv[(size_t)(so + i)] = (int)nb_send[b]; }
+        so += nb_send[b];
+        ro += nb_recv[b];
+    }
+    c->max_planes = std::max(8, ctx->NF + 2);
+    if ((rc = dev_upload(ctx, &c->send_slot, slot))) return rc;
+    if ((rc = dev_upload(ctx, &c->send_cntv, cntv))) return rc;
+    if ((rc = dev_alloc(ctx, &c->sendbuf, (size_t)std::max<long long>(1, ns) * c->max_planes))) return rc;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->packed, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->landed, cudaEventDisableTiming));
+    // The halo messages are small (a few MB per neighbour and stage) and hide behind the interior elements: ONE p2p
+    // channel (= one NCCL CTA per direction) keeps NCCL out of the way of the persistent stage kernel, which takes every
+    // register of the SMs it runs on (hex_fast.cu leaves comm_sms SMs free for it).  Measured on 2 x B200, 128x128x16
+    // elements per GPU: default channels 23.6 ms per step, 1 channel + 1 free SM 22.25 ms (1 GPU: 21.7 ms).
+    setenv("NCCL_MAX_P2P_NCHANNELS", "1", 0);
+    setenv("NCCL_MIN_P2P_NCHANNELS", "1", 0);
+    ncclUniqueId_t id;
+    std::memcpy(&id, id128, sizeof id);
+    NCK(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
+    return ESDG_OK;
+}
+
+int esdg_comm_destroy(esdg_ctx* ctx) {
+    if (!ctx) return ESDG_EINVAL;
+    comm_destroy(ctx);
     return ESDG_OK;
 }
 

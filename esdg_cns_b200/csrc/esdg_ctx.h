@@ -114,6 +114,7 @@ struct esdg_ctx {
     std::vector<unsigned long long> chunk_dep;   // bit c' set: the stage of this chunk reads traces of chunk c'
     std::vector<long long> chunk_begin; // nchunk + 1 element offsets
     long long bnd_lo = 0, bnd_hi = 0;   // leading / trailing elements whose traces are sent to neighbours
+    struct EsdgComm* comm = nullptr;    // NCCL communicator + neighbour lists (esdg_comm_init)
     bool res_zero = true;
 
     // accounting

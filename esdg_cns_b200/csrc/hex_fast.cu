@@ -135,6 +135,8 @@ int set_attrs(esdg_ctx* ctx) {
     CK(cudaFuncSetAttribute(k_hex_traces<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_traces));
     CK(cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, ctx->device));
     if (const char* gv = getenv("ESDG_WS_GRID")) h->sms = std::max(1, atoi(gv));   // experiments
+    h->comm_sms = 2;
+    if (const char* cv = getenv("ESDG_COMM_SMS")) h->comm_sms = std::max(0, atoi(cv));
     return ESDG_OK;
 }
 
@@ -154,14 +156,16 @@ int launch_traces_n(esdg_ctx* ctx, const double* Q, long long e_begin = 0, long 
 }
 
 template <int n>
-int launch_stage_n(esdg_ctx* ctx, const HexParams& p) {
+int launch_stage_n(esdg_ctx* ctx, const HexParams& p, int reserve_sms = 0) {
     HexFast* h = ctx->hex;
     tick(ctx, "hex_stage");
     // the persistent kernel wants at least two batches per SM (its pipeline overlaps batch i with i +- 1)
     const long long nbatch_ws = (p.e_count + h->EB_ws - 1) / h->EB_ws;
     const bool ws = h->kernel_choice == 2 || (h->kernel_choice == 0 && nbatch_ws >= 2LL * h->sms);
     if (ws) {
-        const int grid = (int)std::min<long long>(nbatch_ws, h->sms);
+        // the persistent CTAs take every register of their SM: while a halo exchange is in flight a few SMs stay free
+        // for the NCCL send / receive kernels, which could otherwise not start before this launch has drained
+        const int grid = (int)std::min<long long>(nbatch_ws, std::max(1, h->sms - reserve_sms));
         if (h->diag)
             k_hex_stage_ws<n, true><<<grid, h->threads_ws, h->smem_ws, ctx->stream>>>(p);
         else
@@ -366,11 +370,12 @@ int hexfast_stage(esdg_ctx* ctx, const double* Q, int mode, double a, double b, 
         p.rk_a = a; p.rk_b = b; p.dt = dt;
         p.want_rhstest = want_rhstest;
         int rc;
+        const int reserve = (part == ESDG_PART_INTERIOR) ? h->comm_sms : 0;
         switch (h->n) {
-            case 2: rc = launch_stage_n<2>(ctx, p); break;
-            case 3: rc = launch_stage_n<3>(ctx, p); break;
-            case 4: rc = launch_stage_n<4>(ctx, p); break;
-            default: rc = launch_stage_n<5>(ctx, p); break;
+            case 2: rc = launch_stage_n<2>(ctx, p, reserve); break;
+            case 3: rc = launch_stage_n<3>(ctx, p, reserve); break;
+            case 4: rc = launch_stage_n<4>(ctx, p, reserve); break;
+            default: rc = launch_stage_n<5>(ctx, p, reserve); break;
         }
         if (rc) return rc;
     }

@@ -18,6 +18,7 @@ struct HexFast {
     int threads_ws = 0, EB_ws = 1;     // warp-specialised persistent stage kernel (kernels_hex_ws.cuh)
     size_t smem_ws = 0;
     int sms = 0;                       // persistent grid size
+    int comm_sms = 2;                  // SMs left free for NCCL while the interior part of a split stage runs (ESDG_COMM_SMS)
     int kernel_choice = 0;             // 0: by range size, 1: one-shot, 2: persistent (ESDG_HEX_KERNEL)
 };
 

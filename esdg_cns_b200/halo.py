@@ -9,6 +9,32 @@ receives the matching layers into the halo tail that ``mapP`` points at
 import numpy as np
 
 
+def attach_comm(solver, md, dist, torch, device):
+    """Give a slab context its own NCCL communicator (include/esdg_b200.h: esdg_comm_*).  ``torch.distributed`` only
+    carries the 128-byte unique id from rank 0 to the others; the halo exchange itself -- pack, ncclSend / ncclRecv
+    straight into the halo tail, overlap with the interior elements, all-reduce of rhstest -- then runs inside
+    ``esdg_lsrk45_step`` (``Solver.lsrk45``).  A Julia host does the same with MPI.jl / Distributed for the id."""
+    from . import _lib as L
+    import ctypes as C
+    send = np.concatenate([md.send_lower, md.send_upper])
+    solver.set_send_list(send)
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if dist.get_rank() == 0:
+        buf = (C.c_ubyte * 128)()
+        rc = L.load().esdg_comm_unique_id(buf)
+        if rc:
+            raise L.EsdgError(rc, "esdg_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        uid = torch.tensor(list(buf), dtype=torch.uint8)
+    uid = uid.to(device)
+    dist.broadcast(uid, 0)
+    half = int(md.n_halo) // 2
+    # neighbour order = block order in the send list and in the halo tail: lower first, then upper (-1: no partner)
+    nb = [-1 if md.lower_rank is None else md.lower_rank, -1 if md.upper_rank is None else md.upper_rank]
+    ns = [md.send_lower.size, md.send_upper.size]
+    nr = [half, half]
+    solver.comm_init(uid.cpu().numpy().tobytes(), dist.get_world_size(), dist.get_rank(), nb, ns, nr)
+
+
 class SlabHalo:
     def __init__(self, md, nf, dist, torch, device):
         self.dist, self.torch = dist, torch

@@ -32,7 +32,7 @@ typedef enum {
     ESDG_OK = 0,
     ESDG_EINVAL = 1,  /* bad argument / missing operator / mesh not as declared */
     ESDG_ECUDA = 2,   /* CUDA runtime error (esdg_last_error has the string)    */
-    ESDG_ENCCL = 3,   /* reserved                                               */
+    ESDG_ENCCL = 3,   /* NCCL call failed / libnccl not found (esdg_comm_*)      */
     ESDG_ENOMEM = 4,  /* device allocation failed                               */
     ESDG_ESTATE = 5   /* non-positive density/pressure met in rhs: the Julia
                          DomainError of log/sqrt (euler_variables.jl:67, :8)   */
@@ -202,6 +202,26 @@ int esdg_unpack_halo_sigma(esdg_ctx* ctx, const void* recv_dev /* 6*n_halo doubl
 /* number of double planes per trace point in the pack/unpack buffers (5 = Uf of the generic path,
  * 8 = rho,u,v,w,beta,log rho,log beta,lambda of the tensor-product hex path) */
 int esdg_trace_planes(esdg_ctx* ctx);
+
+/* ---- multi-GPU inside the boundary -----------------------------------------------------------------
+ * One context per rank (= per GPU); the context owns an NCCL communicator and a communication stream.  After
+ * esdg_comm_init, esdg_lsrk45_step runs the partitioned mesh by itself: per stage the boundary-layer elements are
+ * updated first, their new traces are gathered into one contiguous message per (neighbour, plane) and sent with
+ * ncclSend while the interior elements are updated; ncclRecv lands directly in the halo tail of the trace planes the
+ * next stage reads (no staging copies), and rhstest is all-reduced over the ranks.  The Julia caller needs no stepper of
+ * its own: create the id on rank 0 (esdg_comm_unique_id), broadcast its 128 bytes (MPI.jl / Distributed), call
+ * esdg_comm_init on every rank.  NCCL is resolved with dlopen("libnccl.so.2") (ESDG_NCCL_LIB overrides the name).
+ *   neighbours : in the order their blocks appear in the send list (esdg_set_send_list) and in the halo tail
+ *   nb_send[b] : number of send-list entries that go to neighbour b      (sum = length of the send list)
+ *   nb_recv[b] : number of halo points that come from neighbour b        (sum = desc.n_halo)
+ *   nb_rank[b] = -1: a block without a partner (physical boundary): nothing is sent or received, offsets still advance
+ * Stream contract: every kernel of a context runs on ITS stream (esdg_set_stream, default: an own non-blocking stream);
+ * device buffers handed to esdg_pack_send / esdg_unpack_halo by a host-driven exchange must be produced / consumed on
+ * that stream (or ordered against it with events). */
+int esdg_comm_unique_id(void* id128 /* out: 128 bytes */);
+int esdg_comm_init(esdg_ctx* ctx, const void* id128, int nranks, int rank, int n_neighbours, const int* nb_rank,
+                   const int64_t* nb_send, const int64_t* nb_recv);
+int esdg_comm_destroy(esdg_ctx* ctx);
 /* which kernel family a finalized context runs: "hex_line_diag" (tensor-product hexes, axis-aligned elements),
  * "hex_line" (general affine hexes), "generic" (table-driven), "cns" */
 const char* esdg_kernel_path(const esdg_ctx* ctx);

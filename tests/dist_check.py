@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--generic", type=int, default=0)
     ap.add_argument("--cns", type=int, default=0, help="1: compressible Navier-Stokes cavity on y-slabs of a quad mesh")
+    ap.add_argument("--ccomm", type=int, default=0, help="1: the context's own NCCL communicator (esdg_comm_init) instead of the host-driven exchange")
     a = ap.parse_args()
     if a.generic:
         os.environ["ESDG_FORCE_GENERIC"] = "1"
@@ -53,12 +54,22 @@ def main():
     Q0 = SD.primitive_to_conservative(*(lambda r, u, v, w, p: (r, (u, v, w), p))(*SD.taylor_green(x, y, z)))
     dt = 2e-3
     s = api.Solver(md, pops, device=lr, n_halo=md.n_halo, stream=torch.cuda.current_stream().cuda_stream)
-    st = H.GpuSlabStepper(s, md, dist, torch, dev, overlap=bool(a.overlap))
-    s.upload(Q0)
-    for k in range(a.steps):
-        st.step(dt, want_rhstest=(k == a.steps - 1))
-    rt_local = torch.tensor([s.read_rhstest()], dtype=torch.float64, device=dev)
-    dist.all_reduce(rt_local)                      # entropy residual: sum of the slab partials
+    if a.ccomm:
+        if not a.overlap:
+            os.environ["ESDG_COMM_NO_OVERLAP"] = "1"
+        H.attach_comm(s, md, dist, torch, dev)
+        s.upload(Q0)
+        rt = 0.0
+        for k in range(a.steps):
+            rt = s.lsrk45(dt, 1, want_rhstest=(k == a.steps - 1))
+        rt_local = torch.tensor([rt], dtype=torch.float64, device=dev)     # already all-reduced inside the library
+    else:
+        st = H.GpuSlabStepper(s, md, dist, torch, dev, overlap=bool(a.overlap))
+        s.upload(Q0)
+        for k in range(a.steps):
+            st.step(dt, want_rhstest=(k == a.steps - 1))
+        rt_local = torch.tensor([s.read_rhstest()], dtype=torch.float64, device=dev)
+        dist.all_reduce(rt_local)                      # entropy residual: sum of the slab partials
     Ql = np.stack(s.download())                    # (5, Nq, K_local)
     t = torch.from_numpy(np.ascontiguousarray(Ql)).to(dev)
     parts = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
@@ -106,12 +117,19 @@ def cns_check(a, rank, world, lr, dev, torch, dist, api, H, SD):
     md = SD.uniform_quad_mesh_md(prd, Kx, Ky, periodic=(False, False), yslab=(rank, world))
     dt = 2e-4
     s = api.Solver(md, pops, device=lr, n_halo=md.n_halo, cns=settings(md), stream=torch.cuda.current_stream().cuda_stream)
-    st = H.GpuSlabStepperCNS(s, md, dist, torch, dev)
-    s.upload(state(md))
-    for k in range(a.steps):
-        st.step(dt, want_rhstest=(k == a.steps - 1))
-    rt_local = torch.tensor([s.read_rhstest(), s.read_rhstest_visc()], dtype=torch.float64, device=dev)
-    dist.all_reduce(rt_local)
+    if a.ccomm:
+        H.attach_comm(s, md, dist, torch, dev)
+        s.upload(state(md))
+        for k in range(a.steps):
+            s.lsrk45(dt, 1, want_rhstest=(k == a.steps - 1))
+        rt_local = torch.tensor([s.read_rhstest(), s.read_rhstest_visc()], dtype=torch.float64, device=dev)
+    else:
+        st = H.GpuSlabStepperCNS(s, md, dist, torch, dev)
+        s.upload(state(md))
+        for k in range(a.steps):
+            st.step(dt, want_rhstest=(k == a.steps - 1))
+        rt_local = torch.tensor([s.read_rhstest(), s.read_rhstest_visc()], dtype=torch.float64, device=dev)
+        dist.all_reduce(rt_local)
     t = torch.from_numpy(np.ascontiguousarray(np.stack(s.download()))).to(dev)
     parts = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
     dist.gather(t, parts, dst=0)
