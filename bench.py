@@ -42,30 +42,19 @@ def load_peaks():
 
 
 def alg_bytes_per_element_stage(N, nf=5):
-    """B_alg = 8*Nf*(5*Ns + 2*Nfq) per element-stage (Q,res read+write, traces)."""
-    Ns, Nfq = (N + 1) ** 3, 6 * (N + 1) ** 2
-    return 8 * nf * (5 * Ns + 2 * Nfq)
+    from esdg_cns_b200 import roofline
+    return roofline.alg_bytes("hex", N)
 
 
 def alg_flops_per_element_stage(N):
-    """SURVEY 8(d) F_alg for collocated hexes (FMA = 2 flops; unordered pairs once; hand count +-15%)."""
-    n = N + 1
-    Ns, Nfq, Nh, d, nf = n ** 3, 6 * n * n, n ** 3 + 6 * n * n, 3, 5
-    P_sym = 3 * n * n * (n * (n - 1) // 2) + Nfq * n
-    nnz_Ef, nnz_Ph, nnz_L = Nfq * n, Ns * (1 + 2 * d), Ns * 2 * d
-    return (P_sym * 106 + Nfq * 114 + 2 * nf * (nnz_Ef + nnz_Ph + nnz_L) + Ns * (3 * d + 10) + Nfq * (3 * d + 14)
-            + Nh * (3 * d + 5) + 6 * Ns * nf)
+    from esdg_cns_b200 import roofline
+    return roofline.alg_flops("hex", N)
 
 
 def measured_traffic(kernel, K):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture."""
-    p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        with open(p) as fh:
-            t = json.load(fh).get(kernel)
-        if t and t.get("elements") == K:
-            return t["dram_bytes_per_launch"]
-    return None
+    """(dram bytes per launch, provenance) from the committed ncu capture; None when the capture is stale."""
+    from esdg_cns_b200 import roofline
+    return roofline.measured_traffic(kernel, K)
 
 
 def tgv_dt(N, K1D_global):
@@ -196,6 +185,66 @@ def bind_to_gpu_cpus(index):
     except Exception:
         pass
     return None
+
+
+# ------------------------------------------------------------------- the other BASELINE configs
+def other_configs(device, peak_gbs):
+    """BASELINE configs 4, 1 (operators at timing scale) and 3 timed in the same process (a few seconds each), so that
+    their numbers are driver-visible: DOF*stage/s with the state resident, ms per LSRK stage from CUDA events around
+    the kernels, ALGORITHMIC bytes per element-stage (esdg_cns_b200/roofline.py) and the fraction of the measured HBM
+    peak they amount to.  Config 2 (triangles) needs operators the product package does not build; it is measured in
+    tests/test_gpu_perf_report.py with oracle-built operators."""
+    from types import SimpleNamespace
+    from esdg_cns_b200 import api, setup_dg as SD, roofline as R
+    out = []
+
+    def run(name, solver, Q, dt, nf, Ns, Nfq, d, kernels, K, cns=False, nsteps=4):
+        solver.upload(Q)
+        solver.lsrk45(dt, 2)
+        solver.sync()
+        solver.enable_timing(True)
+        solver.lsrk45(dt, nsteps)
+        solver.sync()
+        ms = sum(solver.kernel_time_ms(k)[0] for k in kernels)
+        finite = all(np.isfinite(q).all() for q in solver.download())
+        solver.close()
+        per_stage = ms / (5 * nsteps)
+        B = R.alg_bytes_sizes(nf, Ns, Nfq, d, cns)
+        out.append({"config": name, "elements": int(K), "dof": int(nf * Ns * K), "ms_per_stage": per_stage,
+                    "value": nf * Ns * K / (per_stage * 1e-3), "unit": UNIT, "alg_bytes_per_element_stage": B,
+                    "achieved_gbs": B * K / (per_stage * 1e-3) / 1e9, "frac": B * K / (per_stage * 1e-3) / 1e9 / peak_gbs,
+                    "kernels": list(kernels), "finite": bool(finite)})
+
+    # config 4: hex N=3, 64^3, isentropic vortex extruded in z (SURVEY 8d)
+    N = 3
+    prd, pops = SD.reference_hex(N)
+    md = SD.uniform_hex_mesh_md(prd, (64, 64, 64), domain=((0, 20), (-5, 5), (-5, 5)))
+    x, y, z = SD.hex_node_coords(prd, md)
+    rho, u, v, p = SD.vortex(x, y)
+    Q = SD.primitive_to_conservative(rho, (u, v, 0 * u), p)
+    run("4: hex N=3 64^3 vortex (tensor-product kernels)", api.Solver(md, pops, device=device), Q, tgv_dt(N, 64) * 5 / np.pi, 5,
+        (N + 1) ** 3, 6 * (N + 1) ** 2, 3, ["hex_stage"], md.K)
+    del md, Q, x, y, z
+    # config 1 operators at timing scale: collocated quads N=3, 1024^2, periodic vortex
+    rd, ops = SD.reference_quad(N)
+    md = SD.uniform_quad_mesh_md(rd, 1024, 1024, domain=((0, 20), (-5, 5)))
+    rho, u, v, p = SD.vortex(md.xq, md.yq)
+    Q = SD.primitive_to_conservative(rho, (u, v), p)
+    run("1: quad N=3 1024^2 vortex (generic kernels)", api.Solver(md, ops, device=device), Q, 1e-4, 4, (N + 1) ** 2, 4 * (N + 1), 2,
+        ["generic_rhs", "generic_traces"], md.K)
+    del md, Q
+    # config 3: CNS lid-driven cavity, modal quads N=3, 512^2, BCTYPE 1, both dissipations on
+    rd, ops = SD.reference_quad_modal(N)
+    md = SD.uniform_quad_mesh_md(rd, 512, 512, periodic=(False, False))
+    bc = SD.cavity_bc_sets(md)
+    Re = 1000.0
+    st = SimpleNamespace(Re=Re, mu=1 / Re, lam=-2 / 3 / Re, Pr=.71, bctype=1, inviscid_dissp=True, viscous_dissp=True,
+                         wall=bc.wall, lid=bc.lid, vlid=bc.vlid, mapB=bc.mapB)
+    one = np.ones_like(md.x)
+    Q = SD.primitive_to_conservative(one, (0 * one, 0 * one), one / (.3 ** 2 * 1.4))
+    run("3: CNS quad N=3 512^2 cavity (BR1, wall BCs)", api.Solver(md, ops, cns=st, device=device), Q, 1e-5, 4, rd.r.size,
+        rd.rf.size, 2, ["cns_traces", "cns_sigma", "cns_rhs"], md.K, cns=True)
+    return out
 
 
 # ------------------------------------------------------------------------------------ our arm
@@ -345,7 +394,8 @@ def run_ours(args):
                        "l2_policy": f"state {dof * 8 * 2 / 1e9:.2f} GB/GPU streamed every stage (>> 126 MB L2), no flush needed",
                        "parallelism": f"z-slab x{world}", "halo_exchange": ("none" if world == 1 else "host-driven (torch.distributed)" if args.py_halo else "in-library NCCL (esdg_comm_init)"), "finite": finite, "cpus_bound_per_rank": numa},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(dom_name, K), "kernel": dom_name, "kernel_ms_per_launch": per_launch_s * 1e3,
+                         "traffic": measured_traffic(dom_name, K)[0], "traffic_source": measured_traffic(dom_name, K)[1],
+                         "kernel": dom_name, "kernel_ms_per_launch": per_launch_s * 1e3,
                          "kernel_launches_timed": dom_n, "kernel_share_of_step": dom_ms / ms,
                          "alg_bytes_per_element_stage": B_alg * share, "peak_source": peak_src,
                          "ns_per_element_stage": 1e9 * ms * 1e-3 / (args.steps * 5 * K)},
@@ -353,12 +403,18 @@ def run_ours(args):
                     "h2d_bytes_per_step": dof * 8, "d2h_bytes_per_step": dof * 8,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps},
             "fp64": {"achieved_tflops": fp64_tf, "peak_tflops_measured_dfma": pk.value, "peak_tflops_nominal": 37.2,
+                     "peak_source": "esdg_measure_fp64_peak: own DFMA micro-benchmark run on this GPU in this process (csrc/peak.cu); MEASURED_PEAKS.json has no FP64 entry",
                      "frac_of_measured": fp64_tf / pk.value if pk.value else None,
                      "alg_flops_per_element_stage": F_alg,
                      "note": "the stage kernel is FP64-pipe/latency bound, not HBM bound (profiles/)"},
             "gpu_launches": launches, "clocks": clocks,
             "kernels_ms": {k: {"total_ms": v[0], "launches": v[1]} for k, v in ktimes.items() if v[1]},
         }
+        if world == 1 and not args.small and not args.no_other:
+            s.close()
+            del s
+            torch.cuda.empty_cache()
+            line["other_configs"] = other_configs(local_rank, peak)
         if not args.no_cpu and world == 1:      # reported on rank 0 at N = 1 only
             line["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(line), flush=True)
@@ -375,6 +431,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--small", action="store_true", help="16x16x8 elements per GPU (debugging only; not a bench number)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-other", action="store_true", help="skip the other_configs block (BASELINE configs 1, 3, 4 at timing scale)")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange halos without overlapping interior work")
     ap.add_argument("--py-halo", action="store_true", help="multi-GPU: host-driven halo exchange (torch.distributed) instead of the context's own NCCL communicator")
     args = ap.parse_args()

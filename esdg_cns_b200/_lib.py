@@ -100,6 +100,12 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+        if "ESDG_B200_LIB" not in os.environ:      # (experiment builds carry other flags / hashes)
+            from .roofline import kernel_source_hash
+            built, now = lib.esdg_version().decode().rsplit("src=", 1)[-1], kernel_source_hash()
+            if built != now:
+                raise OSError(f"{LIB_PATH} was built from other sources (library {built}, tree {now}): "
+                              "run `make -C esdg_cns_b200/csrc` -- a stale prebuilt library is never used")
         _lib = lib
     return _lib
 

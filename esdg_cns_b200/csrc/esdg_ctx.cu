@@ -7,7 +7,11 @@
 
 using namespace esdg;
 
-#define ESDG_VERSION "esdg_b200 0.1 (sm_100a)"
+#ifndef ESDG_SRC_HASH
+#define ESDG_SRC_HASH "unknown"
+#endif
+// the source hash (Makefile) lets the loader refuse a stale prebuilt library: esdg_cns_b200/_lib.py recomputes it
+#define ESDG_VERSION "esdg_b200 0.2 (sm_100a) src=" ESDG_SRC_HASH
 #ifndef ESDG_GENERIC_COLL_REGS
 #define ESDG_GENERIC_COLL_REGS 96   // register cap of the generic rhs kernel on collocated 2-D elements (kernels_generic.cuh)
 #endif

@@ -23,20 +23,35 @@
 
 namespace esdg {
 
-#ifndef ESDG_WS_NPT
-#define ESDG_WS_NPT 128     // point threads (a multiple of 128: setmaxnreg acts on warpgroups)
+// Team sizes and register budgets (setmaxnreg acts on warpgroups: multiples of 128 threads; 256 x LREGS + NPT x PREGS
+// must fit the CTA's register pool = (256 + NPT) x the launch count).  N = 4: the line problem needs ~184 registers
+// (n+2 nodes, 5n accumulators, three pairs in flight), which leaves room for 4 point warps at 136.  Measured on the
+// bench slab (profiles/r2_ws_variants.txt): 8 point warps at 72-88 registers 5.8-7.3 ms, 4 at 104: 7.6, 4 at 120: 4.27,
+// 4 at 136: 4.11, 4 at 152 (lines 176): 4.48.  N <= 3: the line problem is smaller, both teams get 8 warps.
+#ifndef ESDG_WS_NPT5
+#define ESDG_WS_NPT5 128
 #endif
-#ifndef ESDG_WS_LREGS       // 256 x LREGS + NPT x PREGS must fit the CTA's register pool ((256 + NPT) x the launch count)
-#define ESDG_WS_LREGS (ESDG_WS_NPT == 128 ? 192 : 184)
+#ifndef ESDG_WS_LREGS5
+#define ESDG_WS_LREGS5 184
 #endif
-#ifndef ESDG_WS_PREGS
-#define ESDG_WS_PREGS (ESDG_WS_NPT == 128 ? 120 : 72)
+#ifndef ESDG_WS_PREGS5
+#define ESDG_WS_PREGS5 136
+#endif
+#ifndef ESDG_WS_NPT4
+#define ESDG_WS_NPT4 128
+#endif
+#ifndef ESDG_WS_LREGS4
+#define ESDG_WS_LREGS4 184
+#endif
+#ifndef ESDG_WS_PREGS4
+#define ESDG_WS_PREGS4 136
 #endif
 
 template <int n>
 struct WsDims {
     using G = HexGeom<n>;
-    static constexpr int NLT = 256, NPT = ESDG_WS_NPT, THREADS = NLT + NPT;
+    static constexpr int NLT = 256, NPT = n == 5 ? ESDG_WS_NPT5 : ESDG_WS_NPT4, THREADS = NLT + NPT;
+    static constexpr int LREGS = n == 5 ? ESDG_WS_LREGS5 : ESDG_WS_LREGS4, PREGS = n == 5 ? ESDG_WS_PREGS5 : ESDG_WS_PREGS4;
     static constexpr int EB = NLT / G::NL;                  // n = 5: 3 elements (225 lines), 4: 5, 3: 9, 2: 21
     static constexpr int EN = EB * G::Nq, EF = EB * G::Nfq;
     static constexpr int ENP = wv_stride<n, EB>();                                 // plane stride of WV (even)
@@ -106,7 +121,7 @@ __global__ void __launch_bounds__(WsDims<n>::THREADS, 1) k_hex_stage_ws(const __
 
     if (tid < NLT) {
         // ================================ line warps ================================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ESDG_WS_LREGS));
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(D::LREGS));
         const double c_igm = 1.0 / (2.0 * (p.gamma - 1.0));
         // exterior traces of this thread's two face points: indices read one batch ahead, copies issued as soon as the
         // thread is done with the previous ones (no other thread touches these shared-memory slots)
@@ -158,7 +173,7 @@ __global__ void __launch_bounds__(WsDims<n>::THREADS, 1) k_hex_stage_ws(const __
         }
     } else {
         // ================================ point warps ===============================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ESDG_WS_PREGS));
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(D::PREGS));
         const int pt = tid - NLT;
         constexpr int MAXF = (EF + NPT - 1) / NPT;
         const bool bulk = trace_runs_aligned(p);
