@@ -75,6 +75,14 @@ _SIGNATURES = {
     "esdg_comm_unique_id": (C.c_int, [C.c_void_p]),
     "esdg_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "esdg_comm_destroy": (C.c_int, [C.c_void_p]),
+    "esdg1d_create": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int] + [C.c_void_p] * 8 + [C.c_double] * 6 + [_PP]),
+    "esdg1d_destroy": (C.c_int, [C.c_void_p]),
+    "esdg1d_last_error": (C.c_char_p, [C.c_void_p]),
+    "esdg1d_upload_state": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "esdg1d_download_state": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "esdg1d_rhs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "esdg1d_ssprk3_step": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
+    "esdg1d_kernel_launches": (C.c_int64, [C.c_void_p]),
     "esdg_kernel_path": (C.c_char_p, [C.c_void_p]),
     "esdg_read_rhstest": (C.c_int, [C.c_void_p, C.c_void_p]),
     "esdg_read_rhstest_visc": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -166,6 +166,16 @@ class Solver:
     def download(self, out=None):
         if out is None:
             out = [np.empty((self.Ns, self.K), order="F") for _ in range(self.nf)]
+        else:
+            # raw pointers cross the ABI: the caller's arrays must be exactly what the library writes
+            # (Ns x K float64, column-major); a copy made here would never reach the caller
+            if len(out) != self.nf:
+                raise ValueError(f"download: expected {self.nf} field arrays")
+            for a in out:
+                if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.shape == (self.Ns, self.K)
+                        and a.flags.f_contiguous and a.flags.writeable):
+                    raise ValueError(f"download: every output must be a writeable float64 array of shape ({self.Ns}, {self.K}) "
+                                     "in column-major (Fortran) order")
         self._ck(self._lib.esdg_download_state(self._ctx, L.ptr_array(out)))
         return out
 
@@ -207,6 +217,10 @@ class Solver:
 
     def sync(self):
         self._ck(self._lib.esdg_sync(self._ctx))
+
+    def set_stream(self, cuda_stream):
+        """Run every kernel of this context on the given CUDA stream (esdg_set_stream)."""
+        self._ck(self._lib.esdg_set_stream(self._ctx, C.c_void_p(int(cuda_stream))))
 
     # -- multi-GPU plumbing --------------------------------------------------------
     def set_send_list(self, idx0):
@@ -296,8 +310,8 @@ _solver_cache = []   # [(md, ops, Solver)], most recent last; the functional API
 
 def _cached_solver(md, ops, cns=None):
     for ent in _solver_cache:
-        if ent[0] is md and ent[1] is ops and (cns is None or ent[2].cns is cns):
-            return ent[2]
+        if ent[0] is md and ent[1] is ops and ent[2].cns is cns:     # exact match, None included: rhs() after rhsRK()
+            return ent[2]                                            # on the same (md, ops) must not get the CNS context
     ent = (md, ops, Solver(md, ops, cns=cns))
     _solver_cache.append(ent)
     while len(_solver_cache) > 4:

@@ -1,6 +1,7 @@
 // libesdg_b200.so -- C ABI implementation (see include/esdg_b200.h).
 #include "ctx_util.h"
 #include "hex_fast.h"
+#include <algorithm>
 
 #include "kernels_generic.cuh"
 #include "kernels_cns.cuh"
@@ -337,7 +338,7 @@ int esdg_set_operator(esdg_ctx* ctx, const char* name, const double* a, int64_t 
     m.rows = rows; m.cols = cols;
     m.a.assign(a, a + rows * cols);
     ctx->ops[name] = std::move(m);
-    ctx->finalized = false;
+    if (ctx->finalized) return fail(ctx, ESDG_EINVAL, "setup calls (esdg_set_*) must precede esdg_finalize: a finalized context owns its device tables; create a new context to change them");
     return ESDG_OK;
 }
 
@@ -353,7 +354,7 @@ int esdg_set_geometry(esdg_ctx* ctx, const char* name, const double* a, int64_t 
     m.rows = rows; m.cols = cols;
     m.a.assign(a, a + rows * cols);
     ctx->geom[name] = std::move(m);
-    ctx->finalized = false;
+    if (ctx->finalized) return fail(ctx, ESDG_EINVAL, "setup calls (esdg_set_*) must precede esdg_finalize: a finalized context owns its device tables; create a new context to change them");
     return ESDG_OK;
 }
 
@@ -361,7 +362,7 @@ int esdg_set_maps(esdg_ctx* ctx, const int64_t* mapP, int64_t n) {
     if (!ctx || !mapP) return fail(ctx, ESDG_EINVAL, "esdg_set_maps: bad argument");
     if (n != (int64_t)ctx->d.Nfq * ctx->d.K) return fail(ctx, ESDG_EINVAL, "esdg_set_maps: mapP must hold Nfq*K entries");
     ctx->mapP_host.assign(mapP, mapP + n);
-    ctx->finalized = false;
+    if (ctx->finalized) return fail(ctx, ESDG_EINVAL, "setup calls (esdg_set_*) must precede esdg_finalize: a finalized context owns its device tables; create a new context to change them");
     return ESDG_OK;
 }
 
@@ -374,7 +375,7 @@ int esdg_set_viscosity(esdg_ctx* ctx, double lambda, double mu, double Pr, doubl
     c.on = true;
     c.lambda = lambda; c.mu = mu; c.Pr = Pr; c.Re = Re;
     c.viscous_dissp = viscous_dissp != 0;
-    ctx->finalized = false;
+    if (ctx->finalized) return fail(ctx, ESDG_EINVAL, "setup calls (esdg_set_*) must precede esdg_finalize: a finalized context owns its device tables; create a new context to change them");
     return ESDG_OK;
 }
 
@@ -389,7 +390,7 @@ int esdg_set_wall_bc(esdg_ctx* ctx, int bctype, const int64_t* wall_idx, int64_t
     c.wall.assign(wall_idx, wall_idx + nwall);
     c.lid.assign(lid_idx, lid_idx + nlid);
     c.vlid.assign(vlid, vlid + nlid);
-    ctx->finalized = false;
+    if (ctx->finalized) return fail(ctx, ESDG_EINVAL, "setup calls (esdg_set_*) must precede esdg_finalize: a finalized context owns its device tables; create a new context to change them");
     return ESDG_OK;
 }
 
@@ -413,7 +414,7 @@ int esdg_set_boundary_nodes(esdg_ctx* ctx, const int64_t* mapB, int64_t nB) {
     if (!ctx || nB < 0 || (nB > 0 && !mapB)) return fail(ctx, ESDG_EINVAL, "esdg_set_boundary_nodes: bad argument");
     ctx->cns.mapB.assign(mapB, mapB + nB);
     ctx->cns.have_mapB = true;
-    ctx->finalized = false;
+    if (ctx->finalized) return fail(ctx, ESDG_EINVAL, "setup calls (esdg_set_*) must precede esdg_finalize: a finalized context owns its device tables; create a new context to change them");
     return ESDG_OK;
 }
 
@@ -508,6 +509,7 @@ static int finalize_cns(esdg_ctx* ctx) {
 
 int esdg_finalize(esdg_ctx* ctx) {
     if (!ctx) return ESDG_EINVAL;
+    if (ctx->finalized) return fail(ctx, ESDG_EINVAL, "esdg_finalize: context already finalized");
     const esdg_desc& d = ctx->d;
     const int DIM = d.dim, NF = d.Nfields, Nh = ctx->Nh;
     CK(cudaSetDevice(ctx->device));
@@ -1092,6 +1094,12 @@ int esdg_set_send_list(esdg_ctx* ctx, const int64_t* idx, int64_t n) {
     if (lo + hi != cnt) { lo = ctx->d.K; hi = 0; }   // scattered boundary set: treat every element as boundary
     ctx->bnd_lo = lo;
     ctx->bnd_hi = hi;
+    if (ctx->send_idx) {                                   // a second call replaces the list
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->allocs.erase(std::remove(ctx->allocs.begin(), ctx->allocs.end(), (void*)ctx->send_idx), ctx->allocs.end());
+        cudaFree(ctx->send_idx);
+        ctx->send_idx = nullptr;
+    }
     return dev_upload(ctx, &ctx->send_idx, h);
 }
 

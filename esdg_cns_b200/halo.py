@@ -35,6 +35,13 @@ def attach_comm(solver, md, dist, torch, device):
     solver.comm_init(uid.cpu().numpy().tobytes(), dist.get_world_size(), dist.get_rank(), nb, ns, nr)
 
 
+def _share_stream(solver, torch):
+    """The host-driven exchange mixes the context's kernels (pack / unpack on the CONTEXT's stream) with tensor copies
+    and NCCL calls on torch's current stream: both must be the same stream, or the copies can read the send buffer
+    before the pack kernel has written it.  (The in-library exchange, attach_comm, orders its own streams.)"""
+    solver.set_stream(torch.cuda.current_stream().cuda_stream)
+
+
 class SlabHalo:
     def __init__(self, md, nf, dist, torch, device):
         self.dist, self.torch = dist, torch
@@ -88,6 +95,7 @@ class GpuSlabStepper:
 
     def __init__(self, solver, md, dist, torch, device, overlap=True):
         self.s = solver
+        _share_stream(solver, torch)
         self.halo = SlabHalo(md, solver.trace_planes(), dist, torch, device)
         solver.set_send_list(self.halo.send_list)
         self.overlap = overlap
@@ -129,6 +137,7 @@ class GpuSlabStepperCNS:
 
     def __init__(self, solver, md, dist, torch, device):
         self.s = solver
+        _share_stream(solver, torch)
         self.halo_v = SlabHalo(md, solver.trace_planes(), dist, torch, device)
         self.halo_s = SlabHalo(md, solver.SIGMA_PLANES, dist, torch, device)
         solver.set_send_list(self.halo_v.send_list)

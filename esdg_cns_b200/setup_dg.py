@@ -100,7 +100,12 @@ def reference_quad(N, lf_scale=.5):
 
 
 def reference_hex(N, lf_scale=.25):
-    """Collocated Gauss hex element, r-fastest nodes (dg3D_euler_hex.jl:34-58,94-98 with the H2 fix)."""
+    """Collocated Gauss hex element, r-fastest nodes (dg3D_euler_hex.jl:34-58,94-98 with the H2 fix).
+
+    ``lf_scale`` is the constant c in ``LFc = c*max(lam, lamP)*sJ``.  NOTE the default: the upstream hex script
+    multiplies its penalty by zero (``LFc = 0*.25*...``, dg3D_euler_hex.jl:193), i.e. it runs entropy CONSERVATIVE;
+    the default here is the .25 the formula carries (the value of the triangle / CNS scripts and of BASELINE config 5),
+    which makes the rhs entropy DISSIPATIVE.  Pass ``lf_scale=0.0`` for the upstream script's behaviour."""
     x, w = gauss_1d(N)
     n = N + 1
     D = lagrange_deriv(x)

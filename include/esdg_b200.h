@@ -228,6 +228,26 @@ const char* esdg_kernel_path(const esdg_ctx* ctx);
 int esdg_read_rhstest(esdg_ctx* ctx, double* rhstest);
 int esdg_read_rhstest_visc(esdg_ctx* ctx, double* rhstest_visc);   /* CNS contexts */
 
+/* ---- 1-D compressible Navier-Stokes with SSPRK(3,3) -----------------------------------------
+ * examples/CompressibleNS/dg1D_CNS_modalESDG.jl: modal ESDG on K intervals, `rhs_ESDG(U, ..., t)` (:338-353 =
+ * rhs_inviscid :220-268 + rhs_viscous :270-336) and the loop `while t < T` (:377-391).  The script's operators
+ * (rd.Vq, rd.Pq, rd.Vf, rd.LIFT, rd.Dr of init_reference_interval; VhP, Ph, Qrh_skew of :142-156) are handed over
+ * as column-major matrices; J = (XR-XL)/K/2, rxJ = 1.  The states the script imposes on the two domain ends (the
+ * exact solution at time t, :339-349) are passed per call as
+ *   bc12 = { rhoL, uL, betaL, rhoR, uR, betaR, v1L, v2L, v3L, v1R, v2R, v3R }
+ * so that the (host-side, scalar) bisection of `exact_sol_viscous_shocktube` stays in the caller. */
+typedef struct esdg1d_ctx esdg1d_ctx;
+int esdg1d_create(int device, int N, int64_t K, int Nq, const double* Vq, const double* Pq, const double* Vf, const double* LIFT,
+                  const double* Dr, const double* VhP, const double* Ph, const double* Qrh_skew, double J, double rxJ, double gamma,
+                  double mu, double lambda, double kappa_over_cv, esdg1d_ctx** out);
+int esdg1d_destroy(esdg1d_ctx* ctx);
+const char* esdg1d_last_error(const esdg1d_ctx* ctx);
+int esdg1d_upload_state(esdg1d_ctx* ctx, const double* const* U /* 3 host arrays, (N+1) x K column-major */);
+int esdg1d_download_state(esdg1d_ctx* ctx, double* const* U);
+int esdg1d_rhs(esdg1d_ctx* ctx, const double* bc12, double* const* rhs_out);          /* rhs_ESDG of the resident state */
+int esdg1d_ssprk3_step(esdg1d_ctx* ctx, double dt, const double* bc12);               /* one pass of the loop body      */
+int64_t esdg1d_kernel_launches(const esdg1d_ctx* ctx);
+
 /* ---- introspection ---------------------------------------------------------- */
 int64_t esdg_kernel_launches(const esdg_ctx* ctx);          /* kernels launched so far      */
 int esdg_kernel_time_ms(esdg_ctx* ctx, const char* kernel, double* total_ms, int64_t* launches);

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared():
     txt = open(os.path.join(ROOT, "include", "esdg_b200.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(esdg_[a-z0-9_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(esdg(?:1d)?_[a-z0-9_]+)\s*\(", txt)))
 
 
 def test_header_symbols_are_exported_and_bound():
@@ -20,7 +20,7 @@ def test_header_symbols_are_exported_and_bound():
     names = _declared()
     assert "esdg_rhs" in names and "esdg_lsrk45_step" in names
     out = subprocess.run(["nm", "-D", _lib.LIB_PATH], capture_output=True, text=True).stdout
-    exported = set(re.findall(r" T (esdg_[a-z0-9_]+)", out))
+    exported = set(re.findall(r" T (esdg(?:1d)?_[a-z0-9_]+)", out))
     for n in names:
         assert n in exported, f"{n} declared in esdg_b200.h but not exported"
         assert hasattr(lib, n)
