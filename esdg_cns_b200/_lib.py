@@ -52,6 +52,7 @@ _SIGNATURES = {
     "esdg_set_wall_bc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]),
     "esdg_set_inflow_outflow_bc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]),
     "esdg_set_boundary_nodes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "esdg_set_structured_hex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]),
     "esdg_finalize": (C.c_int, [C.c_void_p]),
     "esdg_rhs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "esdg_upload_state": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -62,6 +62,8 @@ class Solver:
         # inside an element; the 2-D scripts read `[1,e]` whatever the mesh
         if affine is not None:
             affine = int(affine)                 # caller's claim; esdg_finalize verifies a claimed affine mesh
+        elif getattr(md, "structured", False):
+            affine = 1
         else:
             affine = 1
             if dim == 3 and collocated:
@@ -98,14 +100,21 @@ class Solver:
         else:
             self._set_op("Vq", ops.Vq)
             self._set_op("VhP", ops.VhP)
-        # geometry
-        gnames = ["rxJ", "sxJ", "ryJ", "syJ", "J", "nxJ", "nyJ", "sJ"] if dim == 2 else \
-                 ["rxJ", "sxJ", "txJ", "ryJ", "syJ", "tyJ", "rzJ", "szJ", "tzJ", "J", "nxJ", "nyJ", "nzJ", "sJ"]
-        for n in gnames:
-            a = L.f64(np.atleast_2d(getattr(md, n)))
-            self._ck(lib.esdg_set_geometry(self._ctx, n.encode(), a.ctypes.data, a.shape[0], a.shape[1]))
-        mapP = np.asfortranarray(np.asarray(md.mapP, dtype=np.int64) + (1 - map_index_base))
-        self._ck(lib.esdg_set_maps(self._ctx, mapP.ctypes.data, mapP.size))
+        # geometry + maps: host arrays (the script's MeshData), or -- structured hex meshes -- generated on the device
+        if getattr(md, "structured", False):
+            K3 = np.ascontiguousarray(md.Kxyz, dtype=np.int64)
+            box = np.ascontiguousarray([v for ab in md.domain for v in ab], dtype=np.float64)
+            per = np.ascontiguousarray([int(bool(v)) for v in md.periodic], dtype=np.int32)
+            self._ck(lib.esdg_set_structured_hex(self._ctx, K3.ctypes.data, box.ctypes.data, per.ctypes.data,
+                                                 int(md.zrange[0]), int(md.zrange[1] - md.zrange[0])))
+        else:
+            gnames = ["rxJ", "sxJ", "ryJ", "syJ", "J", "nxJ", "nyJ", "sJ"] if dim == 2 else \
+                     ["rxJ", "sxJ", "txJ", "ryJ", "syJ", "tyJ", "rzJ", "szJ", "tzJ", "J", "nxJ", "nyJ", "nzJ", "sJ"]
+            for n in gnames:
+                a = L.f64(np.atleast_2d(getattr(md, n)))
+                self._ck(lib.esdg_set_geometry(self._ctx, n.encode(), a.ctypes.data, a.shape[0], a.shape[1]))
+            mapP = np.asfortranarray(np.asarray(md.mapP, dtype=np.int64) + (1 - map_index_base))
+            self._ck(lib.esdg_set_maps(self._ctx, mapP.ctypes.data, mapP.size))
         if cns is not None:
             for n in ("Pq", "Vf", "Dr", "Ds"):
                 self._set_op(n, getattr(ops, n))

@@ -507,6 +507,78 @@ static int finalize_cns(esdg_ctx* ctx) {
     return ESDG_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// GPU-side setup of a structured hex mesh: what src/UniformHexMesh.jl + connect_mesh.jl +
+// node_map_functions.jl:139-213 (periodic maps) + geometric_factors.jl produce for an axis-aligned box, written straight
+// into the device tables.  Element e = i + Kx j + Kx Ky (k - kz0) (x fastest, UniformHexMesh.jl:59-63); faces in the
+// order r-, r+, s-, s+, t-, t+; matching face points share their on-face index m.  Points owned by the z-slab below /
+// above map to halo slots Nfq K + (i + Kx j) nfp + m (+ Kx Ky nfp for the upper slab), as esdg_cns_b200/setup_dg.py does.
+__global__ void k_structured_mapP(int* __restrict__ mapP, long long K, int Kx, int Ky, long long Kz, long long kz0, long long kzn,
+                                  int nfp, int px, int py, int pz) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int Nfq = 6 * nfp;
+    if (t >= K * Nfq) return;
+    const long long e = t / Nfq;
+    const int kf = (int)(t - e * Nfq), f = kf / nfp, m = kf - f * nfp;
+    const int i = (int)(e % Kx), j = (int)((e / Kx) % Ky);
+    const long long k = e / ((long long)Kx * Ky) + kz0;
+    const int d = f >> 1, sgn = (f & 1) ? 1 : -1, fn = f ^ 1;
+    long long c[3] = {i, j, k};
+    const long long Kd[3] = {Kx, Ky, Kz};
+    const int per[3] = {px, py, pz};
+    c[d] += sgn;
+    bool ok = true;
+    if (per[d]) c[d] = (c[d] + Kd[d]) % Kd[d];
+    else ok = c[d] >= 0 && c[d] < Kd[d];
+    long long tgt;
+    if (!ok) tgt = t;                                                    // physical boundary: mapP = mapM
+    else if (d == 2 && (c[2] < kz0 || c[2] >= kz0 + kzn))                // owned by a neighbouring slab: halo slot
+        tgt = (long long)Nfq * K + ((long long)c[0] + (long long)Kx * c[1]) * nfp + m + (sgn < 0 ? 0 : (long long)Kx * Ky * nfp);
+    else tgt = (long long)(fn * nfp + m) + Nfq * (c[0] + (long long)Kx * c[1] + (long long)Kx * Ky * (c[2] - kz0));
+    mapP[t] = (int)tgt;
+}
+__global__ void k_structured_geo(double* __restrict__ geo, long long K, int stride, double hx, double hy, double hz) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= K) return;
+    double* g = geo + e * stride;
+    for (int q = 0; q < stride; ++q) g[q] = 0.0;
+    const double a[3] = {hy * hz / 4, hx * hz / 4, hx * hy / 4};          // rxJ, syJ, tzJ
+    g[0] = a[0]; g[4] = a[1]; g[8] = a[2];
+    g[9] = hx * hy * hz / 8;
+    for (int f = 0; f < 6; ++f) {
+        const int d = f >> 1;
+        g[10 + 4 * f + d] = (f & 1) ? a[d] : -a[d];
+        g[10 + 4 * f + 3] = a[d];
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int esdg_set_structured_hex(esdg_ctx* ctx, const int64_t K3[3], const double box[6], const int periodic[3], int64_t kz_begin,
+                            int64_t kz_count) {
+    if (!ctx || !K3 || !box || !periodic) return fail(ctx, ESDG_EINVAL, "esdg_set_structured_hex: bad argument");
+    if (ctx->finalized) return fail(ctx, ESDG_EINVAL, "setup calls (esdg_set_*) must precede esdg_finalize");
+    const esdg_desc& d = ctx->d;
+    if (d.dim != 3 || d.elem != ESDG_HEX || d.Nfaces != 6 || !d.affine)
+        return fail(ctx, ESDG_EINVAL, "esdg_set_structured_hex: affine hex contexts only");
+    if (K3[0] < 1 || K3[1] < 1 || K3[2] < 1 || kz_begin < 0 || kz_count < 1 || kz_begin + kz_count > K3[2] ||
+        K3[0] * K3[1] * kz_count != d.K)
+        return fail(ctx, ESDG_EINVAL, "esdg_set_structured_hex: element counts do not match desc.K");
+    const bool split = kz_count < K3[2];
+    const long long need_halo = split ? 2 * K3[0] * K3[1] * (long long)ctx->Nfp : 0;
+    if (d.n_halo != need_halo) return fail(ctx, ESDG_EINVAL, "esdg_set_structured_hex: desc.n_halo must be 2 Kx Ky Nfp for a z-slab (0 for the whole mesh)");
+    if (!(box[1] > box[0] && box[3] > box[2] && box[5] > box[4])) return fail(ctx, ESDG_EINVAL, "esdg_set_structured_hex: empty box");
+    ctx->structured = true;
+    for (int q = 0; q < 3; ++q) { ctx->sK[q] = K3[q]; ctx->sper[q] = periodic[q] != 0; }
+    for (int q = 0; q < 6; ++q) ctx->sbox[q] = box[q];
+    ctx->skz0 = kz_begin;
+    ctx->skzn = kz_count;
+    return ESDG_OK;
+}
+
 int esdg_finalize(esdg_ctx* ctx) {
     if (!ctx) return ESDG_EINVAL;
     if (ctx->finalized) return fail(ctx, ESDG_EINVAL, "esdg_finalize: context already finalized");
@@ -680,8 +752,14 @@ int esdg_finalize(esdg_ctx* ctx) {
     static const char* g3[9] = {"rxJ", "sxJ", "txJ", "ryJ", "syJ", "tyJ", "rzJ", "szJ", "tzJ"};
     static const char* nn[4] = {"nxJ", "nyJ", "nzJ", "sJ"};
     ctx->geo_stride = DIM * DIM + 1 + d.Nfaces * (DIM + 1);
-    std::vector<double> geo((size_t)d.K * ctx->geo_stride);
-    {
+    std::vector<double> geo(ctx->structured ? 0 : (size_t)d.K * ctx->geo_stride);
+    if (ctx->structured) {
+        if ((rc = dev_alloc(ctx, &ctx->geo, (size_t)d.K * ctx->geo_stride))) return rc;
+        const double hx = (ctx->sbox[1] - ctx->sbox[0]) / ctx->sK[0], hy = (ctx->sbox[3] - ctx->sbox[2]) / ctx->sK[1],
+                     hz = (ctx->sbox[5] - ctx->sbox[4]) / ctx->sK[2];
+        k_structured_geo<<<(unsigned)((d.K + 255) / 256), 256, 0, ctx->stream>>>(ctx->geo, d.K, ctx->geo_stride, hx, hy, hz);
+        CK(cudaGetLastError());
+    } else {
         const HostMat* G[9];
         for (int k = 0; k < DIM * DIM; ++k) {
             G[k] = find(ctx->geom, DIM == 2 ? g2[k] : g3[k]);
@@ -720,7 +798,7 @@ int esdg_finalize(esdg_ctx* ctx) {
                         return fail(ctx, ESDG_EINVAL, "esdg_finalize: volume geometric factors vary inside an element (mesh not affine)");
         }
     }
-    if ((rc = dev_upload(ctx, &ctx->geo, geo))) return rc;
+    if (!ctx->structured && (rc = dev_upload(ctx, &ctx->geo, geo))) return rc;
     if (!d.affine) {
         // curved hexes: the full arrays of the script, rxJ.. = [Vq;Vf]*rxJ.. (Nh x K), J = Vq*J (Nq x K),
         // nxJ.. at the face points (Nfq x K)   (dg3D_euler_hex.jl:69-101)
@@ -750,9 +828,16 @@ int esdg_finalize(esdg_ctx* ctx) {
         if ((rc = dev_upload(ctx, &ctx->geoN, gN))) return rc;
     }
     // ---- maps ------------------------------------------------------------------
-    if ((int64_t)ctx->mapP_host.size() != (int64_t)d.Nfq * d.K)
-        return fail(ctx, ESDG_EINVAL, "esdg_finalize: mapP missing (esdg_set_maps)");
-    {
+    if (ctx->structured) {
+        if ((rc = dev_alloc(ctx, &ctx->mapP, (size_t)d.Nfq * d.K))) return rc;
+        const long long nt = (long long)d.Nfq * d.K;
+        k_structured_mapP<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(ctx->mapP, d.K, (int)ctx->sK[0], (int)ctx->sK[1], ctx->sK[2],
+                                                                                ctx->skz0, ctx->skzn, ctx->Nfp, ctx->sper[0], ctx->sper[1],
+                                                                                ctx->sper[2]);
+        CK(cudaGetLastError());
+    } else if ((int64_t)ctx->mapP_host.size() != (int64_t)d.Nfq * d.K) {
+        return fail(ctx, ESDG_EINVAL, "esdg_finalize: mapP missing (esdg_set_maps or esdg_set_structured_hex)");
+    } else {
         std::vector<int> mp(ctx->mapP_host.size());
         for (size_t i = 0; i < mp.size(); ++i) {
             const int64_t v = ctx->mapP_host[i] - 1;  // Julia 1-based
@@ -822,8 +907,8 @@ int esdg_finalize(esdg_ctx* ctx) {
     }
     if (!ctx->cns.on && (rc = hexfast_try_create(ctx))) return rc;
     if (ctx->hex) {
-        bool diag = true;
-        for (int64_t e = 0; e < d.K && diag; ++e)
+        bool diag = true;                                  // a structured box is axis-aligned by construction
+        for (int64_t e = 0; e < d.K && diag && !ctx->structured; ++e)
             for (int k = 0; k < 9; ++k)
                 if (k % 4 != 0 && geo[(size_t)e * ctx->geo_stride + k] != 0.0) { diag = false; break; }
         ctx->hex->diag = diag && !getenv("ESDG_NO_DIAG");
@@ -929,6 +1014,13 @@ int esdg_lsrk45_step(esdg_ctx* ctx, double dt, int nsteps, double* rhstest_last)
 static int build_chunks(esdg_ctx* ctx) {
     const esdg_desc& d = ctx->d;
     const long long K = d.K;
+    if (ctx->structured && ctx->mapP_host.empty()) {              // device-generated maps: read them back once (1-based)
+        std::vector<int> mp((size_t)d.Nfq * K);
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaMemcpy(mp.data(), ctx->mapP, mp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        ctx->mapP_host.resize(mp.size());
+        for (size_t i = 0; i < mp.size(); ++i) ctx->mapP_host[i] = (int64_t)mp[i] + 1;
+    }
     const int EB = ctx->hex ? 6 * ctx->hex->EB_ws : 1;            // whole batches of either stage kernel per chunk
     int nchunk = (int)std::min<long long>(16, K / std::max<long long>(4096, EB));
     if (const char* ev = getenv("ESDG_HOST_CHUNKS")) nchunk = std::max(1, std::min(64, atoi(ev)));   // experiments

@@ -115,6 +115,12 @@ struct esdg_ctx {
     std::vector<long long> chunk_begin; // nchunk + 1 element offsets
     long long bnd_lo = 0, bnd_hi = 0;   // leading / trailing elements whose traces are sent to neighbours
     struct EsdgComm* comm = nullptr;    // NCCL communicator + neighbour lists (esdg_comm_init)
+    // structured hex mesh generated on the device (esdg_set_structured_hex): global element counts, box, periodicity,
+    // local z-slab; maps and geometric factors never cross the ABI
+    bool structured = false;
+    long long sK[3] = {0, 0, 0}, skz0 = 0, skzn = 0;
+    double sbox[6] = {0, 0, 0, 0, 0, 0};
+    int sper[3] = {1, 1, 1};
     bool res_zero = true;
 
     // accounting

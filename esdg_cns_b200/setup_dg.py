@@ -367,6 +367,40 @@ def uniform_hex_mesh_md(rd, Kxyz, domain=((-1.0, 1.0),) * 3, periodic=(True, Tru
     return md
 
 
+def structured_hex_md(rd, Kxyz, domain=((-1.0, 1.0),) * 3, periodic=(True, True, True), zslab=None):
+    """The same mesh as ``uniform_hex_mesh_md`` WITHOUT its arrays: ``api.Solver`` hands the six integers and the box to
+    ``esdg_set_structured_hex`` and the library generates mapP and the geometric factors on the device (SURVEY 8f
+    rank 3).  Send lists and halo size of a z-slab are the same as there."""
+    n = rd.N + 1
+    nfp = n * n
+    Nfq = 6 * nfp
+    Kx, Ky, Kz = Kxyz
+    (x0, x1), (y0, y1), (z0, z1) = domain
+    hx, hy, hz = (x1 - x0) / Kx, (y1 - y0) / Ky, (z1 - z0) / Kz
+    if zslab is None:
+        rank, nranks = 0, 1
+    else:
+        rank, nranks = zslab
+        if Kz % nranks:
+            raise ValueError("Kz must be divisible by the number of ranks")
+    k0, k1 = rank * (Kz // nranks), (rank + 1) * (Kz // nranks)
+    K = Kx * Ky * (k1 - k0)
+    e = np.arange(K)
+    ex, ey, ez = e % Kx, (e // Kx) % Ky, e // (Kx * Ky) + k0
+    md = SimpleNamespace(K=K, dim=3, Kxyz=(Kx, Ky, Kz), zrange=(k0, k1), structured=True, domain=domain, periodic=periodic,
+                         elem_origin=(x0 + hx * ex, y0 + hy * ey, z0 + hz * ez), h=(hx, hy, hz), n_halo=0)
+    if nranks > 1:
+        m = np.arange(nfp)
+        md.n_halo = 2 * Kx * Ky * nfp
+        bottom = np.nonzero(ez == k0)[0]
+        top = np.nonzero(ez == k1 - 1)[0]
+        md.send_lower = ((4 * nfp + m)[None, :] + Nfq * bottom[:, None]).reshape(-1)
+        md.send_upper = ((5 * nfp + m)[None, :] + Nfq * top[:, None]).reshape(-1)
+        md.lower_rank = (rank - 1) % nranks if (periodic[2] or k0 > 0) else None
+        md.upper_rank = (rank + 1) % nranks if (periodic[2] or k1 < Kz) else None
+    return md
+
+
 def hex_node_coords(rd, md):
     """Physical coordinates of the volume quadrature nodes (Nq x K each)."""
     ox, oy, oz = md.elem_origin

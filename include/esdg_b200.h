@@ -129,6 +129,15 @@ int esdg_set_boundary_nodes(esdg_ctx* ctx, const int64_t* mapB, int64_t nB);
 
 /* Validates that everything required by the descriptor was supplied, compresses the
  * operators and uploads them.  Must be called once before any hot call. */
+/* GPU-side setup of a structured hex mesh, INSTEAD of esdg_set_geometry + esdg_set_maps: mapP and
+ * the geometric factors of an axis-aligned box of K3[0] x K3[1] x K3[2] elements (element index x fastest,
+ * src/UniformHexMesh.jl:59-63; faces r-, r+, s-, s+, t-, t+; matching face points share their on-face index, which is
+ * what connect_mesh.jl + node_map_functions.jl:23-55,139-213 produce for the r-fastest node ordering) are generated
+ * on the device by esdg_finalize -- a 128^3 mesh needs six integers instead of 2.5 GB of Int64 maps.  This context holds
+ * the layers kz_begin .. kz_begin + kz_count - 1; trace points owned by the slab below / above map to the halo slots
+ * Nfq K + (i + Kx j) Nfp + m  (+ Kx Ky Nfp for the upper slab): desc.n_halo = 2 Kx Ky Nfp for a slab, 0 for the whole mesh. */
+int esdg_set_structured_hex(esdg_ctx* ctx, const int64_t K3[3], const double box[6] /* x0,x1,y0,y1,z0,z1 */, const int periodic[3],
+                            int64_t kz_begin, int64_t kz_count);
 int esdg_finalize(esdg_ctx* ctx);
 
 /* ---- hot path ------------------------------------------------------------------

@@ -45,3 +45,43 @@ def test_hex_slabs_with_halo_exchange_match_single_context(N, mesh, nslabs, over
     print(f"hex N={N} {mesh} {nslabs} slabs overlap={overlap} generic={generic}: max |dQ| {diff:.2e}, rhstest {rt:.6e} vs {rt_ref:.6e}")
     assert diff == 0.0
     assert abs(rt - rt_ref) < 1e-12 * max(1.0, abs(rt_ref))
+
+
+@pytest.mark.parametrize("N,mesh,periodic,nslabs", [(4, (5, 4, 6), (True, True, True), 1), (3, (4, 3, 5), (True, False, True), 1),
+                                                    (2, (6, 5, 4), (False, False, False), 1), (4, (4, 3, 6), (True, True, True), 3),
+                                                    (2, (4, 4, 4), (True, True, False), 2)])
+def test_structured_hex_setup_on_the_device_matches_host_built_maps(N, mesh, periodic, nslabs):
+    """esdg_set_structured_hex: mapP and the geometric factors generated on the device give bitwise
+    the states of the host-built arrays of uniform_hex_mesh_md -- whole meshes (periodic and with physical boundaries)
+    and z-slabs with halo slots."""
+    import torch
+    from esdg_cns_b200 import api, halo as H, setup_dg as SD
+    prd, pops = SD.reference_hex(N)
+    dom = ((-np.pi, np.pi), (-2.0, 1.0), (0.0, 3.0))
+    res = []
+    for structured in (False, True):
+        make = SD.structured_hex_md if structured else SD.uniform_hex_mesh_md
+        stream = torch.cuda.current_stream().cuda_stream
+        if nslabs == 1:
+            md = make(prd, mesh, domain=dom, periodic=periodic)
+            x, y, z = SD.hex_node_coords(prd, md)
+            rho, u, v, w, p = SD.taylor_green(x, y, z)
+            Q = SD.primitive_to_conservative(rho + .05 * np.sin(x), (u + .3, v - .2, w + .1 * np.sin(y) + .4), p)
+            s = api.Solver(md, pops, stream=stream)
+            assert s.hex_diag()
+            s.upload(Q)
+            rt = s.lsrk45(1e-3, 2, want_rhstest=True)
+            res.append((np.stack(s.download()), rt))
+        else:
+            mds = [make(prd, mesh, domain=dom, periodic=periodic, zslab=(r, nslabs)) for r in range(nslabs)]
+            sol = [api.Solver(md, pops, n_halo=md.n_halo, stream=stream) for md in mds]
+            for s, md in zip(sol, mds):
+                x, y, z = SD.hex_node_coords(prd, md)
+                rho, u, v, w, p = SD.taylor_green(x, y, z)
+                s.upload(SD.primitive_to_conservative(rho + .05 * np.sin(x), (u + .3, v - .2, w + .1 * np.sin(y) + .4), p))
+            st = H.LocalSlabs(sol, mds, torch, torch.device("cuda", 0))
+            for k in range(2):
+                st.step(1e-3, want_rhstest=(k == 1))
+            res.append((np.concatenate([np.stack(s.download()) for s in sol], axis=2), sum(s.read_rhstest() for s in sol)))
+    assert np.array_equal(res[0][0], res[1][0])
+    assert res[0][1] == res[1][1]
