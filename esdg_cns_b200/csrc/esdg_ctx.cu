@@ -2,6 +2,7 @@
 #include "ctx_util.h"
 #include "hex_fast.h"
 #include <algorithm>
+#include <functional>
 
 #include "kernels_generic.cuh"
 #include "kernels_cns.cuh"
@@ -1021,25 +1022,47 @@ static int build_chunks(esdg_ctx* ctx) {
         ctx->mapP_host.resize(mp.size());
         for (size_t i = 0; i < mp.size(); ++i) ctx->mapP_host[i] = (int64_t)mp[i] + 1;
     }
-    const int EB = ctx->hex ? 6 * ctx->hex->EB_ws : 1;            // whole batches of either stage kernel per chunk
-    int nchunk = (int)std::min<long long>(16, K / std::max<long long>(4096, EB));
-    if (const char* ev = getenv("ESDG_HOST_CHUNKS")) nchunk = std::max(1, std::min(64, atoi(ev)));   // experiments
-    if (nchunk < 2) nchunk = 1;
-    long long per = ((K + nchunk - 1) / nchunk + EB - 1) / EB * EB;
-    ctx->chunk_begin.clear();
-    for (long long b = 0; b < K; b += per) ctx->chunk_begin.push_back(b);
-    ctx->chunk_begin.push_back(K);
-    nchunk = (int)ctx->chunk_begin.size() - 1;
+    int nchunk;
+    std::function<int(long long)> chunk_of;
+    const char* ev = getenv("ESDG_HOST_CHUNKS");
+    if (ctx->structured && ctx->skzn == ctx->sK[2] && ctx->sK[1] >= 8 && !(ev && atoi(ev) < 0)) {
+        // structured slab: chunks along y (rows of Kx elements in every z-layer).  After five stages a chunk depends on
+        // +-4 chunks whatever their size, so what shortens the dependency cone is MANY chunks: up to 64 of them, each a
+        // strided element range (Kz segments of rows * Kx elements) that one launch / one 2-D copy per field covers
+        const long long Kx = ctx->sK[0], Ky = ctx->sK[1];
+        nchunk = (int)std::min<long long>(64, Ky / 2);
+        if (ev && atoi(ev) > 0) nchunk = std::max(1, std::min<int>({64, atoi(ev), (int)Ky}));
+        const long long rows = (Ky + nchunk - 1) / nchunk;
+        ctx->chunk_begin.clear();
+        for (long long j = 0; j < Ky; j += rows) ctx->chunk_begin.push_back(j * Kx);
+        ctx->chunk_begin.push_back(Ky * Kx);
+        ctx->chunk_seg_stride = Kx * Ky;
+        ctx->chunk_nseg = ctx->skzn;
+        nchunk = (int)ctx->chunk_begin.size() - 1;
+        chunk_of = [=](long long e) { return (int)(((e / Kx) % Ky) / rows); };
+    } else {
+        const int EB = ctx->hex ? 6 * ctx->hex->EB_ws : 1;            // whole batches of either stage kernel per chunk
+        nchunk = (int)std::min<long long>(16, K / std::max<long long>(4096, EB));
+        if (ev && atoi(ev) != 0) nchunk = std::max(1, std::min(64, std::abs(atoi(ev))));   // experiments
+        if (nchunk < 2) nchunk = 1;
+        const long long per = ((K + nchunk - 1) / nchunk + EB - 1) / EB * EB;
+        ctx->chunk_begin.clear();
+        for (long long b = 0; b < K; b += per) ctx->chunk_begin.push_back(b);
+        ctx->chunk_begin.push_back(K);
+        ctx->chunk_seg_stride = 0;
+        ctx->chunk_nseg = 1;
+        nchunk = (int)ctx->chunk_begin.size() - 1;
+        chunk_of = [=](long long e) {
+            int c = (int)(e / per);
+            return c < nchunk ? c : nchunk - 1;
+        };
+    }
     ctx->chunk_dep.assign(nchunk, 0ull);
-    auto chunk_of = [&](long long e) {
-        int c = (int)(e / per);
-        return c < nchunk ? c : nchunk - 1;
-    };
-    for (int c = 0; c < nchunk; ++c) {
+    for (long long e = 0; e < K; ++e) {
+        const int c = chunk_of(e);
         unsigned long long m = 1ull << c;
-        for (long long e = ctx->chunk_begin[c]; e < ctx->chunk_begin[c + 1]; ++e)
-            for (int k = 0; k < d.Nfq; ++k) m |= 1ull << chunk_of((ctx->mapP_host[(size_t)(e * d.Nfq + k)] - 1) / d.Nfq);
-        ctx->chunk_dep[c] = m;
+        for (int k = 0; k < d.Nfq; ++k) m |= 1ull << chunk_of((ctx->mapP_host[(size_t)(e * d.Nfq + k)] - 1) / d.Nfq);
+        ctx->chunk_dep[c] |= m;
     }
     CK(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
@@ -1105,14 +1128,21 @@ int esdg_lsrk45_host(esdg_ctx* ctx, const double* const* Q_in, double* const* Q_
     for (int idx = 0; idx < nchunk; ++idx) {
         const int u = order[idx];
         const long long b = ctx->chunk_begin[u], len = ctx->chunk_begin[u + 1] - b;
-        for (int f = 0; f < ctx->NF; ++f)
-            CK(cudaMemcpyAsync(ctx->Q + f * n + b * Ns, Q_in[f] + b * Ns, (size_t)len * Ns * sizeof(double),
-                               cudaMemcpyHostToDevice, ctx->h2d_stream));
+        const long long nseg = ctx->chunk_nseg, sst = ctx->chunk_seg_stride;
+        for (int f = 0; f < ctx->NF; ++f) {
+            if (nseg == 1)
+                CK(cudaMemcpyAsync(ctx->Q + f * n + b * Ns, Q_in[f] + b * Ns, (size_t)len * Ns * sizeof(double),
+                                   cudaMemcpyHostToDevice, ctx->h2d_stream));
+            else
+                CK(cudaMemcpy2DAsync(ctx->Q + f * n + b * Ns, (size_t)sst * Ns * sizeof(double), Q_in[f] + b * Ns,
+                                     (size_t)sst * Ns * sizeof(double), (size_t)len * Ns * sizeof(double), (size_t)nseg,
+                                     cudaMemcpyHostToDevice, ctx->h2d_stream));
+        }
         CK(cudaEventRecord(ctx->chunk_up[u], ctx->h2d_stream));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_up[u], 0));
         h->prod = bufU;
         h->cons = bufU ^ 1;
-        if ((rc = hexfast_traces_range(ctx, ctx->Q, b, len))) return rc;
+        if ((rc = hexfast_traces_range(ctx, ctx->Q, b, len * nseg, nseg == 1 ? 0 : len, sst))) return rc;
         up[u] = 1;
         // issue every task that has become ready, deepest stage first (ties: upload order): chunks near chunk 0 finish
         // all their stages -- and start their download -- while the outer chunks are still on the bus
@@ -1127,14 +1157,20 @@ int esdg_lsrk45_host(esdg_ctx* ctx, const double* const* Q_in, double* const* Q_
             const long long cb = ctx->chunk_begin[c], cl = ctx->chunk_begin[c + 1] - cb;
             h->cons = bufU ^ (st & 1);                            // stage st reads the traces stage st-1 wrote
             h->prod = h->cons ^ 1;
-            if ((rc = hexfast_stage_range(ctx, ctx->Q, 1, RK4A[st % 5], RK4B[st % 5], dt, cb, cl))) return rc;
+            if ((rc = hexfast_stage_range(ctx, ctx->Q, 1, RK4A[st % 5], RK4B[st % 5], dt, cb, cl * nseg, nseg == 1 ? 0 : cl, sst))) return rc;
             done[c] = st + 1;
             if (done[c] == nstage) {                              // finished: its download goes behind it
                 CK(cudaEventRecord(ctx->chunk_done[c], ctx->stream));
                 CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->chunk_done[c], 0));
-                for (int f = 0; f < ctx->NF; ++f)
-                    CK(cudaMemcpyAsync(Q_out[f] + cb * Ns, ctx->Q + f * n + cb * Ns, (size_t)cl * Ns * sizeof(double),
-                                       cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                for (int f = 0; f < ctx->NF; ++f) {
+                    if (nseg == 1)
+                        CK(cudaMemcpyAsync(Q_out[f] + cb * Ns, ctx->Q + f * n + cb * Ns, (size_t)cl * Ns * sizeof(double),
+                                           cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                    else
+                        CK(cudaMemcpy2DAsync(Q_out[f] + cb * Ns, (size_t)sst * Ns * sizeof(double), ctx->Q + f * n + cb * Ns,
+                                             (size_t)sst * Ns * sizeof(double), (size_t)cl * Ns * sizeof(double), (size_t)nseg,
+                                             cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                }
             }
         }
     }

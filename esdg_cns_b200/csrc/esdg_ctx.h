@@ -112,7 +112,9 @@ struct esdg_ctx {
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     std::vector<cudaEvent_t> chunk_up, chunk_done;
     std::vector<unsigned long long> chunk_dep;   // bit c' set: the stage of this chunk reads traces of chunk c'
-    std::vector<long long> chunk_begin; // nchunk + 1 element offsets
+    std::vector<long long> chunk_begin; // nchunk + 1 element offsets (contiguous chunks) ...
+    long long chunk_seg_stride = 0;     // ... or, > 0: chunk c = segments [chunk_begin[c], chunk_begin[c+1]) + s * chunk_seg_stride, s < chunk_nseg
+    long long chunk_nseg = 1;
     long long bnd_lo = 0, bnd_hi = 0;   // leading / trailing elements whose traces are sent to neighbours
     struct EsdgComm* comm = nullptr;    // NCCL communicator + neighbour lists (esdg_comm_init)
     // structured hex mesh generated on the device (esdg_set_structured_hex): global element counts, box, periodicity,

@@ -38,6 +38,10 @@ constexpr int HEX_SGEO = 40;  // shared-memory copy: + 1/sJ per face
 
 struct HexParams {
     long long K, e_begin, e_count;
+    // strided element ranges (pipelined host step: chunks along y of a structured slab): the e_count elements are
+    // e_count / seg_len segments of seg_len consecutive elements, segment s starting at e_begin + s * seg_stride.
+    // seg_len == 0: one contiguous range.  Batches never straddle a segment.
+    long long seg_len, seg_stride;
     long long q_stride;      // Nq*K
     long long t_stride;      // Nfq*K + n_halo
     const double* Q;
@@ -104,6 +108,22 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 // the mbarrier also waits for every cp.async this thread has issued so far (counts as this thread's arrival)
 __device__ __forceinline__ void cp_async_mbar_arrive(unsigned long long* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// batches of EB elements over the (possibly strided) element range of a launch
+__device__ __forceinline__ long long range_batches(const HexParams& p, int EB) {
+    if (p.seg_len <= 0) return (p.e_count + EB - 1) / EB;
+    return (p.e_count / p.seg_len) * ((p.seg_len + EB - 1) / EB);
+}
+__device__ __forceinline__ void range_batch(const HexParams& p, int EB, long long bi, long long& e0, int& nb) {
+    if (p.seg_len <= 0) {
+        e0 = p.e_begin + bi * EB;
+        nb = (int)max(0LL, min((long long)EB, p.e_begin + p.e_count - e0));
+        return;
+    }
+    const long long bps = (p.seg_len + EB - 1) / EB, seg = bi / bps, w = bi - seg * bps;
+    e0 = p.e_begin + seg * p.seg_stride + w * EB;
+    nb = seg * p.seg_len < p.e_count ? (int)max(0LL, min((long long)EB, p.seg_len - w * EB)) : 0;
 }
 
 template <int n>

@@ -77,6 +77,8 @@ void fill_hex_params(esdg_ctx* ctx, HexParams& p) {
     p.K = d.K;
     p.e_begin = 0;
     p.e_count = d.K;
+    p.seg_len = 0;
+    p.seg_stride = 0;
     p.q_stride = (long long)d.Nq * d.K;
     p.t_stride = ctx->trace_stride;
     p.Q = ctx->Q;
@@ -140,14 +142,20 @@ int set_attrs(esdg_ctx* ctx) {
     return ESDG_OK;
 }
 
+long long host_batches(const HexParams& p, int EB) {   // == range_batches (hex_common.cuh)
+    if (p.seg_len <= 0) return (p.e_count + EB - 1) / EB;
+    return (p.e_count / p.seg_len) * ((p.seg_len + EB - 1) / EB);
+}
+
 template <int n>
-int launch_traces_n(esdg_ctx* ctx, const double* Q, long long e_begin = 0, long long e_count = -1) {
+int launch_traces_n(esdg_ctx* ctx, const double* Q, long long e_begin = 0, long long e_count = -1, long long seg_len = 0,
+                    long long seg_stride = 0) {
     HexFast* h = ctx->hex;
     HexParams p;
     fill_hex_params<n>(ctx, p);
     p.Q = Q;
-    if (e_count >= 0) { p.e_begin = e_begin; p.e_count = e_count; }
-    const int blocks = (int)((p.e_count + h->EB_tr - 1) / h->EB_tr);
+    if (e_count >= 0) { p.e_begin = e_begin; p.e_count = e_count; p.seg_len = seg_len; p.seg_stride = seg_stride; }
+    const int blocks = (int)host_batches(p, h->EB_tr);
     tick(ctx, "hex_traces");
     k_hex_traces<n><<<blocks, h->threads_tr, h->smem_traces, ctx->stream>>>(p);
     tock(ctx);
@@ -160,7 +168,7 @@ int launch_stage_n(esdg_ctx* ctx, const HexParams& p, int reserve_sms = 0) {
     HexFast* h = ctx->hex;
     tick(ctx, "hex_stage");
     // the persistent kernel wants at least two batches per SM (its pipeline overlaps batch i with i +- 1)
-    const long long nbatch_ws = (p.e_count + h->EB_ws - 1) / h->EB_ws;
+    const long long nbatch_ws = host_batches(p, h->EB_ws);
     const bool ws = h->kernel_choice == 2 || (h->kernel_choice == 0 && nbatch_ws >= 2LL * h->sms);
     if (ws) {
         // the persistent CTAs take every register of their SM: while a halo exchange is in flight a few SMs stay free
@@ -171,7 +179,7 @@ int launch_stage_n(esdg_ctx* ctx, const HexParams& p, int reserve_sms = 0) {
         else
             k_hex_stage_ws<n, false><<<grid, h->threads_ws, h->smem_ws, ctx->stream>>>(p);
     } else {
-        const int blocks = (int)((p.e_count + h->EB - 1) / h->EB);
+        const int blocks = (int)host_batches(p, h->EB);
         if (h->diag)
             k_hex_stage_line<n, true><<<blocks, h->threads, h->smem_stage, ctx->stream>>>(p);
         else
@@ -303,17 +311,18 @@ int hexfast_traces(esdg_ctx* ctx, const double* Q) {
     return fail(ctx, ESDG_EINVAL, "hex path: unsupported degree");
 }
 
-int hexfast_traces_range(esdg_ctx* ctx, const double* Q, long long e_begin, long long e_count) {
+int hexfast_traces_range(esdg_ctx* ctx, const double* Q, long long e_begin, long long e_count, long long seg_len, long long seg_stride) {
     switch (ctx->hex->n) {
-        case 2: return launch_traces_n<2>(ctx, Q, e_begin, e_count);
-        case 3: return launch_traces_n<3>(ctx, Q, e_begin, e_count);
-        case 4: return launch_traces_n<4>(ctx, Q, e_begin, e_count);
-        case 5: return launch_traces_n<5>(ctx, Q, e_begin, e_count);
+        case 2: return launch_traces_n<2>(ctx, Q, e_begin, e_count, seg_len, seg_stride);
+        case 3: return launch_traces_n<3>(ctx, Q, e_begin, e_count, seg_len, seg_stride);
+        case 4: return launch_traces_n<4>(ctx, Q, e_begin, e_count, seg_len, seg_stride);
+        case 5: return launch_traces_n<5>(ctx, Q, e_begin, e_count, seg_len, seg_stride);
     }
     return fail(ctx, ESDG_EINVAL, "hex path: unsupported degree");
 }
 
-int hexfast_stage_range(esdg_ctx* ctx, const double* Q, int mode, double a, double b, double dt, long long e_begin, long long e_count) {
+int hexfast_stage_range(esdg_ctx* ctx, const double* Q, int mode, double a, double b, double dt, long long e_begin, long long e_count,
+                        long long seg_len, long long seg_stride) {
     HexFast* h = ctx->hex;
     HexParams p;
     switch (h->n) {
@@ -325,6 +334,8 @@ int hexfast_stage_range(esdg_ctx* ctx, const double* Q, int mode, double a, doub
     p.Q = Q;
     p.e_begin = e_begin;
     p.e_count = e_count;
+    p.seg_len = seg_len;
+    p.seg_stride = seg_stride;
     p.mode = mode;
     p.rk_a = a; p.rk_b = b; p.dt = dt;
     switch (h->n) {

@@ -32,7 +32,9 @@ void hexfast_destroy(esdg_ctx* ctx);
 // traces + log stash of state Q into a fresh buffer (becomes `prod`)
 int hexfast_traces(esdg_ctx* ctx, const double* Q);
 // element-range versions for the pipelined host step (buffers selected by the caller through h->prod / h->cons)
-int hexfast_traces_range(esdg_ctx* ctx, const double* Q, long long e_begin, long long e_count);
-int hexfast_stage_range(esdg_ctx* ctx, const double* Q, int mode, double a, double b, double dt, long long e_begin, long long e_count);
+// (seg_len, seg_stride): strided ranges, see HexParams (0, 0 = contiguous)
+int hexfast_traces_range(esdg_ctx* ctx, const double* Q, long long e_begin, long long e_count, long long seg_len = 0, long long seg_stride = 0);
+int hexfast_stage_range(esdg_ctx* ctx, const double* Q, int mode, double a, double b, double dt, long long e_begin, long long e_count,
+                        long long seg_len = 0, long long seg_stride = 0);
 // one rhs evaluation (mode 0) or fused LSRK stage (mode 1) over a part of the elements
 int hexfast_stage(esdg_ctx* ctx, const double* Q, int mode, double a, double b, double dt, int want_rhstest, int part);

@@ -74,8 +74,9 @@ __global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex
     double* s_lp = s_lm + n;
     double* s_w = s_lp + n;
     const int tid = threadIdx.x;
-    const long long e0 = p.e_begin + (long long)blockIdx.x * EB;
-    const int nb = (int)min((long long)EB, p.e_begin + p.e_count - e0);
+    long long e0;
+    int nb;
+    range_batch(p, EB, blockIdx.x, e0, nb);
     constexpr int MAXF = (EF + NT - 1) / NT;
     int ipv[MAXF];
 #pragma unroll
@@ -157,8 +158,9 @@ __global__ void __launch_bounds__(TraceDims<n>::THREADS) k_hex_traces(const __gr
     double* s_lp = s_lm + n;
     const int tid = threadIdx.x;
     if (tid < n) { s_lm[tid] = p.lm[tid]; s_lp[tid] = p.lp[tid]; }
-    const long long e0 = p.e_begin + (long long)blockIdx.x * EB;
-    const int nb = (int)min((long long)EB, p.e_begin + p.e_count - e0);
+    long long e0;
+    int nb;
+    range_batch(p, EB, blockIdx.x, e0, nb);
     bool bad = false;
     stage_geo<EB>(tid, NT, nb, e0, p, sGeo);
     for (int it = tid; it < nb * G::Nq; it += NT) node_entropy<n, EB>(it, e0 * G::Nq + it, p, sV, bad);

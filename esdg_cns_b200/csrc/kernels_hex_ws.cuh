@@ -110,8 +110,7 @@ __global__ void __launch_bounds__(WsDims<n>::THREADS, 1) k_hex_stage_ws(const __
         s_w[tid] = p.w[tid];
     }
     __syncthreads();
-    const long long nbatch = (p.e_count + EB - 1) / EB;
-    const long long e_end = p.e_begin + p.e_count;
+    const long long nbatch = range_batches(p, EB);
 #ifdef ESDG_PHASE_TIMING
     __shared__ unsigned long long s_cyc[16];
     if (tid < 16) s_cyc[tid] = 0;
@@ -125,11 +124,11 @@ __global__ void __launch_bounds__(WsDims<n>::THREADS, 1) k_hex_stage_ws(const __
         const double c_igm = 1.0 / (2.0 * (p.gamma - 1.0));
         // exterior traces of this thread's two face points: indices read one batch ahead, copies issued as soon as the
         // thread is done with the previous ones (no other thread touches these shared-memory slots)
-        const long long stride_e = (long long)gridDim.x * EB;
         int ipn[2] = {0, 0};
         {
-            const long long e0 = p.e_begin + (long long)blockIdx.x * EB;
-            const int nb = (int)min((long long)EB, e_end - e0);
+            long long e0;
+            int nb;
+            range_batch(p, EB, blockIdx.x, e0, nb);
             if (tid < nb * NL) {
                 line_mapP<n, EB>(tid, e0, p, ipn);
                 line_gather<n, EB>(tid, ipn, p, sPx);
@@ -138,16 +137,17 @@ __global__ void __launch_bounds__(WsDims<n>::THREADS, 1) k_hex_stage_ws(const __
         unsigned it = 0;
         for (long long bi = blockIdx.x; bi < nbatch; bi += gridDim.x, ++it) {
             const int b = it & 1;
-            const long long e0 = p.e_begin + bi * EB;
-            const int nb = (int)min((long long)EB, e_end - e0);
-            const int nb1 = (int)max(0LL, min((long long)EB, e_end - (e0 + stride_e)));
+            long long e0, e1 = 0;
+            int nb, nb1 = 0;
+            range_batch(p, EB, bi, e0, nb);
+            if (bi + gridDim.x < nbatch) range_batch(p, EB, bi + gridDim.x, e1, nb1);
             const double* sWV0 = sIn + b * D::IN_DOUBLES;
             const double* sWV = sWV0 + ((e0 * Nq) & 1);       // batch stored with the parity of its first global node index
             const double* sWF = sWV0 + D::WV_DOUBLES;
             const double* sGeo = sGeo3 + (it % 3) * D::GEO_DOUBLES;
             const bool active = tid < nb * NL, active1 = tid < nb1 * NL;
             double acc[n][5];
-            if (active1) line_mapP<n, EB>(tid, e0 + stride_e, p, ipn);
+            if (active1) line_mapP<n, EB>(tid, e1, p, ipn);
             WS_MARK(0);
             mbar_wait(&full_wv[b], (it >> 1) & 1);
             WS_MARK(1);
@@ -272,10 +272,19 @@ __global__ void __launch_bounds__(WsDims<n>::THREADS, 1) k_hex_stage_ws(const __
             for (int k = pt; k < nb * Nq; k += NPT) node_prims_inplace<n, EB>(k, p, sWV, bad);
             mbar_arrive(&full_wv[b]);
         };
-        const long long stride_e = (long long)gridDim.x * EB;
         const unsigned nloc = (unsigned)((nbatch - blockIdx.x + gridDim.x - 1) / gridDim.x);   // batches of this CTA
-        auto batch_e0 = [&](unsigned i) { return p.e_begin + (long long)blockIdx.x * EB + i * stride_e; };
-        auto batch_nb = [&](unsigned i) { return (int)min((long long)EB, e_end - batch_e0(i)); };
+        auto batch_e0 = [&](unsigned i) {
+            long long e0;
+            int nb;
+            range_batch(p, EB, (long long)blockIdx.x + (long long)i * gridDim.x, e0, nb);
+            return e0;
+        };
+        auto batch_nb = [&](unsigned i) {
+            long long e0;
+            int nb;
+            range_batch(p, EB, (long long)blockIdx.x + (long long)i * gridDim.x, e0, nb);
+            return nb;
+        };
         // step j runs beside the line warps' batch j-1: loads of batch j, update + traces of batch j-2, primitives of
         // batch j (single call sites, so that the three lambdas are inlined)
 #if defined(ESDG_WS_EXPERIMENT) && ESDG_WS_EXPERIMENT == 1   // timing experiment: line team alone (garbage data)

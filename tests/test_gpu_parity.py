@@ -312,10 +312,13 @@ def test_hex_line_kernel_matches_generic_kernels(monkeypatch):
     assert _relerr(Qa, Qb) < 1e-12
 
 
-@pytest.mark.parametrize("N,mesh,nsteps,chunks", [(4, (32, 32, 10), 1, None), (3, (40, 40, 6), 2, None), (2, (5, 4, 3), 1, None),
-                                                  (4, (16, 16, 24), 1, 12), (4, (16, 16, 24), 1, 7), (3, (12, 10, 22), 3, 11),
-                                                  (2, (8, 8, 32), 1, 32)])
-def test_pipelined_host_step_is_bitwise_the_resident_loop(N, mesh, nsteps, chunks, monkeypatch):
+@pytest.mark.parametrize("N,mesh,nsteps,chunks,structured", [
+    (4, (32, 32, 10), 1, None, False), (3, (40, 40, 6), 2, None, False), (2, (5, 4, 3), 1, None, False),
+    (4, (16, 16, 24), 1, 12, False), (4, (16, 16, 24), 1, 7, False), (3, (12, 10, 22), 3, 11, False), (2, (8, 8, 32), 1, 32, False),
+    # device-generated structured meshes: chunks along y, strided element ranges (even / uneven row counts, many chunks)
+    (4, (32, 32, 10), 1, None, True), (4, (20, 24, 5), 2, 5, True), (3, (16, 37, 6), 2, 9, True), (2, (8, 64, 3), 1, 64, True),
+    (4, (12, 16, 7), 1, -4, True)])
+def test_pipelined_host_step_is_bitwise_the_resident_loop(N, mesh, nsteps, chunks, structured, monkeypatch):
     """esdg_lsrk45_host (wavefront of (chunk, stage) tasks behind the chunked upload, downloads behind the finished
     chunks) == upload + lsrk45 + download, for chunk counts that split layers evenly, unevenly and one layer per chunk."""
     import torch
@@ -323,7 +326,7 @@ def test_pipelined_host_step_is_bitwise_the_resident_loop(N, mesh, nsteps, chunk
         monkeypatch.setenv("ESDG_HOST_CHUNKS", str(chunks))
     from esdg_cns_b200 import api, setup_dg as SD
     prd, pops = SD.reference_hex(N)
-    pmd = SD.uniform_hex_mesh_md(prd, mesh, domain=((-np.pi, np.pi),) * 3)
+    pmd = (SD.structured_hex_md if structured else SD.uniform_hex_mesh_md)(prd, mesh, domain=((-np.pi, np.pi),) * 3)
     x, y, z = SD.hex_node_coords(prd, pmd)
     rho, u, v, w, p = SD.taylor_green(x, y, z)
     Q = SD.primitive_to_conservative(rho + .05 * np.sin(x) * np.cos(z), (u, v, w + .1 * np.sin(y)), p)
