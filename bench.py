@@ -230,8 +230,10 @@ def other_configs(device, peak_gbs):
     md = SD.uniform_quad_mesh_md(rd, 1024, 1024, domain=((0, 20), (-5, 5)))
     rho, u, v, p = SD.vortex(md.xq, md.yq)
     Q = SD.primitive_to_conservative(rho, (u, v), p)
-    run("1: quad N=3 1024^2 vortex (generic kernels)", api.Solver(md, ops, device=device), Q, 1e-4, 4, (N + 1) ** 2, 4 * (N + 1), 2,
-        ["generic_rhs", "generic_traces"], md.K)
+    sq = api.Solver(md, ops, device=device)
+    tp = sq.kernel_path() == "quad_line"
+    run("1: quad N=3 1024^2 vortex (%s kernels)" % ("tensor-product" if tp else "generic"), sq, Q, 1e-4, 4, (N + 1) ** 2, 4 * (N + 1), 2,
+        ["quad_stage"] if tp else ["generic_rhs", "generic_traces"], md.K)
     del md, Q
     # config 3: CNS lid-driven cavity, modal quads N=3, 512^2, BCTYPE 1, both dissipations on
     rd, ops = SD.reference_quad_modal(N)

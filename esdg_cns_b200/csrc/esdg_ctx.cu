@@ -1,6 +1,7 @@
 // libesdg_b200.so -- C ABI implementation (see include/esdg_b200.h).
 #include "ctx_util.h"
 #include "hex_fast.h"
+#include "quad_fast.h"
 #include <algorithm>
 #include <functional>
 
@@ -191,7 +192,7 @@ int cns_stage(esdg_ctx* ctx, const double* Qsrc, int mode, double a, double b, d
 int total_partials(const esdg_ctx* ctx) {
     // hex path: one slot per element (a batch writes the slot of its first element, the rest stay zero), so the
     // deterministic reduction does not depend on which stage kernel / batch size / element split produced them
-    return ctx->hex ? (int)ctx->d.K : grid_blocks(ctx);
+    return (ctx->hex || ctx->quad) ? (int)ctx->d.K : grid_blocks(ctx);
 }
 
 int reduce_rhstest(esdg_ctx* ctx, bool split) {
@@ -210,6 +211,7 @@ int reduce_rhstest(esdg_ctx* ctx, bool split) {
 int do_traces(esdg_ctx* ctx, const double* Q) {
     if (ctx->cns.on) return cns_traces(ctx, Q);
     if (ctx->hex) return hexfast_traces(ctx, Q);
+    if (ctx->quad) return quadfast_traces(ctx, Q);
     return launch_traces(ctx, Q);
 }
 
@@ -233,6 +235,11 @@ int do_stage(esdg_ctx* ctx, const double* Q, int mode, double a, double b, doubl
     }
     if (ctx->hex) {
         if ((rc = hexfast_stage(ctx, Q, mode, a, b, dt, want, part))) return rc;
+        if (want && part != ESDG_PART_BOUNDARY) return reduce_rhstest(ctx, part == ESDG_PART_INTERIOR);
+        return ESDG_OK;
+    }
+    if (ctx->quad) {
+        if ((rc = quadfast_stage(ctx, Q, mode, a, b, dt, want, part))) return rc;
         if (want && part != ESDG_PART_BOUNDARY) return reduce_rhstest(ctx, part == ESDG_PART_INTERIOR);
         return ESDG_OK;
     }
@@ -311,6 +318,7 @@ int esdg_destroy(esdg_ctx* ctx) {
     comm_destroy(ctx);
     for (void* p : ctx->allocs) cudaFree(p);
     hexfast_destroy(ctx);
+    quadfast_destroy(ctx);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ESDG_OK;
@@ -907,6 +915,7 @@ int esdg_finalize(esdg_ctx* ctx) {
         return fail(ctx, ESDG_EINVAL, "esdg_finalize: wall BCs need the CNS path (call esdg_set_viscosity; mu = 0 gives Euler with walls)");
     }
     if (!ctx->cns.on && (rc = hexfast_try_create(ctx))) return rc;
+    if (!ctx->cns.on && (rc = quadfast_try_create(ctx))) return rc;
     if (ctx->hex) {
         bool diag = true;                                  // a structured box is axis-aligned by construction
         for (int64_t e = 0; e < d.K && diag && !ctx->structured; ++e)
@@ -1190,8 +1199,10 @@ int esdg_sync(esdg_ctx* ctx) {
 }
 
 // ---- multi-GPU plumbing ----------------------------------------------------------
-static double* cur_traces(esdg_ctx* ctx) { return ctx->hex ? ctx->hex->trace[ctx->hex->prod] : ctx->traces; }
-static int cur_planes(const esdg_ctx* ctx) { return ctx->hex ? ESDG_HEX_TRACE_PLANES : ctx->NF; }
+static double* cur_traces(esdg_ctx* ctx) {
+    return ctx->hex ? ctx->hex->trace[ctx->hex->prod] : (ctx->quad ? ctx->quad->trace[ctx->quad->prod] : ctx->traces);
+}
+static int cur_planes(const esdg_ctx* ctx) { return ctx->hex ? ESDG_HEX_TRACE_PLANES : (ctx->quad ? ESDG_QUAD_TRACE_PLANES : ctx->NF); }
 
 int esdg_trace_planes(esdg_ctx* ctx) { return ctx ? cur_planes(ctx) : 0; }
 
@@ -1199,6 +1210,7 @@ const char* esdg_kernel_path(const esdg_ctx* ctx) {
     if (!ctx || !ctx->finalized) return "";
     if (ctx->cns.on) return "cns";
     if (ctx->hex) return ctx->hex->diag ? "hex_line_diag" : "hex_line";
+    if (ctx->quad) return "quad_line";
     return "generic";
 }
 

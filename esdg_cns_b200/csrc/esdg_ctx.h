@@ -105,6 +105,8 @@ struct esdg_ctx {
 
     // specialised hex path (kernels_hex.cuh); null if the operators do not match
     struct HexFast* hex = nullptr;
+    // specialised quad path (kernels_quad_line.cuh); null if the operators do not match
+    struct QuadFast* quad = nullptr;
     CnsState cns;
     DopriState dopri;
     double* rhs_target = nullptr;   // where mode-0 rhs evaluations write (default: rhs)

@@ -1,0 +1,133 @@
+"""GPU parity of the tensor-product QUAD kernels (esdg_cns_b200/csrc/kernels_quad_line.cuh; BASELINE config 1,
+dg2D_euler_quad.jl:141-207) against the numpy oracle, the generic table-driven kernels and the LSRK45 loop.
+
+Tolerance: the north star's 1e-12 relative in FP64 (helpers.parity_tol raises it to 4x the oracle's own rounding cloud
+where the reference's logmean formula is conditioned worse than that).
+"""
+import numpy as np
+import pytest
+
+from helpers import relerr as _relerr, parity_tol
+
+pytestmark = pytest.mark.gpu
+
+
+def _sheared(N, Kx, Ky):
+    """The vortex mesh of config 1 under a linear shear: every element an (affine) parallelogram, all four geometric
+    factors non-zero.  Connectivity (periodic mapP) is that of the unsheared mesh."""
+    from oracle import solvers as SV, setupdg as S, mesh as M, physics as P
+    rd, md0, ops, _ = SV.setup_quad_vortex(N, Kx, Ky)
+    VX, VY, EToV = M.uniform_quad_mesh(Kx, Ky)
+    VX = 15 * (1 + VX) / 2
+    VY = 5 * VY
+    md = S.init_mesh((VX + .3 * VY, VY + .1 * VX), EToV, rd)
+    md.mapP = md0.mapP
+    SV.interp_geofacs(md, rd, ops)
+    rho, u, v, p = P.vortex(md0.xq, md0.yq, 0)
+    Q = list(P.primitive_to_conservative(rho, (u, v), p))
+    return rd, md, ops, Q
+
+
+@pytest.mark.parametrize("N,Kx,Ky", [(1, 5, 4), (2, 7, 3), (3, 16, 16), (4, 6, 9)])
+@pytest.mark.parametrize("lf", [0.0, 0.5])
+def test_quad_line_rhs_matches_oracle(N, Kx, Ky, lf):
+    from oracle import solvers as SV
+    from esdg_cns_b200 import api
+    rd, md, ops, Q = SV.setup_quad_vortex(N, Kx, Ky)
+    ops.lf_scale = lf
+    ref, rt_ref = SV.rhs_collocated(Q, md, ops, rd, lf, True)
+    s = api.Solver(md, ops)
+    assert s.kernel_path() == "quad_line" and s.trace_planes() == 7
+    out, rt = s.rhs(Q, True)
+    tol = parity_tol(lambda: SV.rhs_collocated(Q, md, ops, rd, lf, False)[0], ref)
+    err = _relerr(out, ref)
+    print(f"quad N={N} {Kx}x{Ky} lf={lf}: relerr {err:.2e} tol {tol:.2e} rhstest {rt:.3e} (oracle {rt_ref:.3e})")
+    assert err < tol
+    assert abs(rt - rt_ref) < 1e-11 * max(1.0, abs(rt_ref))
+    if lf == 0.0:
+        assert abs(rt) < 1e-11
+
+
+@pytest.mark.parametrize("N", [2, 3])
+def test_quad_line_sheared_mesh(N):
+    """Parallelogram elements: the general (non-diagonal) metric contraction and oblique normals."""
+    from oracle import solvers as SV
+    from esdg_cns_b200 import api
+    rd, md, ops, Q = _sheared(N, 6, 5)
+    ref, rt_ref = SV.rhs_collocated(Q, md, ops, rd, .5, True)
+    s = api.Solver(md, ops)
+    assert s.kernel_path() == "quad_line"
+    out, rt = s.rhs(Q, True)
+    err = _relerr(out, ref)
+    tol = parity_tol(lambda: SV.rhs_collocated(Q, md, ops, rd, .5, False)[0], ref)
+    print(f"sheared quad N={N}: relerr {err:.2e} tol {tol:.2e}")
+    assert err < tol
+    assert abs(rt - rt_ref) < 1e-11 * max(1.0, abs(rt_ref))
+
+
+def test_quad_line_matches_generic_kernels(monkeypatch):
+    """Same operators through the table-driven kernels (ESDG_FORCE_GENERIC): rhs and 3 LSRK45 steps agree within the
+    rounding cloud of the reference formula (both sit ~1e-12 from the oracle on the vortex's near-uniform far field)."""
+    from oracle import solvers as SV
+    from esdg_cns_b200 import api
+    rd, md, ops, Q = SV.setup_quad_vortex(3, 9, 7)
+    res = []
+    for force in (False, True):
+        if force:
+            monkeypatch.setenv("ESDG_FORCE_GENERIC", "1")
+        s = api.Solver(md, ops)
+        assert s.kernel_path() == ("quad_line" if not force else s.kernel_path())
+        r, rt = s.rhs(Q, True)
+        s.upload(Q)
+        rts = s.lsrk45(1e-2, 3, want_rhstest=True)
+        res.append((r, rt, s.download(), rts, s.kernel_path()))
+        s.close()
+    assert res[0][4] == "quad_line" and res[1][4] != "quad_line"
+    ref = SV.rhs_collocated(Q, md, ops, rd, .5, False)[0]
+    assert _relerr(res[0][0], res[1][0]) < 2 * parity_tol(lambda: SV.rhs_collocated(Q, md, ops, rd, .5, False)[0], ref)
+    assert abs(res[0][1] - res[1][1]) < 1e-12
+    assert max(np.abs(a - b).max() for a, b in zip(res[0][2], res[1][2])) < 1e-12
+    assert abs(res[0][3] - res[1][3]) < 1e-12
+
+
+def test_quad_line_lsrk45_matches_oracle_steps():
+    """Config 1 at the script's CFL: 5 LSRK45 steps (25 fused stage launches) against the oracle's loop."""
+    from oracle import solvers as SV
+    from esdg_cns_b200 import api
+    N, K1D = 3, 16
+    rd, md, ops, Q = SV.setup_quad_vortex(N, K1D, K1D)
+    dt = 2 * (2 / K1D) / ((N + 1) * (N + 2) / 2)
+    Qo, res = [q.copy() for q in Q], [np.zeros_like(q) for q in Q]
+    for _ in range(5):
+        Qo, res, rto = SV.lsrk45_step(Qo, res, dt, lambda q, t: SV.rhs_collocated(q, md, ops, rd, .5, t))
+    s = api.Solver(md, ops)
+    s.upload(Q)
+    n0 = s.kernel_launches()
+    rtg = s.lsrk45(dt, 5, want_rhstest=True)
+    Qg = s.download()
+    err = max(np.abs(a - b).max() for a, b in zip(Qg, Qo))
+    print(f"quad config 1, 5 steps: max abs err {err:.2e}; launches {s.kernel_launches() - n0}")
+    assert err < 1e-12
+    assert abs(rtg - rto) < 1e-12
+
+
+def test_quad_line_ragged_last_batch_and_freestream():
+    """K not a multiple of the CTA batch (16 elements at N=3); a constant state has zero rhs."""
+    from esdg_cns_b200 import api, setup_dg as SD
+    prd, pops = SD.reference_quad(3)
+    pmd = SD.uniform_quad_mesh_md(prd, 7, 5)
+    s = api.Solver(pmd, pops)
+    assert s.kernel_path() == "quad_line"
+    Q = [np.full((16, 35), v) for v in (1.1, .3, -.2, 2.5)]
+    out, _ = s.rhs(Q, False)
+    assert max(np.abs(r).max() for r in out) < 1e-12
+
+
+def test_quad_line_domain_error():
+    from esdg_cns_b200 import api, setup_dg as SD, _lib
+    prd, pops = SD.reference_quad(2)
+    pmd = SD.uniform_quad_mesh_md(prd, 4, 4)
+    Q = [np.full((9, 16), v) for v in (1.0, .3, -.2, 2.5)]
+    Q[0][4, 7] = -1.0
+    with pytest.raises(_lib.DomainError):
+        api.rhs(Q, pmd, pops)
