@@ -139,6 +139,7 @@ void fill_cns(esdg_ctx* ctx, CnsParams& P, const double* Qsrc) {
 }
 
 int cns_traces(esdg_ctx* ctx, const double* Qsrc) {
+    if (ctx->quad) return quadfast_traces(ctx, Qsrc);      // Gauss-nodal tensor-product path (kernels_cnsq.cuh)
     CnsParams P;
     fill_cns(ctx, P, Qsrc);
     tick(ctx, "cns_traces");
@@ -150,6 +151,7 @@ int cns_traces(esdg_ctx* ctx, const double* Qsrc) {
 
 // sigma pass (the V traces of Qsrc, halo included, must be valid): sigma (modal) + sigma traces of the local elements
 int cns_sigma_pass(esdg_ctx* ctx, const double* Qsrc, int want) {
+    if (ctx->quad) return cnsq_sigma(ctx, Qsrc, want);
     CnsParams P;
     fill_cns(ctx, P, Qsrc);
     P.g.want_rhstest = want;
@@ -162,6 +164,18 @@ int cns_sigma_pass(esdg_ctx* ctx, const double* Qsrc, int want) {
 
 // rhs pass (V traces and sigma traces, halo included, must be valid)
 int cns_rhs_pass(esdg_ctx* ctx, const double* Qsrc, int mode, double a, double b, double dt, int want) {
+    if (ctx->quad) {
+        int rc = cnsq_rhs(ctx, Qsrc, mode, a, b, dt, want);
+        if (rc) return rc;
+        if (want) {
+            tick(ctx, "reduce_partials");
+            k_reduce_partials_cns<<<1, 256, 0, ctx->stream>>>(ctx->partials, ctx->cns.partial_vrhs, ctx->cns.partial_visc, cnsq_blocks(ctx),
+                                                             ctx->rhstest_dev);
+            tock(ctx);
+            CK(cudaGetLastError());
+        }
+        return ESDG_OK;
+    }
     CnsParams P;
     fill_cns(ctx, P, Qsrc);
     P.g.mode = mode;
@@ -230,7 +244,7 @@ int do_stage(esdg_ctx* ctx, const double* Q, int mode, double a, double b, doubl
             rc = cns_stage(ctx, Q, mode, a, b, dt, want);
         }
         if (rc) return rc;
-        if (mode == 1) return cns_traces(ctx, ctx->Q);
+        if (mode == 1 && !ctx->quad) return cns_traces(ctx, ctx->Q);   // the tensor-product stage kernel wrote them
         return ESDG_OK;
     }
     if (ctx->hex) {
@@ -911,6 +925,7 @@ int esdg_finalize(esdg_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->rhstest_dev, 0, 2 * sizeof(double), ctx->stream));
     if (ctx->cns.on) {
         if ((rc = finalize_cns(ctx))) return rc;
+        if ((rc = cnsq_try_create(ctx))) return rc;
     } else if (!ctx->cns.wall.empty() || !ctx->cns.lid.empty() || !ctx->cns.inflow.empty() || !ctx->cns.outflow.empty()) {
         return fail(ctx, ESDG_EINVAL, "esdg_finalize: wall BCs need the CNS path (call esdg_set_viscosity; mu = 0 gives Euler with walls)");
     }
@@ -940,8 +955,11 @@ int esdg_upload_state(esdg_ctx* ctx, const double* const* Q) {
     if (rc) return rc;
     if (!Q) return fail(ctx, ESDG_EINVAL, "esdg_upload_state: Q is NULL");
     const size_t n = (size_t)ctx->d.Ns * ctx->d.K;
+    const bool nodal = ctx->quad && ctx->quad->cns;      // state kept in the Gauss-nodal basis (kernels_cnsq.cuh)
+    double* dst = nodal ? ctx->Qin : ctx->Q;
     for (int f = 0; f < ctx->NF; ++f)
-        CK(cudaMemcpyAsync(ctx->Q + f * n, Q[f], n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(dst + f * n, Q[f], n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (nodal && (rc = cnsq_basis(ctx, true, ctx->Qin, ctx->Q))) return rc;
     CK(cudaMemsetAsync(ctx->res, 0, ctx->NF * n * sizeof(double), ctx->stream));
     ctx->traces_valid = false;
     ctx->dopri.ready = false;
@@ -953,8 +971,13 @@ int esdg_download_state(esdg_ctx* ctx, double* const* Q) {
     if (rc) return rc;
     if (!Q) return fail(ctx, ESDG_EINVAL, "esdg_download_state: Q is NULL");
     const size_t n = (size_t)ctx->d.Ns * ctx->d.K;
+    const double* src = ctx->Q;
+    if (ctx->quad && ctx->quad->cns) {
+        if ((rc = cnsq_basis(ctx, false, ctx->Q, ctx->Qin))) return rc;
+        src = ctx->Qin;
+    }
     for (int f = 0; f < ctx->NF; ++f)
-        CK(cudaMemcpyAsync(Q[f], ctx->Q + f * n, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(Q[f], src + f * n, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     return check_bad(ctx);
 }
 
@@ -966,17 +989,25 @@ int esdg_rhs(esdg_ctx* ctx, const double* const* Q, double* const* rhs_out, int 
         return fail(ctx, ESDG_EINVAL, "esdg_rhs: context has halo points; drive it with esdg_compute_traces / esdg_stage_update");
     const size_t n = (size_t)ctx->d.Ns * ctx->d.K;
     const double* src = ctx->Q;
+    const bool nodal = ctx->quad && ctx->quad->cns;
     if (Q) {
+        double* stage = nodal ? ctx->rhs : ctx->Qin;
         for (int f = 0; f < ctx->NF; ++f)
-            CK(cudaMemcpyAsync(ctx->Qin + f * n, Q[f], n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(stage + f * n, Q[f], n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (nodal && (rc = cnsq_basis(ctx, true, ctx->rhs, ctx->Qin))) return rc;
         src = ctx->Qin;
     }
     if (!(src == ctx->Q && ctx->traces_valid))
         if ((rc = do_traces(ctx, src))) return rc;
     if ((rc = do_stage(ctx, src, 0, 0, 0, 0, compute_rhstest, ESDG_PART_ALL))) return rc;
     ctx->traces_valid = (src == ctx->Q);
+    const double* out = ctx->rhs;
+    if (nodal) {                                   // the stage is done with its source: Qin is free again
+        if ((rc = cnsq_basis(ctx, false, ctx->rhs, ctx->Qin))) return rc;
+        out = ctx->Qin;
+    }
     for (int f = 0; f < ctx->NF; ++f)
-        CK(cudaMemcpyAsync(rhs_out[f], ctx->rhs + f * n, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(rhs_out[f], out + f * n, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     double t[2] = {0, 0};
     if (compute_rhstest) CK(cudaMemcpyAsync(t, ctx->rhstest_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if ((rc = check_bad(ctx))) return rc;
@@ -1208,7 +1239,7 @@ int esdg_trace_planes(esdg_ctx* ctx) { return ctx ? cur_planes(ctx) : 0; }
 
 const char* esdg_kernel_path(const esdg_ctx* ctx) {
     if (!ctx || !ctx->finalized) return "";
-    if (ctx->cns.on) return "cns";
+    if (ctx->cns.on) return ctx->quad ? "cns_quad_line" : "cns";
     if (ctx->hex) return ctx->hex->diag ? "hex_line_diag" : "hex_line";
     if (ctx->quad) return "quad_line";
     return "generic";
@@ -1441,10 +1472,14 @@ int esdg_dopri45_step(esdg_ctx* ctx, double* t, double* dt, double dt0, double e
     DopriArgs e;
     e.ns = 7;
     for (int s = 0; s < 7; ++s) { e.K[s] = D.K[s]; e.c[s] = DP_E[s]; }
-    tick(ctx, "dopri_err");
-    k_dopri_err<<<D.n_err_blocks, 256, 0, ctx->stream>>>(ctx->Q, e, err_tol, n, D.err_partial);
-    tock(ctx);
-    CK(cudaGetLastError());
+    if (ctx->quad && ctx->quad->cns) {               // the script's norm is taken over ITS coefficients
+        if ((rc = cnsq_dopri_err(ctx, e.K, e.c, err_tol, D.n_err_blocks, D.err_partial))) return rc;
+    } else {
+        tick(ctx, "dopri_err");
+        k_dopri_err<<<D.n_err_blocks, 256, 0, ctx->stream>>>(ctx->Q, e, err_tol, n, D.err_partial);
+        tock(ctx);
+        CK(cudaGetLastError());
+    }
     tick(ctx, "reduce_partials");
     k_reduce_partials<<<1, 256, 0, ctx->stream>>>(D.err_partial, D.n_err_blocks, D.err_dev);
     tock(ctx);

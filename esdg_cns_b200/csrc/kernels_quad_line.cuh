@@ -40,6 +40,16 @@ struct QuadParams {
     double* partial;
     int* bad;
     double T[64], lm[8], lp[8], w[8], lmw[8], lpw[8];
+    // compressible Navier-Stokes extension (kernels_cnsq.cuh; k_quad_stage_line<n, true>)
+    double* sig;             // 6 planes x q_stride: sigma_x[2..4], sigma_y[2..4] at the volume nodes
+    double* sig_tr;          // 6 planes x t_stride: the same at the face points
+    const unsigned char* bc; // [Nfq*K] bits 0-2: 0 interior, 1 wall, 2 lid; bit 3: member of md.mapB
+    const double* vlid;      // [Nfq*K] lid speed (read where kind == 2)
+    int bctype, viscous_dissp;
+    double lam, mu, Pr, Re, inv_theta2;   // lam already sign-flipped (dg2D_CNS_cavity_optimized.jl:614)
+    double D[64];            // 1-D differentiation matrix at the Gauss nodes
+    double* partial_visc;    // per CTA: sum wJq (theta . sigma)            (:802-806)
+    double* partial_vrhs;    // per CTA: sum wJq VUq . visc_rhs             (:966)
 };
 
 template <int n>
@@ -50,6 +60,8 @@ struct QuadDims {
     static constexpr int EN = EB * Nq, EF = EB * Nfq;
     // WV[6][EN] WF[7][EF] P[7][EF] A2[2][4][EN] (V[4][EN] aliases A2 block 0) geo[EB][17] lm lp w
     static constexpr int SMEM_DOUBLES = 6 * EN + 2 * QUAD_TP * EF + 8 * EN + EB * QUAD_GEO + 3 * n;
+    // CNS: own traces come straight from global memory; instead sigma at the nodes S[6][EN] and the exterior sigma traces SP[6][EF]
+    static constexpr int SMEM_DOUBLES_CNS = 6 * EN + QUAD_TP * EF + 8 * EN + 6 * EN + 6 * EF + EB * QUAD_GEO + 3 * n;
 };
 
 template <int W>
@@ -139,6 +151,59 @@ __device__ __forceinline__ void trace_from_entropy2_v(const VD<W>* V, const VD<W
     Tv[6] = vsqrt_fast(vabs(un)) + vsqrt_fast(c2);
 }
 
+__device__ __forceinline__ Node2 ld_node2_g(const double* Tp, long long S, long long idx) {
+    Node2 a;
+    a.rho = Tp[idx]; a.u[0] = Tp[S + idx]; a.u[1] = Tp[2 * S + idx]; a.beta = Tp[3 * S + idx]; a.lr = Tp[4 * S + idx]; a.lb = Tp[5 * S + idx];
+    return a;
+}
+// entropy variables 2..4 from the primitive trace (u/2, v/2, beta): v4 = -rho/rhoe = -2 (gamma-1) beta, v2 = -v4 u, v3 = -v4 v
+__device__ __forceinline__ void v234_from_prim(double hu, double hv, double beta, double gamma, double* V) {
+    const double c = 2.0 * (gamma - 1.0) * beta;
+    V[1] = 2.0 * c * hu;
+    V[2] = 2.0 * c * hv;
+    V[3] = -c;
+}
+// impose_BCs_entropyvars! (dg2D_CNS_cavity_optimized.jl:178-216): exterior entropy variables at a wall (kind 1) / lid (kind 2) node
+__device__ __forceinline__ void bc_entropy_vars_q(int bctype, int kind, double vlid, double inv_theta2, double nx, double ny, const double* Vf,
+                                                  double* VP) {
+    if (bctype == 1) {
+        VP[1] = kind == 2 ? -Vf[1] - 2 * vlid * Vf[3] : -Vf[1];
+        VP[2] = -Vf[2];
+        VP[3] = Vf[3];
+    } else if (bctype == 2) {
+        VP[1] = kind == 2 ? inv_theta2 - Vf[1] : -Vf[1];
+        VP[2] = -Vf[2];
+        VP[3] = -inv_theta2 - Vf[3];
+    } else if (bctype == 3) {
+        const double Vn = Vf[1] * nx + Vf[2] * ny;
+        VP[3] = Vf[3];
+        VP[1] = Vf[1] - 2 * Vn * nx;
+        VP[2] = Vf[2] - 2 * Vn * ny;
+    }
+}
+// impose_BCs_stress! (:218-262); s*[0..2] = fields 2..4
+__device__ __forceinline__ void bc_stress_q(int bctype, int kind, double vlid, double nx, double ny, const double* sxf, const double* syf,
+                                            double* sxP, double* syP) {
+    if (bctype == 1) {
+        sxP[0] = sxf[0]; syP[0] = syf[0];
+        sxP[1] = sxf[1]; syP[1] = syf[1];
+        sxP[2] = kind == 2 ? -sxf[2] + 2 * vlid * sxf[0] : -sxf[2];
+        syP[2] = kind == 2 ? -syf[2] + 2 * vlid * syf[0] : -syf[2];
+    } else if (bctype == 2) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { sxP[k] = sxf[k]; syP[k] = syf[k]; }
+    } else if (bctype == 3) {
+        const double snx = sxf[0] * nx + sxf[1] * ny;
+        const double sny = syf[0] * nx + syf[1] * ny;
+        sxP[0] = -sxf[0] + 2 * nx * snx;
+        syP[0] = -syf[0] + 2 * nx * sny;
+        sxP[1] = -sxf[1] + 2 * ny * snx;
+        syP[1] = -syf[1] + 2 * ny * sny;
+        sxP[2] = -sxf[2];
+        syP[2] = -syf[2];
+    }
+}
+
 // line l of an element: direction d (0: r, nodes i + n a at fixed i = m; 1: s, nodes a + n m), first node, stride and the
 // trace indices of its two end points (side 0: coordinate -1, side 1: +1)
 template <int n>
@@ -149,18 +214,23 @@ __device__ __forceinline__ void quad_line(int ll, int& d, int& base, int& stride
     else { base = n * m; stride = 1; f0 = m; f1 = 2 * n + (n - 1 - m); }                  // s = -1: face 1, s = +1: face 3 (reversed)
 }
 
-template <int n>
+// CNS = true: the inviscid part of rhsRK! with the wall mirror state (dg2D_CNS_cavity_optimized.jl:157-176, :447-528) plus, per line,
+// the BR1 divergence of sigma (k_cnsq_sigma, kernels_cnsq.cuh), its surface term with the stress BCs and the penalisation
+// (:590-611, :817-846); final rhs = (viscous numerator - inviscid numerator) / J.
+template <int n, bool CNS = false>
 __global__ void __launch_bounds__(QuadDims<n>::THREADS, 3) k_quad_stage_line(const __grid_constant__ QuadParams p) {
     using D = QuadDims<n>;
     constexpr int Nq = D::Nq, Nfq = D::Nfq, NL = D::NL, EB = D::EB, NT = D::THREADS, EN = D::EN, EF = D::EF;
     constexpr PairTab<n> PT{};
     extern __shared__ __align__(16) double sm[];
-    __shared__ double red[NT / 32];
+    __shared__ double red[2][NT / 32];
     double* sWV = sm;                       // [6][EN]
-    double* sWF = sWV + 6 * EN;             // [7][EF] own traces
-    double* sP = sWF + QUAD_TP * EF;        // [7][EF] exterior traces
+    double* sWF = sWV + 6 * EN;             // [7][EF] own traces (Euler only)
+    double* sP = CNS ? sWF : sWF + QUAD_TP * EF;   // [7][EF] exterior traces
     double* sA = sP + QUAD_TP * EF;         // [2][4][EN]; block 0 later holds V[4][EN]
-    double* sGeo = sA + 8 * EN;             // [EB][17]
+    double* sS = sA + 8 * EN;               // CNS: [6][EN] sigma at the nodes, [6][EF] exterior sigma traces
+    double* sSP = sS + 6 * EN;
+    double* sGeo = CNS ? sSP + 6 * EF : sS; // [EB][17]
     double* s_lm = sGeo + EB * QUAD_GEO;
     double* s_lp = s_lm + n;
     double* s_w = s_lp + n;
@@ -173,11 +243,21 @@ __global__ void __launch_bounds__(QuadDims<n>::THREADS, 3) k_quad_stage_line(con
         const int ip = p.mapP[gf0 + it];
 #pragma unroll
         for (int q = 0; q < QUAD_TP; ++q) {
-            cp_async8(sWF + q * EF + it, p.Tcur + q * p.t_stride + gf0 + it);
+            if (!CNS) cp_async8(sWF + q * EF + it, p.Tcur + q * p.t_stride + gf0 + it);
             cp_async8(sP + q * EF + it, p.Tcur + q * p.t_stride + ip);
+        }
+        if (CNS) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) cp_async8(sSP + q * EF + it, p.sig_tr + q * p.t_stride + ip);
         }
     }
     for (int it = tid; it < nb * QUAD_GEO; it += NT) cp_async8(sGeo + it, p.geo + e0 * QUAD_GEO + it);
+    if (CNS) {
+        for (int it = tid; it < nb * Nq; it += NT) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) cp_async8(sS + q * EN + it, p.sig + q * p.q_stride + gq0 + it);
+        }
+    }
     cp_async_commit();
     if (tid < n) { s_lm[tid] = p.lm[tid]; s_lp[tid] = p.lp[tid]; s_w[tid] = p.w[tid]; }
     bool bad = false;
@@ -199,6 +279,7 @@ __global__ void __launch_bounds__(QuadDims<n>::THREADS, 3) k_quad_stage_line(con
     cp_async_wait_all();
     __syncthreads();
     // ---- C: one line per thread ------------------------------------------------------------------------------
+    double tvisc = 0.0;
     if (tid < nb * NL) {
         const int eb = tid / NL, ll = tid - eb * NL;
         int d, base, stride, f0, f1;
@@ -241,7 +322,18 @@ __global__ void __launch_bounds__(QuadDims<n>::THREADS, 3) k_quad_stage_line(con
             }
         }
         // volume-face pairs (lane = side)
-        Node2 fn[2] = {ld_node2(sWF, EF, fidx[0]), ld_node2(sWF, EF, fidx[1])};
+        Node2 fn[2];
+        double lamOwn[2];
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            if (CNS) {
+                fn[side] = ld_node2_g(p.Tcur, p.t_stride, gf0 + fidx[side]);
+                lamOwn[side] = p.Tcur[6 * p.t_stride + gf0 + fidx[side]];
+            } else {
+                fn[side] = ld_node2(sWF, EF, fidx[side]);
+                lamOwn[side] = sWF[6 * EF + fidx[side]];
+            }
+        }
         double h[2][4];
 #pragma unroll
         for (int f = 0; f < 4; ++f) h[0][f] = h[1][f] = 0.0;
@@ -272,20 +364,37 @@ __global__ void __launch_bounds__(QuadDims<n>::THREADS, 3) k_quad_stage_line(con
                 const int face = (side ? f1 : f0) / n;
                 const double* gf = Gm + 5 + face * 3;
                 nJ[0][side] = gf[0]; nJ[1][side] = gf[1]; sJ[side] = gf[2];
-                lamM[side] = sWF[6 * EF + fidx[side]];
+                lamM[side] = lamOwn[side];
                 lamP[side] = sP[6 * EF + fidx[side]];
             }
-            pair_flux2_v<2>(M, P, nJ, c_igm, FS);
-            if (p.lf_scale != 0.0) {
-                const VD<2> LFc = p.lf_scale * vmax(lamM, lamP) * sJ;
+            VD<2> jump[4];
+            const bool lf = p.lf_scale != 0.0;
+            if (lf) {   // U+ - U of the GATHERED exterior state (a boundary point maps to itself: no penalty there, :500-507)
                 const VD<2> ibM = vrcp(M.beta), ibP = vrcp(P.beta);
                 const VD<2> qM = vfma(M.u[0], M.u[0], M.u[1] * M.u[1]), qP = vfma(P.u[0], P.u[0], P.u[1] * P.u[1]);
                 const VD<2> tM = 2.0 * M.rho, tP = 2.0 * P.rho;
-                VD<2> jump[4];
                 jump[0] = P.rho - M.rho;
                 jump[1] = vfma(tP, P.u[0], -(tM * M.u[0]));
                 jump[2] = vfma(tP, P.u[1], -(tM * M.u[1]));
                 jump[3] = vfma(P.rho, vfma(ibP, c_igm, 2.0 * qP), -(M.rho * vfma(ibM, c_igm, 2.0 * qM)));
+            }
+            if (CNS) {   // impose_BCs_inviscid! (:157-176): rho+ = rho, beta+ = beta, u+ = u - 2 (u.n) n at wall / lid points
+#pragma unroll
+                for (int side = 0; side < 2; ++side) {
+                    const int kd = p.bc[gf0 + fidx[side]] & 7;
+                    if (kd == 1 || kd == 2) {
+                        const double isJ = fast_rcp(sJ[side]);
+                        const double nx = nJ[0][side] * isJ, ny = nJ[1][side] * isJ;
+                        const double Un = fn[side].u[0] * nx + fn[side].u[1] * ny;
+                        P.rho[side] = fn[side].rho; P.beta[side] = fn[side].beta; P.lr[side] = fn[side].lr; P.lb[side] = fn[side].lb;
+                        P.u[0][side] = fn[side].u[0] - 2 * Un * nx;
+                        P.u[1][side] = fn[side].u[1] - 2 * Un * ny;
+                    }
+                }
+            }
+            pair_flux2_v<2>(M, P, nJ, c_igm, FS);
+            if (lf) {
+                const VD<2> LFc = p.lf_scale * vmax(lamM, lamP) * sJ;
 #pragma unroll
                 for (int f = 0; f < 4; ++f) FS[f] = vfma(-LFc, jump[f], FS[f]);
             }
@@ -301,6 +410,77 @@ __global__ void __launch_bounds__(QuadDims<n>::THREADS, 3) k_quad_stage_line(con
         for (int a = 0; a < n; ++a)
 #pragma unroll
             for (int f = 0; f < 4; ++f) A[f * EN + base + a * stride] = acc[a][f];
+        if constexpr (CNS) {
+            // viscous numerator of this line: D (g_x sigma_x + g_y sigma_y) + lift(.5 [[sigma]].nJ + J tau [[v]])
+            const double Je = Gm[4];
+            double ft[2][3];
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const double* l = side ? p.lp : p.lm;
+                double sxf[3] = {0, 0, 0}, syf[3] = {0, 0, 0}, sxP[3], syP[3];
+#pragma unroll
+                for (int a = 0; a < n; ++a)
+#pragma unroll
+                    for (int f = 0; f < 3; ++f) {
+                        sxf[f] = fma(l[a], sS[f * EN + base + a * stride], sxf[f]);
+                        syf[f] = fma(l[a], sS[(3 + f) * EN + base + a * stride], syf[f]);
+                    }
+#pragma unroll
+                for (int f = 0; f < 3; ++f) {
+                    sxP[f] = sSP[f * EF + fidx[side]];
+                    syP[f] = sSP[(3 + f) * EF + fidx[side]];
+                }
+                const double* gf = Gm + 5 + ((side ? f1 : f0) / n) * 3;
+                const double isJ = fast_rcp(gf[2]);
+                const double nx = gf[0] * isJ, ny = gf[1] * isJ;
+                const long long self = gf0 + fidx[side];
+                const int code = p.bc[self];
+                const int kd = code & 7;
+                const double vlid = kd == 2 ? p.vlid[self] : 0.0;
+                if (kd == 1 || kd == 2) bc_stress_q(p.bctype, kd, vlid, nx, ny, sxf, syf, sxP, syP);
+#pragma unroll
+                for (int f = 0; f < 3; ++f) ft[side][f] = .5 * ((sxP[f] - sxf[f]) * gf[0] + (syP[f] - syf[f]) * gf[1]);
+                if (p.viscous_dissp) {   // penalisation tau [[v]] (:817-840)
+                    double VM[4], VPv[4];
+                    v234_from_prim(fn[side].u[0], fn[side].u[1], fn[side].beta, p.gamma, VM);
+                    v234_from_prim(sP[EF + fidx[side]], sP[2 * EF + fidx[side]], sP[3 * EF + fidx[side]], p.gamma, VPv);
+                    if (kd == 1 || kd == 2) bc_entropy_vars_q(p.bctype, kd, vlid, p.inv_theta2, nx, ny, VM, VPv);
+                    const double iv4 = fast_rcp(VM[3]);
+                    const double tau = -iv4 / p.Re;
+                    const double d1 = VPv[1] - VM[1], d2 = VPv[2] - VM[2], d3 = VPv[3] - VM[3];
+                    double p3 = tau * d3;
+                    if (code & 8) {
+                        const double a1 = .5 * (VPv[1] + VM[1]), a2 = .5 * (VPv[2] + VM[2]);
+                        p3 = p.bctype == 1 ? -tau * (a1 * d1 + a2 * d2) * iv4 : -tau * (a1 * d1 + a2 * d2 + d3 * d3 * .5) * iv4;
+                    }
+                    ft[side][0] = fma(Je, tau * d1, ft[side][0]);
+                    ft[side][1] = fma(Je, tau * d2, ft[side][1]);
+                    ft[side][2] = fma(Je, p3, ft[side][2]);
+                }
+            }
+            const int m = ll - d * n;
+#pragma unroll
+            for (int f = 0; f < 3; ++f) {
+                double accv[n];
+#pragma unroll
+                for (int a = 0; a < n; ++a) accv[a] = fma(p.lmw[a], ft[0][f], p.lpw[a] * ft[1][f]);
+#pragma unroll
+                for (int b = 0; b < n; ++b) {
+                    const double S = fma(g1, sS[(3 + f) * EN + base + b * stride], g0 * sS[f * EN + base + b * stride]);
+#pragma unroll
+                    for (int a = 0; a < n; ++a) accv[a] = fma(p.D[a * n + b], S, accv[a]);
+                }
+#pragma unroll
+                for (int a = 0; a < n; ++a) {
+                    if (p.want_rhstest) {   // sum wJq VUq . visc_rhs (:966): wJ (accv / J) = w accv; v_{2+f} from the node primitives
+                        const double c = 2.0 * (p.gamma - 1.0) * sWV[3 * EN + base + a * stride];
+                        const double v = f == 2 ? -c : 2.0 * c * sWV[(1 + f) * EN + base + a * stride];
+                        tvisc = fma(p.w[a] * p.w[m] * v, accv[a], tvisc);
+                    }
+                    A[(1 + f) * EN + base + a * stride] -= accv[a];   // this thread's own slots
+                }
+            }
+        }
     }
     __syncthreads();
     // ---- E: update ------------------------------------------------------------------------------------------
@@ -388,13 +568,21 @@ __global__ void __launch_bounds__(QuadDims<n>::THREADS, 3) k_quad_stage_line(con
         }
     }
     if (p.want_rhstest) {
-        for (int o = 16; o > 0; o >>= 1) tsum += __shfl_down_sync(0xffffffffu, tsum, o);
-        if ((tid & 31) == 0) red[tid >> 5] = tsum;
+        for (int o = 16; o > 0; o >>= 1) {
+            tsum += __shfl_down_sync(0xffffffffu, tsum, o);
+            if (CNS) tvisc += __shfl_down_sync(0xffffffffu, tvisc, o);
+        }
+        if ((tid & 31) == 0) { red[0][tid >> 5] = tsum; red[1][tid >> 5] = tvisc; }
         __syncthreads();
         if (tid == 0) {
-            double t = 0.0;
-            for (int wv = 0; wv < NT / 32; ++wv) t += red[wv];
-            p.partial[e0] = t;   // one slot per element, as on the hex path (esdg_ctx.cu:total_partials)
+            double t = 0.0, tv = 0.0;
+            for (int wv = 0; wv < NT / 32; ++wv) { t += red[0][wv]; tv += red[1][wv]; }
+            if (CNS) {
+                p.partial[blockIdx.x] = t;
+                p.partial_vrhs[blockIdx.x] = tv;
+            } else {
+                p.partial[e0] = t;   // one slot per element, as on the hex path (esdg_ctx.cu:total_partials)
+            }
         }
     }
     if (bad) atomicOr(p.bad, 1);

