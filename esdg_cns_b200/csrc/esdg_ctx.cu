@@ -1701,7 +1701,7 @@ static int comm_lsrk45(esdg_ctx* ctx, double dt, int nsteps, double* rhstest_las
         if ((rc = comm_exchange_finish(ctx))) return rc;
         c->fresh = false;
     }
-    const bool overlap = ctx->hex != nullptr && !getenv("ESDG_COMM_NO_OVERLAP");
+    const bool overlap = (ctx->hex != nullptr || (ctx->quad != nullptr && !ctx->quad->cns)) && !getenv("ESDG_COMM_NO_OVERLAP");
     for (int s = 0; s < nsteps; ++s)
         for (int k = 0; k < 5; ++k) {
             const int want = (rhstest_last != nullptr) && (s == nsteps - 1) && (k == 4);

@@ -259,6 +259,10 @@ __global__ void __launch_bounds__(QuadDims<n>::THREADS, 3) k_quad_stage_line(con
         }
     }
     cp_async_commit();
+    if (p.mode == 1) {   // the LSRK register is needed last: pull it into L2 meanwhile
+        constexpr int LPF = (EN * 8 + 127) / 128;
+        for (int it = tid; it < 4 * LPF; it += NT) prefetch_l2(p.res + (it / LPF) * p.q_stride + gq0 + (it % LPF) * 16);
+    }
     if (tid < n) { s_lm[tid] = p.lm[tid]; s_lp[tid] = p.lp[tid]; s_w[tid] = p.w[tid]; }
     bool bad = false;
     const double c_igm = 1.0 / (2.0 * (p.gamma - 1.0));
@@ -482,10 +486,25 @@ __global__ void __launch_bounds__(QuadDims<n>::THREADS, 3) k_quad_stage_line(con
             }
         }
     }
+    // E operands: requested before the barrier, all in flight together (the LSRK register is touched nowhere else)
+    constexpr int EIT = (EN + NT - 1) / NT;
+    double Ue[EIT][4], Re[EIT][4];
+#pragma unroll
+    for (int k = 0; k < EIT; ++k) {
+        const int it = tid + k * NT;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            Ue[k][f] = it < nb * Nq ? p.Q[f * p.q_stride + gq0 + it] : 1.0;
+            Re[k][f] = (it < nb * Nq && p.mode == 1) ? p.res[f * p.q_stride + gq0 + it] : 0.0;
+        }
+    }
     __syncthreads();
     // ---- E: update ------------------------------------------------------------------------------------------
     double tsum = 0.0;
-    for (int it = tid; it < nb * Nq; it += NT) {
+#pragma unroll
+    for (int k = 0; k < EIT; ++k) {
+        const int it = tid + k * NT;
+        if (it >= nb * Nq) break;
         const long long g = gq0 + it;
         const int eb = it / Nq, i = it - eb * Nq;
         const double J = sGeo[eb * QUAD_GEO + 4];
@@ -494,7 +513,7 @@ __global__ void __launch_bounds__(QuadDims<n>::THREADS, 3) k_quad_stage_line(con
         const VD<1> mJ = -vrcp(Jv);
 #pragma unroll
         for (int f = 0; f < 4; ++f) {
-            U[f][0] = p.Q[f * p.q_stride + g];
+            U[f][0] = Ue[k][f];
             rr[f][0] = (sA[f * EN + it] + sA[(4 + f) * EN + it]) * mJ[0];
         }
         if (p.want_rhstest) {
@@ -514,7 +533,7 @@ __global__ void __launch_bounds__(QuadDims<n>::THREADS, 3) k_quad_stage_line(con
             VD<1> Un[4];
 #pragma unroll
             for (int f = 0; f < 4; ++f) {
-                const double rs = fma(p.rk_a, p.res[f * p.q_stride + g], p.dt * rr[f][0]);
+                const double rs = fma(p.rk_a, Re[k][f], p.dt * rr[f][0]);
                 Un[f][0] = fma(p.rk_b, rs, U[f][0]);
                 p.res[f * p.q_stride + g] = rs;
                 p.Qout[f * p.q_stride + g] = Un[f][0];

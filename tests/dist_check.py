@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--generic", type=int, default=0)
     ap.add_argument("--cns", type=int, default=0, help="1: compressible Navier-Stokes cavity on y-slabs of a quad mesh")
+    ap.add_argument("--quad", type=int, default=0, help="1: Euler on y-slabs of a periodic quad mesh (tensor-product quad kernels), K = Kx Ky 0")
     ap.add_argument("--ccomm", type=int, default=0, help="1: the context's own NCCL communicator (esdg_comm_init) instead of the host-driven exchange")
     a = ap.parse_args()
     if a.generic:
@@ -47,11 +48,17 @@ def main():
         dist.destroy_process_group()
         sys.exit(0 if int(flag[0]) == 1 else 1)
     N, Kxyz = a.N, tuple(a.K)
-    dom = ((-np.pi, np.pi),) * 3
-    prd, pops = SD.reference_hex(N)
-    md = SD.uniform_hex_mesh_md(prd, Kxyz, domain=dom, zslab=(rank, world))
-    x, y, z = SD.hex_node_coords(prd, md)
-    Q0 = SD.primitive_to_conservative(*(lambda r, u, v, w, p: (r, (u, v, w), p))(*SD.taylor_green(x, y, z)))
+    if a.quad:
+        dom = ((0.0, 20.0), (-5.0, 5.0))
+        prd, pops = SD.reference_quad(N)
+        md = SD.uniform_quad_mesh_md(prd, Kxyz[0], Kxyz[1], domain=dom, yslab=(rank, world))
+        Q0 = SD.primitive_to_conservative(*(lambda r, u, v, p: (r, (u, v), p))(*SD.vortex(md.xq, md.yq)))
+    else:
+        dom = ((-np.pi, np.pi),) * 3
+        prd, pops = SD.reference_hex(N)
+        md = SD.uniform_hex_mesh_md(prd, Kxyz, domain=dom, zslab=(rank, world))
+        x, y, z = SD.hex_node_coords(prd, md)
+        Q0 = SD.primitive_to_conservative(*(lambda r, u, v, w, p: (r, (u, v, w), p))(*SD.taylor_green(x, y, z)))
     dt = 2e-3
     s = api.Solver(md, pops, device=lr, n_halo=md.n_halo, stream=torch.cuda.current_stream().cuda_stream)
     if a.ccomm:
@@ -77,16 +84,20 @@ def main():
     ok = True
     if rank == 0:
         full = np.concatenate([p.cpu().numpy() for p in parts], axis=2)
-        mdf = SD.uniform_hex_mesh_md(prd, Kxyz, domain=dom)
-        xf, yf, zf = SD.hex_node_coords(prd, mdf)
-        Qf = SD.primitive_to_conservative(*(lambda r, u, v, w, p: (r, (u, v, w), p))(*SD.taylor_green(xf, yf, zf)))
+        if a.quad:
+            mdf = SD.uniform_quad_mesh_md(prd, Kxyz[0], Kxyz[1], domain=dom)
+            Qf = SD.primitive_to_conservative(*(lambda r, u, v, p: (r, (u, v), p))(*SD.vortex(mdf.xq, mdf.yq)))
+        else:
+            mdf = SD.uniform_hex_mesh_md(prd, Kxyz, domain=dom)
+            xf, yf, zf = SD.hex_node_coords(prd, mdf)
+            Qf = SD.primitive_to_conservative(*(lambda r, u, v, w, p: (r, (u, v, w), p))(*SD.taylor_green(xf, yf, zf)))
         s1 = api.Solver(mdf, pops, device=lr)
         s1.upload(Qf)
         rt1 = s1.lsrk45(dt, a.steps, want_rhstest=True)
         ref = np.stack(s1.download())
         err = np.abs(full - ref).max() / np.abs(ref).max()
         rterr = abs(float(rt_local[0]) - rt1)
-        print(f"dist_check world={world} N={N} K={Kxyz} overlap={a.overlap} generic={a.generic}: "
+        print(f"dist_check world={world} N={N} K={Kxyz} quad={a.quad} path={s.kernel_path()} overlap={a.overlap} generic={a.generic}: "
               f"state max rel diff {err:.3e}; rhstest {float(rt_local[0]):.12e} vs single-GPU {rt1:.12e}")
         ok = err < 1e-13 and rterr < 1e-10 * max(1.0, abs(rt1))
     flag = torch.tensor([1 if ok else 0], device=dev)

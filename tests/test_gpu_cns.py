@@ -339,3 +339,46 @@ def test_convergence_sweep_harness_boundary_error_decreases():
         assert hist["t"][-1] >= .2 and hist["rhstest"][-1] <= 1e-10
     assert errs[(3, 8)] < errs[(2, 8)] < errs[(1, 8)]
     assert errs[(2, 16)] < errs[(2, 8)]
+
+
+@pytest.mark.parametrize("bctype", [1, 3])
+def test_cns_quad_nodal_line_kernels_match_modal_gemm_kernels(bctype, monkeypatch):
+    """Quads run in the Gauss-nodal basis on the tensor-product line kernels (kernels_cnsq.cuh: 2 launches per stage, no GEMM);
+    ESDG_CNS_MODAL=1 keeps the table-driven modal kernels (kernels_cns.cuh: 3 launches, DMMA batch GEMMs).  Same rhs, same
+    state after LSRK45 steps, same DOPRI45 decisions."""
+    from oracle import cns
+    from esdg_cns_b200 import api
+    rd, md, ops, bc, _ = cns.setup_cavity("quad", 3, 6)
+    Q = _state(md)
+    par = cns.cavity_params(Re=200.0, bctype=bctype)
+    res = []
+    for modal in (False, True):
+        if modal:
+            monkeypatch.setenv("ESDG_CNS_MODAL", "1")
+        s = api.Solver(md, ops, cns=_cns_settings(par, bc, md))
+        assert s.kernel_path() == ("cns" if modal else "cns_quad_line")
+        r, rt, rtv = s.rhs(Q, True)
+        s.upload(Q)
+        n0 = s.kernel_launches()
+        s.lsrk45(1e-3, 3)
+        nl = s.kernel_launches() - n0
+        Q3 = s.download()
+        s.upload(Q)
+        h = s.dopri45(1e9, 1e-3, max_attempts=4)
+        hist = list(zip(h["accepted"], h["err"][1:], h["dt"][1:]))
+        res.append((r, rt, rtv, Q3, hist, s.download(), nl))
+        s.close()
+    a, b = res
+    scale = max(np.abs(x).max() for x in b[0])
+    print(f"bctype {bctype}: rhs diff {max(np.abs(x - y).max() for x, y in zip(a[0], b[0])) / scale:.2e}; launches per 3 steps {a[6]} vs {b[6]}")
+    # both sit inside the rounding cloud of the reference formulas around the oracle (helpers.parity_tol)
+    ref = cns.rhsRK(Q, md, ops, bc, par)[0]
+    tol = parity_tol(lambda: cns.rhsRK(Q, md, ops, bc, par)[0], ref)
+    assert relerr(a[0], ref) < tol and relerr(b[0], ref) < tol
+    assert max(np.abs(x - y).max() for x, y in zip(a[0], b[0])) / scale < 2 * tol
+    assert abs(a[1] - b[1]) < 1e-10 and abs(a[2] - b[2]) < 1e-10
+    assert max(np.abs(x - y).max() for x, y in zip(a[3], b[3])) < 1e-11
+    assert [h[0] for h in a[4]] == [h[0] for h in b[4]]
+    assert all(abs(x[1] - y[1]) < 1e-6 * max(1.0, abs(y[1])) and abs(x[2] - y[2]) < 1e-6 * y[2] for x, y in zip(a[4], b[4]))
+    assert max(np.abs(x - y).max() for x, y in zip(a[5], b[5])) < 1e-8      # step sizes agree to ~1e-6 (error estimate partly round-off)
+    assert a[6] < b[6]

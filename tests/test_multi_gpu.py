@@ -57,3 +57,19 @@ def test_two_gpu_cns_slabs_match_single_gpu():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ccomm,overlap", [(1, 1), (1, 0), (0, 1)])
+def test_two_gpu_quad_slabs_match_single_gpu(ccomm, overlap):
+    """Euler on y-slabs of a quad mesh (tensor-product quad kernels, 7-plane halo): in-library NCCL exchange overlapped with
+    the interior rows, without overlap, and host-driven -- bit-identical to the single-GPU run."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(29650 + 2 * ccomm + overlap),
+           os.path.join(ROOT, "tests", "dist_check.py"), "--quad", "1", "--ccomm", str(ccomm), "--overlap", str(overlap),
+           "--N", "3", "--K", "6", "8", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0
