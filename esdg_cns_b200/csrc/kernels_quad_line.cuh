@@ -52,6 +52,12 @@ struct QuadParams {
     double* partial_vrhs;    // per CTA: sum wJq VUq . visc_rhs             (:966)
 };
 
+#ifndef ESDG_QUAD_OWN_SMEM
+#define ESDG_QUAD_OWN_SMEM 1   // Euler: own traces staged in shared memory by cp.async (1.28 ms per stage on quads N=3 1024^2) instead of being
+#endif                         // read by the line thread (1.37 ms); profiles/r2_quad_variants.txt
+
+
+
 template <int n>
 struct QuadDims {
     static constexpr int Nq = n * n, Nfq = 4 * n, NL = 2 * n;
@@ -226,6 +232,7 @@ __global__ void __launch_bounds__(QuadDims<n>::THREADS, 3) k_quad_stage_line(con
     __shared__ double red[2][NT / 32];
     double* sWV = sm;                       // [6][EN]
     double* sWF = sWV + 6 * EN;             // [7][EF] own traces (Euler only)
+    constexpr bool OWN_SMEM = !CNS && ESDG_QUAD_OWN_SMEM;   // own traces staged in shared memory or read by the line thread itself
     double* sP = CNS ? sWF : sWF + QUAD_TP * EF;   // [7][EF] exterior traces
     double* sA = sP + QUAD_TP * EF;         // [2][4][EN]; block 0 later holds V[4][EN]
     double* sS = sA + 8 * EN;               // CNS: [6][EN] sigma at the nodes, [6][EF] exterior sigma traces
@@ -243,7 +250,7 @@ __global__ void __launch_bounds__(QuadDims<n>::THREADS, 3) k_quad_stage_line(con
         const int ip = p.mapP[gf0 + it];
 #pragma unroll
         for (int q = 0; q < QUAD_TP; ++q) {
-            if (!CNS) cp_async8(sWF + q * EF + it, p.Tcur + q * p.t_stride + gf0 + it);
+            if (OWN_SMEM) cp_async8(sWF + q * EF + it, p.Tcur + q * p.t_stride + gf0 + it);
             cp_async8(sP + q * EF + it, p.Tcur + q * p.t_stride + ip);
         }
         if (CNS) {
@@ -330,7 +337,7 @@ __global__ void __launch_bounds__(QuadDims<n>::THREADS, 3) k_quad_stage_line(con
         double lamOwn[2];
 #pragma unroll
         for (int side = 0; side < 2; ++side) {
-            if (CNS) {
+            if (!OWN_SMEM) {
                 fn[side] = ld_node2_g(p.Tcur, p.t_stride, gf0 + fidx[side]);
                 lamOwn[side] = p.Tcur[6 * p.t_stride + gf0 + fidx[side]];
             } else {
