@@ -29,7 +29,7 @@ struct CnsqDims {
 };
 
 template <int n>
-__global__ void __launch_bounds__(CnsqDims<n>::THREADS, 4) k_cnsq_sigma(const __grid_constant__ QuadParams p) {
+__global__ void __launch_bounds__(CnsqDims<n>::THREADS, 512 / CnsqDims<n>::THREADS) k_cnsq_sigma(const __grid_constant__ QuadParams p) {
     using D = QuadDims<n>;
     constexpr int Nq = D::Nq, Nfq = D::Nfq, NL = D::NL, EB = D::EB, NT = D::THREADS, EN = D::EN, EF = D::EF;
     extern __shared__ __align__(16) double sm[];

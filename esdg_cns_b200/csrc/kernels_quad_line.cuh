@@ -52,6 +52,9 @@ struct QuadParams {
     double* partial_vrhs;    // per CTA: sum wJq VUq . visc_rhs             (:966)
 };
 
+#ifndef ESDG_QUAD_THREADS
+#define ESDG_QUAD_THREADS 128
+#endif
 #ifndef ESDG_QUAD_OWN_SMEM
 #define ESDG_QUAD_OWN_SMEM 1   // Euler: own traces staged in shared memory by cp.async (1.28 ms per stage on quads N=3 1024^2) instead of being
 #endif                         // read by the line thread (1.37 ms); profiles/r2_quad_variants.txt
@@ -61,8 +64,9 @@ struct QuadParams {
 template <int n>
 struct QuadDims {
     static constexpr int Nq = n * n, Nfq = 4 * n, NL = 2 * n;
-    static constexpr int THREADS = 128;
+    static constexpr int THREADS = ESDG_QUAD_THREADS;
     static constexpr int EB = THREADS / NL;                   // n = 4: 16 elements, 60 KB of shared memory, 3 CTAs per SM
+    static constexpr int MIN_CTAS = 384 / THREADS;            // 12 warps per SM at 168 registers
     static constexpr int EN = EB * Nq, EF = EB * Nfq;
     // WV[6][EN] WF[7][EF] P[7][EF] A2[2][4][EN] (V[4][EN] aliases A2 block 0) geo[EB][17] lm lp w
     static constexpr int SMEM_DOUBLES = 6 * EN + 2 * QUAD_TP * EF + 8 * EN + EB * QUAD_GEO + 3 * n;
@@ -224,7 +228,7 @@ __device__ __forceinline__ void quad_line(int ll, int& d, int& base, int& stride
 // the BR1 divergence of sigma (k_cnsq_sigma, kernels_cnsq.cuh), its surface term with the stress BCs and the penalisation
 // (:590-611, :817-846); final rhs = (viscous numerator - inviscid numerator) / J.
 template <int n, bool CNS = false>
-__global__ void __launch_bounds__(QuadDims<n>::THREADS, 3) k_quad_stage_line(const __grid_constant__ QuadParams p) {
+__global__ void __launch_bounds__(QuadDims<n>::THREADS, QuadDims<n>::MIN_CTAS) k_quad_stage_line(const __grid_constant__ QuadParams p) {
     using D = QuadDims<n>;
     constexpr int Nq = D::Nq, Nfq = D::Nfq, NL = D::NL, EB = D::EB, NT = D::THREADS, EN = D::EN, EF = D::EF;
     constexpr PairTab<n> PT{};

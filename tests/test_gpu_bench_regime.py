@@ -17,7 +17,7 @@ alone (the two oracles do), so the bound there is "no further from the 80-bit va
 import numpy as np
 import pytest
 
-from helpers import relerr as _relerr, NORTH_STAR_TOL
+from helpers import relerr as _relerr, NORTH_STAR_TOL, noise_floor
 
 pytestmark = pytest.mark.gpu
 
@@ -207,3 +207,74 @@ def test_pair_flux_across_the_logmean_switch():
         # away from the last few ulp around the switch the kernel takes the reference's branch and agrees to round-off
         assert err[~near].max() < 2e-13, (case, err[~near].max(), np.argmax(np.where(near, 0, err)))
     print("pair flux across the logmean switch: max rel err (off-switch), # > 1e-12 within 8 ulp of the switch, # such points:", worst)
+
+
+# ---- the 2-D configs at THEIR timing-scale node spacing (bench.py other_configs) -----------------------------------
+def test_quad_at_bench_spacing():
+    """bench.py times config 1 on 1024^2 quads over [0,20]x[-5,5] (elements 0.0195 x 0.0098): a 24x24 sub-box of that
+    mesh around the vortex core, same element size, through the tensor-product quad kernels and -- same operators -- the
+    table-driven ones.  Here nearly every pair takes the Taylor branch of logmean."""
+    from oracle import solvers as SV, setupdg as S, mesh as M, physics as P
+    from esdg_cns_b200 import api
+    N, Kb = 3, 24
+    hx, hy = 20.0 / 1024, 10.0 / 1024
+    VX, VY, EToV = M.uniform_quad_mesh(Kb, Kb)
+    VX = 5.0 + .5 * Kb * hx * VX
+    VY = .3 + .5 * Kb * hy * VY
+    rd = S.init_reference_quad(N)
+    md = S.init_mesh((VX, VY), EToV, rd)
+    S.make_periodic(md, rd, (Kb * hx, Kb * hy))
+    ops = SV.build_sbp_ops(rd)
+    SV.interp_geofacs(md, rd, ops)
+    # differentiated node coordinates of 0.02-wide elements away from the origin carry ~1e-10 relative noise from node
+    # to node (see _exactly_affine): every consumer gets the exactly-affine arrays (the 2-D scripts read row [1,e] anyway)
+    for nm in ("rxJ", "sxJ", "ryJ", "syJ", "J"):
+        a = getattr(md, nm)
+        a[:] = 0.0 if nm in ("sxJ", "ryJ") else a[:1]
+    md.wJq = np.diag(rd.wq) @ (rd.Vq @ md.J if md.J.shape[0] != rd.wq.size else md.J)
+    nfp = md.nxJ.shape[0] // 4
+    for nm in ("nxJ", "nyJ", "sJ"):
+        a = getattr(md, nm)
+        for f in range(4):
+            a[f * nfp:(f + 1) * nfp] = a[f * nfp:f * nfp + 1]
+        if nm != "sJ":
+            a[np.abs(a) < 1e-8 * md.sJ] = 0.0
+    rho, u, v, p = P.vortex(md.xq, md.yq, 0)
+    Q = list(P.primitive_to_conservative(rho, (u, v), p))
+    ref, rt_ref = SV.rhs_collocated(Q, md, ops, rd, .5, True)
+    tol = 2 * max(NORTH_STAR_TOL, 4 * noise_floor(lambda: SV.rhs_collocated(Q, md, ops, rd, .5, False)[0], ref))
+    s = api.Solver(md, ops)
+    assert s.kernel_path() == "quad_line"
+    out, rt = s.rhs(Q, True)
+    err = _relerr(out, ref)
+    print(f"quad sub-box of the 1024^2 bench mesh: relerr {err:.2e} (bound {tol:.2e}); rhstest {rt:.3e} / {rt_ref:.3e}")
+    assert err < tol
+    assert abs(rt - rt_ref) < 1e-11 * max(1.0, abs(rt_ref))
+
+
+def test_cns_quad_at_bench_spacing():
+    """bench.py times config 3 on 512^2 quads over [-1,1]^2 (h = 0.0039).  The oracle cannot hold that mesh, so the same
+    neighbour-to-neighbour variation is put on 32^2 elements: a smooth O(1) cavity-like field scaled by 32/512."""
+    from oracle import cns, physics as P
+    from esdg_cns_b200 import api
+    from types import SimpleNamespace
+    rd, md, ops, bc, _ = cns.setup_cavity("quad", 3, 32)
+    par = cns.cavity_params(Re=1000.0, bctype=1)
+    x, y = md.x, md.y
+    a = 32.0 / 512
+    rho = 1 + a * .2 * np.sin(np.pi * x) * np.cos(np.pi * y)
+    u = a * (1 - x * x) * (1 + y) * .5
+    v = a * .3 * np.sin(np.pi * x) * (1 - y * y)
+    p = (1 / (.3 ** 2 * 1.4)) * (1 + a * .1 * np.cos(np.pi * (x + y)))
+    Q = list(P.primitive_to_conservative(rho, (u, v), p))
+    ref, rt_ref, rtv_ref = cns.rhsRK(Q, md, ops, bc, par)
+    tol = 2 * max(NORTH_STAR_TOL, 4 * noise_floor(lambda: cns.rhsRK(Q, md, ops, bc, par)[0], ref))
+    st = SimpleNamespace(Re=par.Re, mu=par.mu, lam=par.lam, Pr=par.Pr, bctype=par.bctype, inviscid_dissp=True, viscous_dissp=True,
+                         wall=bc.wall, lid=bc.lid, vlid=bc.vlid, mapB=md.mapB)
+    s = api.Solver(md, ops, cns=st)
+    assert s.kernel_path() == "cns_quad_line"
+    out, rt, rtv = s.rhs(Q, True)
+    err = _relerr(out, ref)
+    print(f"CNS quads at bench-like spacing: relerr {err:.2e} (bound {tol:.2e}); rhstest {rt:.3e} / {rt_ref:.3e}, visc {rtv:.3e} / {rtv_ref:.3e}")
+    assert err < tol
+    assert abs(rt - rt_ref) < 1e-10 * max(1.0, abs(rt_ref)) and abs(rtv - rtv_ref) < 1e-10 * max(1.0, abs(rtv_ref))
