@@ -936,7 +936,7 @@ int esdg_finalize(esdg_ctx* ctx) {
         for (int64_t e = 0; e < d.K && diag && !ctx->structured; ++e)
             for (int k = 0; k < 9; ++k)
                 if (k % 4 != 0 && geo[(size_t)e * ctx->geo_stride + k] != 0.0) { diag = false; break; }
-        ctx->hex->diag = diag && !getenv("ESDG_NO_DIAG");
+        ctx->hex->diag = diag && d.affine && !getenv("ESDG_NO_DIAG");
     }
     ctx->finalized = true;
     return ESDG_OK;
@@ -1240,7 +1240,7 @@ int esdg_trace_planes(esdg_ctx* ctx) { return ctx ? cur_planes(ctx) : 0; }
 const char* esdg_kernel_path(const esdg_ctx* ctx) {
     if (!ctx || !ctx->finalized) return "";
     if (ctx->cns.on) return ctx->quad ? "cns_quad_line" : "cns";
-    if (ctx->hex) return ctx->hex->diag ? "hex_line_diag" : "hex_line";
+    if (ctx->hex) return ctx->hex->curved ? "hex_line_curved" : (ctx->hex->diag ? "hex_line_diag" : "hex_line");
     if (ctx->quad) return "quad_line";
     return "generic";
 }

@@ -55,6 +55,10 @@ struct HexParams {
     const int* mapP;
     const double* geo;
     int geo_stride;
+    // curved elements (desc.affine = 0; dg3D_euler_hex.jl:69-101): rxJ.. at every hybridized point [e][9][Nh], J at every
+    // volume node [e][Nq], (nxJ, nyJ, nzJ, sJ) at every face point [e][4][Nfq]; null on affine meshes
+    const double *geoG, *geoJ, *geoN;
+    const double* geoL;      // the same factors LINE-major: [e][(n+2)*3][NL] (node a of the line, rotated component c) -> coalesced over the lines
     double gamma, lf_scale, lg1, l2g1;   // lg1 = log(gamma-1), l2g1 = log(2(gamma-1))
     double rk_a, rk_b, dt;
     int mode;                // 0: write rhs ; 1: fused LSRK stage + traces of the new state
@@ -177,6 +181,20 @@ __device__ __forceinline__ Node ld_node_rot(const double* W, int S, int idx, int
     a.beta = W[4 * S + idx];
     a.lr = W[5 * S + idx];
     a.lb = W[6 * S + idx];
+    return a;
+}
+
+// the same, re-read at every use (volatile: the compiler must not keep the node in registers between pairs)
+__device__ __forceinline__ Node ld_node_rot_again(const double* W, int S, int idx, int pl0, int pl1, int pl2) {
+    const volatile double* V = W;
+    Node a;
+    a.rho = V[idx];
+    a.u[0] = V[pl0 * S + idx];
+    a.u[1] = V[pl1 * S + idx];
+    a.u[2] = V[pl2 * S + idx];
+    a.beta = V[4 * S + idx];
+    a.lr = V[5 * S + idx];
+    a.lb = V[6 * S + idx];
     return a;
 }
 
@@ -502,6 +520,139 @@ __device__ __forceinline__ void line_compute(int l, const double* sWV, const dou
     }
 }
 
+// this thread's (n + 2) x 3 geometric factors: geoL (line-major, coalesced over the lines) -> its column of sGL, asynchronously
+template <int n, int EB>
+__device__ __forceinline__ void line_geometry_load(int l, long long e0, const HexParams& p, double* sGL, int GS) {
+    constexpr int NL = HexGeom<n>::NL, NG = 3 * (n + 2);
+    const int eb = l / NL, ll = l - eb * NL;
+    const double* GL = p.geoL + (e0 + eb) * NG * NL + ll;
+#pragma unroll
+    for (int k = 0; k < NG; ++k) cp_async8(sGL + k * GS, GL + k * NL);
+}
+
+// The line problem on a CURVED element (dg3D_euler_hex.jl:145-151): every pair (i, j) of hybridized points is contracted with
+// the AVERAGE of the two points' geometric factors, .5 (rxJ[i] + rxJ[j]) .., the surface flux takes the face point's own
+// normal.  The (n + 2) x 3 factors of a line's direction sit in the thread's own column of shared memory (registers are
+// full: at N = 4 keeping them there cost 190 bytes of spills inside the pair loop).
+template <int n, int EB, int WC = 2>
+__device__ __forceinline__ void line_compute_curved(int l, long long e0, const double* sWV, const double* sWF, const double* sP,
+                                                    const double* sGL, int GS, const HexParams& p, double c_igm, double (&acc)[n][5]) {
+    using G = HexGeom<n>;
+    constexpr int Nq = G::Nq, nfp = G::nfp, Nfq = G::Nfq, NL = G::NL, EF = EB * Nfq;
+    constexpr PairTab<n> PT{};
+    const int eb = l / NL, ll = l - eb * NL;
+    const int d = ll / nfp, m = ll - d * nfp;
+    int base, stride;
+    face_line<n>(d, m, base, stride);
+    const int c1 = d == 2 ? 0 : d + 1, c2 = c1 == 2 ? 0 : c1 + 1;
+    const int pl0 = 1 + d, pl1 = 1 + c1, pl2 = 1 + c2;
+    // (d_x, d_y, d_z) J of direction d at the line's n volume nodes and 2 face points (rotated components) were copied
+    // by THIS thread from the line-major array geoL into its own column of sGL (stride GS): gn(a, c) = sGL[(3 a + c) GS]
+    auto gn = [&](int a, int c) { return sGL[(a * 3 + c) * GS]; };
+    int fidx[2];
+#pragma unroll
+    for (int side = 0; side < 2; ++side) fidx[side] = eb * Nfq + (2 * d + side) * nfp + m;
+    // registers are full (accumulators, two face nodes, the pair in flight): the line's volume nodes are re-read from shared
+    // memory for every pair instead of being held (7 loads per node and pair against ~100 FP64 issue slots per pair)
+    auto nd = [&](int a) { return ld_node_rot_again(sWV, wv_stride<n, EB>(), eb * Nq + base + a * stride, pl0, pl1, pl2); };
+#pragma unroll
+    for (int a = 0; a < n; ++a)
+#pragma unroll
+        for (int f = 0; f < 5; ++f) acc[a][f] = 0.0;
+    // volume-volume pairs
+#pragma unroll
+    for (int k0 = 0; k0 < PT.NP; k0 += WC) {
+        NodeV<WC> A, B;
+        VD<WC> g[3], F[5];
+#pragma unroll
+        for (int q = 0; q < WC; ++q) {
+            const int k = k0 + q < PT.NP ? k0 + q : k0;
+            set_lane(A, q, nd(PT.a[k]));
+            set_lane(B, q, nd(PT.b[k]));
+#pragma unroll
+            for (int c = 0; c < 3; ++c) g[c][q] = .5 * (gn(PT.a[k], c) + gn(PT.b[k], c));
+        }
+        pair_flux_v<WC, false>(A, B, g, c_igm, F);
+#pragma unroll
+        for (int q = 0; q < WC; ++q) {
+            if (k0 + q < PT.NP) {
+                const int a = PT.a[k0 + q], b = PT.b[k0 + q];
+#pragma unroll
+                for (int f = 0; f < 5; ++f) {
+                    acc[a][f] = fma(p.T[a * n + b], F[f].v[q], acc[a][f]);
+                    acc[b][f] = fma(p.T[b * n + a], F[f].v[q], acc[b][f]);
+                }
+            }
+        }
+    }
+    // volume-face pairs (lane = side)
+    Node fn[2];
+#pragma unroll
+    for (int side = 0; side < 2; ++side) fn[side] = ld_node_rot(sWF, EF, fidx[side], pl0, pl1, pl2);
+    double h[2][5];
+#pragma unroll
+    for (int f = 0; f < 5; ++f) h[0][f] = h[1][f] = 0.0;
+#pragma unroll
+    for (int a = 0; a < n; ++a) {
+        NodeV<2> A, B;
+        VD<2> g[3], F[5];
+#pragma unroll
+        const Node na = nd(a);
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            set_lane(A, side, na);
+            set_lane(B, side, fn[side]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) g[c][side] = .5 * (gn(a, c) + gn(n + side, c));
+        }
+        pair_flux_v<2, false>(A, B, g, c_igm, F);
+#pragma unroll
+        for (int f = 0; f < 5; ++f) {
+            acc[a][f] = fma(-p.lmw[a], F[f][0], acc[a][f]);
+            acc[a][f] = fma(p.lpw[a], F[f][1], acc[a][f]);
+            h[0][f] = fma(p.lm[a], F[f][0], h[0][f]);
+            h[1][f] = fma(p.lp[a], F[f][1], h[1][f]);
+        }
+    }
+    // surface flux at the two face points with their own normals
+    VD<2> FS[5];
+    {
+        NodeV<2> M, P;
+        VD<2> nJ[3], sJ, lamM, lamP;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            set_lane(M, side, fn[side]);
+            set_lane(P, side, ld_node_rot(sP, EF, fidx[side], pl0, pl1, pl2));
+            const double* gf = p.geoN + (e0 + eb) * 4 * Nfq + (2 * d + side) * nfp + m;
+            nJ[0][side] = gf[d * Nfq]; nJ[1][side] = gf[c1 * Nfq]; nJ[2][side] = gf[c2 * Nfq]; sJ[side] = gf[3 * Nfq];
+            lamM[side] = sWF[7 * EF + fidx[side]];
+            lamP[side] = sP[7 * EF + fidx[side]];
+        }
+        pair_flux_v<2, false>(M, P, nJ, c_igm, FS);
+        if (p.lf_scale != 0.0) {
+            const VD<2> LFc = p.lf_scale * vmax(lamM, lamP) * sJ;
+            const VD<2> ibM = vrcp(M.beta), ibP = vrcp(P.beta);
+            const VD<2> qM = vfma(M.u[0], M.u[0], vfma(M.u[1], M.u[1], M.u[2] * M.u[2]));
+            const VD<2> qP = vfma(P.u[0], P.u[0], vfma(P.u[1], P.u[1], P.u[2] * P.u[2]));
+            const VD<2> tM = 2.0 * M.rho, tP = 2.0 * P.rho;
+            VD<2> jump[5];
+            jump[0] = P.rho - M.rho;
+            jump[1] = vfma(tP, P.u[0], -(tM * M.u[0]));
+            jump[2] = vfma(tP, P.u[1], -(tM * M.u[1]));
+            jump[3] = vfma(tP, P.u[2], -(tM * M.u[2]));
+            jump[4] = vfma(P.rho, vfma(ibP, c_igm, 2.0 * qP), -(M.rho * vfma(ibM, c_igm, 2.0 * qM)));
+#pragma unroll
+            for (int f = 0; f < 5; ++f) FS[f] = vfma(-LFc, jump[f], FS[f]);
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+        const double Hm = FS[f][0] + h[0][f], Hp = FS[f][1] - h[1][f];
+#pragma unroll
+        for (int a = 0; a < n; ++a) acc[a][f] = fma(p.lpw[a], Hp, fma(p.lmw[a], Hm, acc[a][f]));
+    }
+}
+
 // exterior-trace indices of the two face points of line l in the batch starting at element e0 ...
 template <int n, int EB>
 __device__ __forceinline__ void line_mapP(int l, long long e0, const HexParams& p, int (&ip)[2]) {
@@ -623,7 +774,7 @@ __device__ __forceinline__ void node_load(long long g, const HexParams& p, NodeI
     }
 }
 
-template <int n, int EB>
+template <int n, int EB, bool CURVED = false>
 __device__ __forceinline__ void node_update(int it, long long g, const HexParams& p, const NodeIn& in, const double* sA3, double* sV,
                                             const double* sGeo, const double* s_w, double& tsum, bool& bad) {
     using G = HexGeom<n>;
@@ -633,7 +784,7 @@ __device__ __forceinline__ void node_update(int it, long long g, const HexParams
 #pragma unroll
     for (int f = 0; f < 5; ++f) { U[f][0] = in.U[f]; R[f] = in.R[f]; }
     const int eb = it / Nq, i = it - eb * Nq;
-    const double J = sGeo[eb * HEX_SGEO + 9];
+    const double J = CURVED ? p.geoJ[g] : sGeo[eb * HEX_SGEO + 9];   // curved: `rhsQ ./ J` node by node (dg3D_euler_hex.jl:212)
     VD<1> Jv;
     Jv[0] = J;
     const VD<1> mJ = -vrcp(Jv);
@@ -698,7 +849,7 @@ __device__ __forceinline__ void node_entropy(int it, long long g, const HexParam
 #ifndef ESDG_F_SEQ
 #define ESDG_F_SEQ 0   // 1: the two ends of a line one after the other (W = 1, fewer registers) instead of interleaved (W = 2)
 #endif
-template <int n, int EB>
+template <int n, int EB, bool CURVED = false>
 __device__ __forceinline__ void line_traces(int l, long long e0, const HexParams& p, const double* sV, const double* sGeo,
                                             const double* s_lm, const double* s_lp) {
     using G = HexGeom<n>;
@@ -724,9 +875,15 @@ __device__ __forceinline__ void line_traces(int l, long long e0, const HexParams
     const double* ge = sGeo + eb * HEX_SGEO;
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
-        const double* gf = ge + 10 + (2 * d + side) * 4;
-        const double s2 = 2.0 * ge[HEX_GEO + 2 * d + side];
-        nh[0][side] = gf[0] * s2; nh[1][side] = gf[1] * s2; nh[2][side] = gf[2] * s2;
+        if (CURVED) {   // the face point's own normal (dg3D_euler_hex.jl:80-84)
+            const double* gn = p.geoN + (e0 + eb) * 4 * Nfq + (2 * d + side) * nfp + m;
+            const double s2 = 2.0 * fast_rcp(gn[3 * Nfq]);
+            nh[0][side] = gn[0] * s2; nh[1][side] = gn[Nfq] * s2; nh[2][side] = gn[2 * Nfq] * s2;
+        } else {
+            const double* gf = ge + 10 + (2 * d + side) * 4;
+            const double s2 = 2.0 * ge[HEX_GEO + 2 * d + side];
+            nh[0][side] = gf[0] * s2; nh[1][side] = gf[1] * s2; nh[2][side] = gf[2] * s2;
+        }
     }
     double* T0 = p.Tnext + (e0 + eb) * Nfq + 2 * d * nfp + m;
 #if ESDG_F_SEQ

@@ -32,6 +32,8 @@ void fill_hex_params(esdg_ctx* ctx, HexParams& p) {
     p.mapP = ctx->mapP;
     p.geo = ctx->geo;
     p.geo_stride = ctx->geo_stride;
+    p.geoG = ctx->geoG; p.geoJ = ctx->geoJ; p.geoN = ctx->geoN;
+    p.geoL = h->geoL;
     p.gamma = d.gamma;
     p.lf_scale = d.lf_scale;
     p.lg1 = std::log(d.gamma - 1.0);
@@ -75,6 +77,9 @@ int set_attrs(esdg_ctx* ctx) {
     CK(cudaFuncSetAttribute(k_hex_stage_ws<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_ws));
     CK(cudaFuncSetAttribute(k_hex_stage_ws<n, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_ws));
     CK(cudaFuncSetAttribute(k_hex_traces<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_traces));
+    h->smem_curved = (size_t)LD::SMEM_DOUBLES_CURVED * sizeof(double);
+    CK(cudaFuncSetAttribute(k_hex_stage_line_curved<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_curved));
+    CK(cudaFuncSetAttribute(k_hex_traces<n, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_traces));
     CK(cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, ctx->device));
     if (const char* gv = getenv("ESDG_WS_GRID")) h->sms = std::max(1, atoi(gv));   // experiments
     h->comm_sms = 2;
@@ -97,7 +102,10 @@ int launch_traces_n(esdg_ctx* ctx, const double* Q, long long e_begin = 0, long 
     if (e_count >= 0) { p.e_begin = e_begin; p.e_count = e_count; p.seg_len = seg_len; p.seg_stride = seg_stride; }
     const int blocks = (int)host_batches(p, h->EB_tr);
     tick(ctx, "hex_traces");
-    k_hex_traces<n><<<blocks, h->threads_tr, h->smem_traces, ctx->stream>>>(p);
+    if (h->curved)
+        k_hex_traces<n, true><<<blocks, h->threads_tr, h->smem_traces, ctx->stream>>>(p);
+    else
+        k_hex_traces<n><<<blocks, h->threads_tr, h->smem_traces, ctx->stream>>>(p);
     tock(ctx);
     CK(cudaGetLastError());
     return ESDG_OK;
@@ -109,8 +117,11 @@ int launch_stage_n(esdg_ctx* ctx, const HexParams& p, int reserve_sms = 0) {
     tick(ctx, "hex_stage");
     // the persistent kernel wants at least two batches per SM (its pipeline overlaps batch i with i +- 1)
     const long long nbatch_ws = host_batches(p, h->EB_ws);
-    const bool ws = h->kernel_choice == 2 || (h->kernel_choice == 0 && nbatch_ws >= 2LL * h->sms);
-    if (ws) {
+    const bool ws = !h->curved && (h->kernel_choice == 2 || (h->kernel_choice == 0 && nbatch_ws >= 2LL * h->sms));
+    if (h->curved) {
+        const int blocks = (int)host_batches(p, h->EB);
+        k_hex_stage_line_curved<n><<<blocks, h->threads, h->smem_curved, ctx->stream>>>(p);
+    } else if (ws) {
         // the persistent CTAs take every register of their SM: while a halo exchange is in flight a few SMs stay free
         // for the NCCL send / receive kernels, which could otherwise not start before this launch has drained
         const int grid = (int)std::min<long long>(nbatch_ws, std::max(1, h->sms - reserve_sms));
@@ -130,6 +141,37 @@ int launch_stage_n(esdg_ctx* ctx, const HexParams& p, int reserve_sms = 0) {
     return ESDG_OK;
 }
 
+// curved meshes: the geometric factors each line needs -- direction d of line (d, m): G[3 c + d] for the rotated components
+// c = d, d+1, d+2 at its n volume nodes and its two face points -- gathered line-major, [e][(n+2)*3][NL]
+int build_line_geometry(esdg_ctx* ctx) {
+    HexFast* h = ctx->hex;
+    const esdg_desc& d = ctx->d;
+    const int n = h->n, nfp = n * n, NL = 3 * nfp, Nq = d.Nq, NA = n + 2;
+    static const char* g3[9] = {"rxJ", "sxJ", "txJ", "ryJ", "syJ", "tyJ", "rzJ", "szJ", "tzJ"};
+    const HostMat* G[9];
+    for (int k = 0; k < 9; ++k) {
+        G[k] = find(ctx->geom, g3[k]);
+        if (!G[k] || G[k]->rows != Nq + d.Nfq) return fail(ctx, ESDG_EINVAL, "esdg_finalize: curved mesh needs rxJ.. at every hybridized point");
+    }
+    std::vector<double> gl((size_t)d.K * 3 * NA * NL);
+    for (int l = 0; l < NL; ++l) {
+        const int dir = l / nfp, m = l % nfp, ip = m % n, jp = m / n;
+        int base, stride;   // == face_line (hex_common.cuh)
+        if (dir == 0) { base = n * jp + n * n * ip; stride = 1; }
+        else if (dir == 1) { base = jp + n * n * ip; stride = n; }
+        else { base = jp + n * ip; stride = n * n; }
+        for (int a = 0; a < NA; ++a) {
+            const int node = a < n ? base + a * stride : Nq + (2 * dir + (a - n)) * nfp + m;
+            for (int c = 0; c < 3; ++c) {
+                const int comp = (dir + c) % 3;
+                const HostMat* g = G[3 * comp + dir];
+                for (int64_t e = 0; e < d.K; ++e) gl[((size_t)e * 3 * NA + (a * 3 + c)) * NL + l] = g->at(node, e);
+            }
+        }
+    }
+    return dev_upload(ctx, &h->geoL, gl);
+}
+
 int set_attrs_dispatch(esdg_ctx* ctx) {
     switch (ctx->hex->n) {
         case 2: return set_attrs<2>(ctx);
@@ -146,7 +188,7 @@ int hexfast_try_create(esdg_ctx* ctx) {
     const esdg_desc& d = ctx->d;
     if (d.elem != ESDG_HEX || d.dim != 3 || !d.collocated) return ESDG_OK;
     if (getenv("ESDG_FORCE_GENERIC")) return ESDG_OK;
-    if (!d.affine) return ESDG_OK;   // curved elements: per-point geometric factors, generic kernels
+    if (!d.affine && getenv("ESDG_CURVED_GENERIC")) return ESDG_OK;   // curved elements on the table-driven kernels (cross-check)
     int n = (int)std::lround(std::cbrt((double)d.Nq));
     if (n * n * n != d.Nq || n < 2 || n > 5 || d.Nfaces != 6 || d.Nfq != 6 * n * n) return ESDG_OK;
     const int Nq = d.Nq, nfp = n * n, Nfq = d.Nfq, Nh = Nq + Nfq;
@@ -216,6 +258,7 @@ int hexfast_try_create(esdg_ctx* ctx) {
     HexFast* h = new HexFast();
     ctx->hex = h;
     h->n = n;
+    h->curved = !d.affine;
     for (int a = 0; a < n; ++a) {
         h->lm[a] = lm[a];
         h->lp[a] = lp[a];
@@ -225,6 +268,7 @@ int hexfast_try_create(esdg_ctx* ctx) {
     (void)Nh;
     int rc;
     if ((rc = set_attrs_dispatch(ctx))) return rc;
+    if (h->curved && (rc = build_line_geometry(ctx))) return rc;
     for (int q = 0; q < 2; ++q) {
         if ((rc = dev_alloc(ctx, &h->trace[q], (size_t)HEX_TP * ctx->trace_stride))) return rc;
         if ((rc = dev_alloc(ctx, &h->logs[q], (size_t)2 * d.Nq * d.K))) return rc;

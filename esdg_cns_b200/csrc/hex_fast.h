@@ -7,12 +7,14 @@ constexpr int ESDG_HEX_TRACE_PLANES = 8;   // == esdg::HEX_TP (hex_common.cuh)
 struct HexFast {
     int n = 0;                 // N + 1
     bool diag = false;         // axis-aligned elements: only rxJ, syJ, tzJ non-zero
+    bool curved = false;       // desc.affine = 0: per-point geometric factors, one-shot kernel with line_compute_curved
+    double* geoL = nullptr;    // curved: rxJ.. line-major, [e][(n+2)*3][NL]
     double T[64], lm[8], lp[8], w[8];
     double* trace[2] = {nullptr, nullptr};   // 8 planes x trace_stride each
     double* logs[2] = {nullptr, nullptr};    // 2 planes x Nq*K each (log rho, log beta at volume nodes)
     int prod = 0;              // buffer most recently produced (pack/unpack act on it)
     int cons = 0;              // buffer the running stage consumes
-    size_t smem_stage = 0, smem_traces = 0;
+    size_t smem_stage = 0, smem_traces = 0, smem_curved = 0;
     int threads = 0, EB = 1;           // one-shot stage kernel launch shape (kernels_hex_line.cuh)
     int threads_tr = 0, EB_tr = 1;     // k_hex_traces launch shape
     int threads_ws = 0, EB_ws = 1;     // warp-specialised persistent stage kernel (kernels_hex_ws.cuh)

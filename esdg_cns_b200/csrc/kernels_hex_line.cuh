@@ -17,6 +17,7 @@ struct LineDims {
     // WV[7][EN] WF[8][EF] P[8][EF] A3[15][EN] (V[5][EN] aliases A3 block 0) geo[EB][40] lm lp w
     static constexpr int WV_DOUBLES = 7 * wv_stride<n, EB>();
     static constexpr int SMEM_DOUBLES = WV_DOUBLES + 16 * EF + 15 * EN + EB * HEX_SGEO + 3 * n;
+    static constexpr int SMEM_DOUBLES_CURVED = SMEM_DOUBLES + 1 + 3 * (n + 2) * THREADS;   // + one column of geometric factors per line thread
 };
 
 // own traces (bulk copies when every run is 16-byte aligned, else 8-byte cp.async) and exterior traces (gather
@@ -57,8 +58,9 @@ __device__ __forceinline__ bool trace_runs_aligned(const HexParams& p) {
     return ((p.t_stride & 1) == 0) && ((((size_t)p.Tcur) & 15) == 0);
 }
 
-template <int n, bool DIAG>
-__global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex_stage_line(const __grid_constant__ HexParams p) {
+// CURVED: per-pair averaged geometric factors, per-point normals and Jacobians (line_compute_curved, hex_common.cuh)
+template <int n, bool DIAG, bool CURVED>
+__device__ __forceinline__ void hex_stage_line_body(const HexParams& p) {
     using D = LineDims<n>;
     using G = HexGeom<n>;
     constexpr int Nq = G::Nq, Nfq = G::Nfq, NL = G::NL, EB = D::EB, NT = D::THREADS, EN = D::EN, EF = D::EF;
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex
     double* s_lm = sGeo + EB * HEX_SGEO;
     double* s_lp = s_lm + n;
     double* s_w = s_lp + n;
+    double* sGL = s_w + n + ((3 * n) & 1);   // CURVED: [3 (n + 2)][NT]
     const int tid = threadIdx.x;
     long long e0;
     int nb;
@@ -98,6 +101,9 @@ __global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex
     bool bad = false;
     const bool bulk = trace_runs_aligned(p);
     issue_trace_loads<n, EB, NT>(tid, nb, e0, p, sWF, sP, &mbar, bulk, ipv);
+    if constexpr (CURVED) {
+        if (tid < nb * NL) line_geometry_load<n, EB>(tid, e0, p, sGL + tid, NT);
+    }
     cp_async_commit();
     stage_geo<EB>(tid, NT, nb, e0, p, sGeo);
     // ---- A ----
@@ -108,7 +114,8 @@ __global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex
     // ---- C ----
     if (tid < nb * NL) {
         double acc[n][5];
-        line_compute<n, EB, DIAG>(tid, sWV, sWF, sP, sGeo, p, c_igm, acc);
+        if constexpr (CURVED) line_compute_curved<n, EB>(tid, e0, sWV, sWF, sP, sGL + tid, NT, p, c_igm, acc);
+        else line_compute<n, EB, DIAG>(tid, sWV, sWF, sP, sGeo, p, c_igm, acc);
         line_store<n, EB>(tid, acc, sA);
     }
     __syncthreads();
@@ -117,12 +124,12 @@ __global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex
     for (int it = tid; it < nb * Nq; it += NT) {
         NodeIn in;
         node_load(e0 * Nq + it, p, in);
-        node_update<n, EB>(it, e0 * Nq + it, p, in, sA, sA, sGeo, s_w, tsum, bad);
+        node_update<n, EB, CURVED>(it, e0 * Nq + it, p, in, sA, sA, sGeo, s_w, tsum, bad);
     }
     if (p.mode == 1) {
         __syncthreads();
         // ---- F ----
-        for (int l = tid; l < nb * NL; l += NT) line_traces<n, EB>(l, e0, p, sA, sGeo, s_lm, s_lp);
+        for (int l = tid; l < nb * NL; l += NT) line_traces<n, EB, CURVED>(l, e0, p, sA, sGeo, s_lm, s_lp);
     }
     if (p.want_rhstest) {
         for (int o = 16; o > 0; o >>= 1) tsum += __shfl_down_sync(0xffffffffu, tsum, o);
@@ -137,6 +144,17 @@ __global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex
     if (bad) atomicOr(p.bad, 1);
 }
 
+template <int n, bool DIAG>
+__global__ void __launch_bounds__(LineDims<n>::THREADS, LineDims<n>::MINB) k_hex_stage_line(const __grid_constant__ HexParams p) {
+    hex_stage_line_body<n, DIAG, false>(p);
+}
+// curved elements: 168 registers = three warps per SM sub-partition, i.e. two 160-thread CTAs per SM at N = 4 (at 200 registers
+// only 8 warps fit an SM and the second CTA does not: measured 42.9 -> see profiles/r2_curved_hex.txt)
+template <int n>
+__global__ void __launch_bounds__(LineDims<n>::THREADS, n == 5 ? 2 : 3) k_hex_stage_line_curved(const __grid_constant__ HexParams p) {
+    hex_stage_line_body<n, false, true>(p);
+}
+
 // Traces (+ log stash) of a given state: runs once after an upload and in the rhs-only entry point.
 template <int n>
 struct TraceDims {
@@ -146,7 +164,7 @@ struct TraceDims {
     static constexpr int SMEM_DOUBLES = EB * 5 * G::Nq + EB * HEX_SGEO + 2 * n;
 };
 
-template <int n>
+template <int n, bool CURVED = false>
 __global__ void __launch_bounds__(TraceDims<n>::THREADS) k_hex_traces(const __grid_constant__ HexParams p) {
     using D = TraceDims<n>;
     using G = HexGeom<n>;
@@ -165,7 +183,7 @@ __global__ void __launch_bounds__(TraceDims<n>::THREADS) k_hex_traces(const __gr
     stage_geo<EB>(tid, NT, nb, e0, p, sGeo);
     for (int it = tid; it < nb * G::Nq; it += NT) node_entropy<n, EB>(it, e0 * G::Nq + it, p, sV, bad);
     __syncthreads();
-    for (int l = tid; l < nb * G::NL; l += NT) line_traces<n, EB>(l, e0, p, sV, sGeo, s_lm, s_lp);
+    for (int l = tid; l < nb * G::NL; l += NT) line_traces<n, EB, CURVED>(l, e0, p, sV, sGeo, s_lm, s_lp);
     if (bad) atomicOr(p.bad, 1);
 }
 

@@ -367,6 +367,67 @@ def uniform_hex_mesh_md(rd, Kxyz, domain=((-1.0, 1.0),) * 3, periodic=(True, Tru
     return md
 
 
+def curved_hex_mesh_md(rd, Kxyz, domain=((-1.0, 1.0),) * 3, amp=.08):
+    """A periodic hex mesh with CURVED (trilinear, non-affine) elements: the vertices of the uniform mesh are displaced by a
+    smooth periodic field of amplitude ``amp`` element widths, so every element is a general hexahedron, the mesh stays
+    watertight (a trilinear map is reproduced exactly by any N >= 1) and the connectivity is that of the uniform mesh.
+    Geometric factors in the curl form of src/geometric_factors.jl:34-67 at the Gauss nodes, interpolated to the face
+    points as the hex script does (dg3D_euler_hex.jl:69-101): ``rxJ.. : Nh x K``, ``J : Nq x K``, ``nxJ.., sJ : Nfq x K``."""
+    md = uniform_hex_mesh_md(rd, Kxyz, domain=domain)
+    n = rd.N + 1
+    Kx, Ky, Kz = Kxyz
+    (x0, x1), (y0, y1), (z0, z1) = domain
+    hx, hy, hz = md.h
+    x1d, _ = gauss_1d(rd.N)
+    D = lagrange_deriv(x1d)
+    I = np.eye(n)
+    Dr, Ds, Dt = np.kron(I, np.kron(I, D)), np.kron(I, np.kron(D, I)), np.kron(D, np.kron(I, I))
+    lm, lp = lagrange_eval(x1d, -1.0)[0], lagrange_eval(x1d, 1.0)[0]
+    e = np.arange(md.K)
+    ex, ey, ez = e % Kx, (e // Kx) % Ky, e // (Kx * Ky)
+
+    def vertex(ix, iy, iz):                       # displaced vertex (ix, iy, iz) of the lattice, periodic in the displacement
+        X, Y, Z = x0 + hx * ix, y0 + hy * iy, z0 + hz * iz
+        a, b, c = 2 * np.pi * ix / Kx, 2 * np.pi * iy / Ky, 2 * np.pi * iz / Kz
+        return (X + amp * hx * np.sin(b + .3) * np.cos(c) * np.cos(a),
+                Y + amp * hy * np.sin(c - .2) * np.cos(a) * np.cos(b),
+                Z + amp * hz * np.sin(a + .5) * np.cos(b) * np.cos(c))
+
+    xyz = [np.zeros((n ** 3, md.K)) for _ in range(3)]
+    for dz in (0, 1):
+        for dy in (0, 1):
+            for dx in (0, 1):
+                shape = ((1 + (2 * dx - 1) * rd.rq) * (1 + (2 * dy - 1) * rd.sq) * (1 + (2 * dz - 1) * rd.tq) / 8)[:, None]
+                V = vertex(ex + dx, ey + dy, ez + dz)
+                for q in range(3):
+                    xyz[q] += shape * V[q][None, :]
+    x, y, z = xyz
+    xr, xs, xt = Dr @ x, Ds @ x, Dt @ x
+    yr, ys, yt = Dr @ y, Ds @ y, Dt @ y
+    zr, zs, zt = Dr @ z, Ds @ z, Dt @ z
+    Fr, Fs, Ft = yr * z, ys * z, yt * z
+    G = {}
+    G["rxJ"], G["sxJ"], G["txJ"] = Dt @ Fs - Ds @ Ft, Dr @ Ft - Dt @ Fr, Ds @ Fr - Dr @ Fs
+    Fr, Fs, Ft = xr * z, xs * z, xt * z
+    G["ryJ"], G["syJ"], G["tyJ"] = -(Dt @ Fs - Ds @ Ft), -(Dr @ Ft - Dt @ Fr), -(Ds @ Fr - Dr @ Fs)
+    Fr, Fs, Ft = yr * x, ys * x, yt * x
+    G["rzJ"], G["szJ"], G["tzJ"] = -(Dt @ Fs - Ds @ Ft), -(Dr @ Ft - Dt @ Fr), -(Ds @ Fr - Dr @ Fs)
+    md.J = xr * (ys * zt - zs * yt) - yr * (xs * zt - zs * xt) + zr * (xs * yt - ys * xt)
+    _, ops = reference_hex(rd.N)
+    Ef = ops.Ef
+    for k, v in G.items():
+        setattr(md, k, np.vstack([v, Ef @ v]))
+    Nq = n ** 3
+    nr, ns, nt = rd.nrJ[:, None], rd.nsJ[:, None], rd.ntJ[:, None]
+    md.nxJ = nr * md.rxJ[Nq:] + ns * md.sxJ[Nq:] + nt * md.txJ[Nq:]
+    md.nyJ = nr * md.ryJ[Nq:] + ns * md.syJ[Nq:] + nt * md.tyJ[Nq:]
+    md.nzJ = nr * md.rzJ[Nq:] + ns * md.szJ[Nq:] + nt * md.tzJ[Nq:]
+    md.sJ = np.sqrt(md.nxJ ** 2 + md.nyJ ** 2 + md.nzJ ** 2)
+    md.xq, md.yq, md.zq = x, y, z
+    md.curved = True
+    return md
+
+
 def structured_hex_md(rd, Kxyz, domain=((-1.0, 1.0),) * 3, periodic=(True, True, True), zslab=None):
     """The same mesh as ``uniform_hex_mesh_md`` WITHOUT its arrays: ``api.Solver`` hands the six integers and the box to
     ``esdg_set_structured_hex`` and the library generates mapP and the geometric factors on the device (SURVEY 8f

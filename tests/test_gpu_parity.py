@@ -358,19 +358,25 @@ def _curved_case(N, K1D, seed=0):
     return rd, md, ops, list(P.primitive_to_conservative(rho, (u, v, w), p))
 
 
-@pytest.mark.parametrize("N,K1D", [(1, 3), (2, 3), (3, 2)])
+@pytest.mark.parametrize("N,K1D", [(1, 3), (2, 3), (3, 2), (4, 2)])
 @pytest.mark.parametrize("lf", [0.0, 0.25])
-def test_curved_hex_rhs_matches_oracle(N, K1D, lf):
+@pytest.mark.parametrize("generic", [False, True])
+def test_curved_hex_rhs_matches_oracle(N, K1D, lf, generic, monkeypatch):
     """curved (trilinear) hexes -- geometric factors at every hybridized point averaged
-    per pair (dg3D_euler_hex.jl:145-151), J per node, normals per face point."""
+    per pair (dg3D_euler_hex.jl:145-151), J per node, normals per face point -- on the tensor-product line kernel
+    (line_compute_curved) and, with ESDG_CURVED_GENERIC=1, on the table-driven kernels."""
     from oracle import solvers as SV
     from esdg_cns_b200 import api
+    if generic:
+        if N == 4:
+            pytest.skip("table-driven kernels: covered at N <= 3")
+        monkeypatch.setenv("ESDG_CURVED_GENERIC", "1")
     rd, md, ops, Q = _curved_case(N, K1D)
     ops.lf_scale = lf
     assert np.abs(md.rxJ - md.rxJ[:1]).max() > 1e-3          # the mesh really is curved
     ref, rt_ref = SV.rhs_collocated(Q, md, ops, rd, lf, True)
     s = api.Solver(md, ops)
-    assert s.affine == 0 and s.kernel_time_ms("hex_stage")[1] == 0
+    assert s.affine == 0 and s.kernel_path() == ("generic" if generic else "hex_line_curved")
     out, rt = s.rhs(Q, True)
     tol = parity_tol(lambda: SV.rhs_collocated(Q, md, ops, rd, lf, False)[0], ref)
     err = _relerr(out, ref)
@@ -383,12 +389,16 @@ def test_curved_hex_rhs_matches_oracle(N, K1D, lf):
         assert rt <= 1e-12
 
 
-def test_curved_hex_freestream_and_lsrk_steps():
+@pytest.mark.parametrize("generic", [False, True])
+def test_curved_hex_freestream_and_lsrk_steps(generic, monkeypatch):
     from oracle import solvers as SV, physics as P
     from esdg_cns_b200 import api
+    if generic:
+        monkeypatch.setenv("ESDG_CURVED_GENERIC", "1")
     rd, md, ops, Q = _curved_case(2, 3, seed=4)
     ops.lf_scale = .25
     s = api.Solver(md, ops)
+    assert s.kernel_path() == ("generic" if generic else "hex_line_curved")
     one = np.ones_like(md.xq)
     Qc = list(P.primitive_to_conservative(1.2 * one, (.3 * one, -.2 * one, .1 * one), .9 * one))
     out, _ = s.rhs(Qc, False)
@@ -455,6 +465,7 @@ def test_symmetric_pair_schedule_matches_row_wise_sum(case, monkeypatch):
         monkeypatch.setenv("ESDG_FORCE_GENERIC", "1")
         rd, md, ops, Q = _hex_case(2, 3, "rand", generic_velocity=True)
     else:
+        monkeypatch.setenv("ESDG_CURVED_GENERIC", "1")
         rd, md, ops, Q = _curved_case(2, 3)
     ops.lf_scale = 0.0
     res = []
@@ -467,3 +478,55 @@ def test_symmetric_pair_schedule_matches_row_wise_sum(case, monkeypatch):
     print(f"{case}: symmetric vs row-wise relerr {err:.2e}; rhstest {res[0][1]:.2e} / {res[1][1]:.2e}")
     assert err < 1e-13
     assert abs(res[1][1]) < 1e-11
+
+
+def test_curved_package_mesh_line_kernel_vs_generic_and_affine_limit(monkeypatch):
+    """setup_dg.curved_hex_mesh_md at N = 4 through the curved line kernel and the table-driven kernels (rhs + 2 LSRK45 steps),
+    and the amp = 0 limit of the curved kernel against the affine tensor-product kernel on the same (uniform) mesh."""
+    from esdg_cns_b200 import api, setup_dg as SD
+    N, mesh, dom = 4, (4, 3, 5), ((-np.pi, np.pi),) * 3
+    prd, pops = SD.reference_hex(N)
+    md = SD.curved_hex_mesh_md(prd, mesh, domain=dom, amp=.1)
+    x, y, z = md.xq, md.yq, md.zq        # O(1) variation from node to node: well away from the low-Mach cancellation of the bench IC
+    Q = SD.primitive_to_conservative(2 + .3 * np.sin(x) * np.cos(2 * z), (.4 + .2 * np.cos(y), -.3 + .2 * np.sin(z + x), .2 + .1 * np.sin(2 * y)),
+                                     1 + .2 * np.cos(x + y) * np.sin(z))
+    res = []
+    for generic in (False, True):
+        if generic:
+            monkeypatch.setenv("ESDG_CURVED_GENERIC", "1")
+        s = api.Solver(md, pops)
+        assert s.kernel_path() == ("generic" if generic else "hex_line_curved")
+        r, rt = s.rhs(Q, True)
+        s.upload(Q)
+        rts = s.lsrk45(2e-3, 2, want_rhstest=True)
+        res.append((r, rt, s.download(), rts))
+        s.close()
+    monkeypatch.delenv("ESDG_CURVED_GENERIC")
+    scale = max(np.abs(x).max() for x in res[1][0])
+    d_rhs = max(np.abs(a - b).max() for a, b in zip(res[0][0], res[1][0])) / scale
+    d_Q = max(np.abs(a - b).max() for a, b in zip(res[0][2], res[1][2]))
+    # both against the oracle evaluated on the package's mesh
+    from oracle import solvers as SV
+    from helpers import parity_tol
+    rdo, _, opo = SV.setup_hex(N, 2)
+    md.wJq = np.diag(rdo.wq) @ md.J
+    opo.lf_scale = pops.lf_scale
+    ref = SV.rhs_collocated(list(Q), md, opo, rdo, pops.lf_scale, False)[0]
+    tol = parity_tol(lambda: SV.rhs_collocated(list(Q), md, opo, rdo, pops.lf_scale, False)[0], ref)
+    e_line, e_gen = _relerr(res[0][0], ref), _relerr(res[1][0], ref)
+    print(f"curved N=4: vs oracle line {e_line:.2e} generic {e_gen:.2e} (tol {tol:.2e}); line vs generic rhs {d_rhs:.2e}, "
+          f"state after 2 steps {d_Q:.2e}; rhstest {res[0][1]:.6e} / {res[1][1]:.6e}")
+    assert e_line < tol and e_gen < tol
+    assert d_rhs < 2 * tol and d_Q < 1e-12
+    assert abs(res[0][1] - res[1][1]) < 1e-10 * max(1.0, abs(res[1][1])) and abs(res[0][3] - res[1][3]) < 1e-10 * max(1.0, abs(res[1][3]))
+    # amp = 0: the "curved" arrays describe the uniform mesh
+    md0 = SD.curved_hex_mesh_md(prd, mesh, domain=dom, amp=0.0)
+    mda = SD.uniform_hex_mesh_md(prd, mesh, domain=dom)
+    sc = api.Solver(md0, pops, affine=0)
+    sa = api.Solver(mda, pops)
+    assert sc.kernel_path() == "hex_line_curved" and sa.kernel_path() == "hex_line_diag"
+    rc, _ = sc.rhs(Q, False)
+    ra, _ = sa.rhs(Q, False)
+    d0 = max(np.abs(a - b).max() for a, b in zip(rc, ra)) / max(np.abs(x).max() for x in ra)
+    print(f"amp = 0: curved kernel vs affine kernel {d0:.2e}")
+    assert d0 < 5e-12

@@ -78,3 +78,30 @@ def test_modal_quad_and_cavity_sets_match_oracle():
         assert np.array_equal(np.sort(pbc.lid), np.sort(bc.lid))
         assert np.array_equal(np.sort(pbc.wall), np.sort(bc.wall))
         assert np.array_equal(np.sort(pbc.mapB), np.sort(md.mapB))
+
+
+def test_curved_hex_mesh_of_the_package_is_watertight_and_preserves_the_free_stream():
+    """setup_dg.curved_hex_mesh_md (displaced vertices, trilinear elements, curl-form geometric factors) driven through the
+    ORACLE's hex rhs: a constant state has zero rhs (metric identities + matching normals on shared faces), the rhs without
+    penalty conserves entropy to round-off, and the mesh really is curved."""
+    from oracle import solvers as SV, physics as P
+    from esdg_cns_b200 import setup_dg as SD
+    N = 2
+    rd, md0, ops = SV.setup_hex(N, 3)
+    prd, pops = SD.reference_hex(N)
+    md = SD.curved_hex_mesh_md(prd, (3, 4, 3), domain=((-1, 1), (-1.5, 1.5), (0, 2)), amp=.1)
+    md.wJq = np.diag(rd.wq) @ md.J
+    assert md.rxJ.shape == (ops.Ef.shape[0] + rd.wq.size, md.K) and md.J.min() > 0
+    assert np.abs(md.rxJ - md.rxJ[:1]).max() > 1e-3 * np.abs(md.rxJ).max()
+    # normals of the two sides of every face are opposite (watertight, conforming)
+    for a in (md.nxJ, md.nyJ, md.nzJ):
+        assert np.abs(a + a.reshape(-1, order="F")[md.mapP.reshape(-1, order="F")].reshape(a.shape, order="F")).max() < 1e-13
+    one = np.ones_like(md.xq)
+    Qc = list(P.primitive_to_conservative(1.2 * one, (.3 * one, -.2 * one, .1 * one), .9 * one))
+    out, _ = SV.rhs_collocated(Qc, md, ops, rd, .25, False)
+    assert max(np.abs(x).max() for x in out) < 1e-12
+    rng = np.random.default_rng(0)
+    rho, p = 2 + .1 * rng.random(one.shape), 1 + .1 * rng.random(one.shape)
+    Q = list(P.primitive_to_conservative(rho, (.3 + .1 * rng.random(one.shape), 1 + .1 * rng.random(one.shape), -.2 + 0 * one), p))
+    _, rt = SV.rhs_collocated(Q, md, ops, rd, 0.0, True)
+    assert abs(rt) < 1e-11
