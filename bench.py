@@ -198,7 +198,7 @@ def other_configs(device, peak_gbs):
     from esdg_cns_b200 import api, setup_dg as SD, roofline as R
     out = []
 
-    def run(name, solver, Q, dt, nf, Ns, Nfq, d, kernels, K, cns=False, nsteps=4):
+    def run(name, solver, Q, dt, nf, Ns, Nfq, d, kernels, K, cns=False, nsteps=4, B=None):
         solver.upload(Q)
         solver.lsrk45(dt, 2)
         solver.sync()
@@ -209,7 +209,7 @@ def other_configs(device, peak_gbs):
         finite = all(np.isfinite(q).all() for q in solver.download())
         solver.close()
         per_stage = ms / (5 * nsteps)
-        B = R.alg_bytes_sizes(nf, Ns, Nfq, d, cns)
+        B = B if B is not None else R.alg_bytes_sizes(nf, Ns, Nfq, d, cns)
         out.append({"config": name, "elements": int(K), "dof": int(nf * Ns * K), "ms_per_stage": per_stage,
                     "value": nf * Ns * K / (per_stage * 1e-3), "unit": UNIT, "alg_bytes_per_element_stage": B,
                     "achieved_gbs": B * K / (per_stage * 1e-3) / 1e9, "frac": B * K / (per_stage * 1e-3) / 1e9 / peak_gbs,
@@ -225,6 +225,16 @@ def other_configs(device, peak_gbs):
     run("4: hex N=3 64^3 vortex (tensor-product kernels)", api.Solver(md, pops, device=device), Q, tgv_dt(N, 64) * 5 / np.pi, 5,
         (N + 1) ** 3, 6 * (N + 1) ** 2, 3, ["hex_stage"], md.K)
     del md, Q, x, y, z
+    # config 5's element on a CURVED mesh: hex N=4, 32^3 trilinear elements, geometric factors at every
+    # hybridized point averaged per pair (dg3D_euler_hex.jl:145-151)
+    prd4, pops4 = SD.reference_hex(4)
+    md = SD.curved_hex_mesh_md(prd4, (32, 32, 32), domain=((-np.pi, np.pi),) * 3, amp=.1)
+    rho, u, v, w, p = SD.taylor_green(md.xq, md.yq, md.zq)
+    Q = SD.primitive_to_conservative(rho, (u, v, w), p)
+    sc = api.Solver(md, pops4, device=device)
+    run("5c: hex N=4 32^3 curved elements (%s)" % sc.kernel_path(), sc, Q, tgv_dt(4, 32), 5, 125, 150, 3, ["hex_stage"], md.K,
+        B=R.alg_bytes_curved_hex(4))
+    del md, Q, rho, u, v, w, p
     # config 1 operators at timing scale: collocated quads N=3, 1024^2, periodic vortex
     rd, ops = SD.reference_quad(N)
     md = SD.uniform_quad_mesh_md(rd, 1024, 1024, domain=((0, 20), (-5, 5)))

@@ -45,6 +45,12 @@ def alg_bytes_sizes(nf, Ns, Nfq, d, cns=False):
     return b
 
 
+def alg_bytes_curved_hex(N):
+    """Curved hexes: the affine figure + the nine geometric factors at every hybridized point (9 Nh 8 B)."""
+    s = sizes("hex", N)
+    return alg_bytes_sizes(s["nf"], s["Ns"], s["Nfq"], 3) + 9 * (s["Nq"] + s["Nfq"]) * 8
+
+
 def alg_bytes(elem, N, cns=False):
     s = sizes(elem, N)
     return alg_bytes_sizes(s["nf"], s["Ns"], s["Nfq"], s["d"], cns)

@@ -232,10 +232,10 @@ int esdg_comm_init(esdg_ctx* ctx, const void* id128, int nranks, int rank, int n
                    const int64_t* nb_send, const int64_t* nb_recv);
 int esdg_comm_destroy(esdg_ctx* ctx);
 /* which kernel family a finalized context runs: "hex_line_diag" (tensor-product hexes, axis-aligned elements),
- * "hex_line" (general affine hexes), "quad_line" (tensor-product quads, dg2D_euler_quad.jl), "generic" (table-driven),
+ * "hex_line" (general affine hexes), "hex_line_curved" (desc.affine = 0: per-pair averaged geometric factors), "quad_line" (tensor-product quads, dg2D_euler_quad.jl), "generic" (table-driven),
  * "cns_quad_line" (Navier-Stokes on quads, state kept in the Gauss-nodal basis between upload and download -- invisible
  * at this boundary: every entry point takes and returns the caller's coefficients), "cns" (table-driven modal kernels:
- * triangles, inflow / outflow contexts).  ESDG_FORCE_GENERIC=1 / ESDG_CNS_MODAL=1 in the environment select the
+ * triangles, inflow / outflow contexts).  ESDG_FORCE_GENERIC=1 / ESDG_CURVED_GENERIC=1 / ESDG_CNS_MODAL=1 in the environment select the
  * table-driven families. */
 const char* esdg_kernel_path(const esdg_ctx* ctx);
 int esdg_read_rhstest(esdg_ctx* ctx, double* rhstest);
