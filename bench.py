@@ -189,11 +189,11 @@ def bind_to_gpu_cpus(index):
 
 # ------------------------------------------------------------------- the other BASELINE configs
 def other_configs(device, peak_gbs):
-    """BASELINE configs 4, 1 (operators at timing scale) and 3 timed in the same process (a few seconds each), so that
+    """BASELINE configs 4, 1, 2 (operators at timing scale) and 3, plus config 5's element on a curved mesh, timed in the
+    same process (a few seconds each), so that
     their numbers are driver-visible: DOF*stage/s with the state resident, ms per LSRK stage from CUDA events around
     the kernels, ALGORITHMIC bytes per element-stage (esdg_cns_b200/roofline.py) and the fraction of the measured HBM
-    peak they amount to.  Config 2 (triangles) needs operators the product package does not build; it is measured in
-    tests/test_gpu_perf_report.py with oracle-built operators."""
+    peak they amount to."""
     from types import SimpleNamespace
     from esdg_cns_b200 import api, setup_dg as SD, roofline as R
     out = []
@@ -244,6 +244,15 @@ def other_configs(device, peak_gbs):
     tp = sq.kernel_path() == "quad_line"
     run("1: quad N=3 1024^2 vortex (%s kernels)" % ("tensor-product" if tp else "generic"), sq, Q, 1e-4, 4, (N + 1) ** 2, 4 * (N + 1), 2,
         ["quad_stage"] if tp else ["generic_rhs", "generic_traces"], md.K)
+    del md, Q
+    # config 2 at timing scale: modal triangles N=4, 2 x 256^2 elements, periodic vortex (dense hybridized operators: table-driven
+    # kernels with DMMA batch GEMMs and the symmetric pair schedule)
+    rdt, opst = SD.reference_tri(4)
+    md = SD.uniform_tri_mesh_md(rdt, 256, 256, domain=((0, 20), (-5, 5)))
+    rho, u, v, p = SD.vortex(md.x, md.y)
+    Q = SD.primitive_to_conservative(rho, (u, v), p)
+    run("2: tri N=4 2x256^2 vortex (modal, generic kernels)", api.Solver(md, opst, device=device), Q, 1e-4, 4, rdt.r.size, rdt.rf.size, 2,
+        ["generic_rhs", "generic_traces"], md.K)
     del md, Q
     # config 3: CNS lid-driven cavity, modal quads N=3, 512^2, BCTYPE 1, both dissipations on
     rd, ops = SD.reference_quad_modal(N)
@@ -444,7 +453,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--small", action="store_true", help="16x16x8 elements per GPU (debugging only; not a bench number)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-other", action="store_true", help="skip the other_configs block (BASELINE configs 1, 3, 4 at timing scale)")
+    ap.add_argument("--no-other", action="store_true", help="skip the other_configs block (BASELINE configs 1-4 at timing scale, curved hexes)")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange halos without overlapping interior work")
     ap.add_argument("--py-halo", action="store_true", help="multi-GPU: host-driven halo exchange (torch.distributed) instead of the context's own NCCL communicator")
     args = ap.parse_args()

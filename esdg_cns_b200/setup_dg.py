@@ -1,4 +1,4 @@
-"""Host-side setup for uniform quad / hex meshes (not on the hot path).
+"""Host-side setup for uniform quad / triangle / hex meshes (not on the hot path).
 
 In a Julia deployment ``rd``/``md``/``ops`` come from the reference's own
 ``SetupDG.jl`` and script-level operator assembly and are handed to the library
@@ -200,6 +200,194 @@ def reference_quad_modal(N, lf_scale=.25):
                           VhP=Vh @ Pq, Lf=LIFT, Vq=Vq, Pq=Pq, Vf=Vf, Dr=Dr, Ds=Ds, modal=True,
                           volume_scale=2.0, lf_scale=lf_scale)
     return rd, ops
+
+
+# ------------------------------------------------------------------ triangles
+def _scaled_legendre(i, xi, eta):
+    """Q_i(xi, eta) = eta^i P_i(xi / eta) (a polynomial: no division) and its partial derivatives."""
+    Q0, Q1 = np.ones_like(xi), xi.copy()
+    dx0, dx1 = np.zeros_like(xi), np.ones_like(xi)
+    de0, de1 = np.zeros_like(xi), np.zeros_like(xi)
+    if i == 0:
+        return Q0, dx0, de0
+    for k in range(1, i):
+        Q2 = ((2 * k + 1) * xi * Q1 - k * eta * eta * Q0) / (k + 1)
+        dx2 = ((2 * k + 1) * (Q1 + xi * dx1) - k * eta * eta * dx0) / (k + 1)
+        de2 = ((2 * k + 1) * xi * de1 - k * (2 * eta * Q0 + eta * eta * de0)) / (k + 1)
+        Q0, Q1, dx0, dx1, de0, de1 = Q1, Q2, dx1, dx2, de1, de2
+    return Q1, dx1, de1
+
+
+def _jacobi_a0(j, alpha, x):
+    """P_j^(alpha, 0)(x) (standard normalisation) and its derivative, by the three-term recurrence."""
+    P0, P1 = np.ones_like(x), ((alpha + 2) * x + alpha) / 2
+    d0, d1 = np.zeros_like(x), np.full_like(x, (alpha + 2) / 2)
+    if j == 0:
+        return P0, d0
+    for n in range(1, j):
+        c = 2 * n + alpha
+        a1 = 2 * (n + 1) * (n + alpha + 1) * c
+        a2 = (c + 1) * alpha * alpha
+        a3 = c * (c + 1) * (c + 2)
+        a4 = 2 * (n + alpha) * n * (c + 2)
+        P2 = ((a2 + a3 * x) * P1 - a4 * P0) / a1
+        d2 = (a3 * P1 + (a2 + a3 * x) * d1 - a4 * d0) / a1
+        P0, P1, d0, d1 = P1, P2, d1, d2
+    return P1, d1
+
+
+def _tri_basis(N, r, s):
+    """A basis of P_N on the reference triangle (collapsed-coordinate products, orthogonal) and its r/s derivatives at
+    the points (r, s): columns ordered (i, j), i + j <= N.  Any basis of P_N gives the same nodal operators."""
+    r, s = np.asarray(r, dtype=np.float64), np.asarray(s, dtype=np.float64)
+    xi, eta = r + (1 + s) / 2, (1 - s) / 2
+    V, Vr, Vs = [], [], []
+    for i in range(N + 1):
+        Q, Qx, Qe = _scaled_legendre(i, xi, eta)
+        for j in range(N - i + 1):
+            R, dR = _jacobi_a0(j, 2 * i + 1, s)
+            V.append(Q * R)
+            Vr.append(Qx * R)
+            Vs.append((.5 * Qx - .5 * Qe) * R + Q * dR)
+    return np.array(V).T, np.array(Vr).T, np.array(Vs).T
+
+
+def _warp_factor(N, rout):
+    """1-D warp of the equispaced points towards the GLL points, evaluated at rout (Hesthaven & Warburton's warp & blend;
+    src/Basis2DTri.jl:170-186)."""
+    req = np.linspace(-1, 1, N + 1)
+    warp = lagrange_eval(req, rout) @ (gll_1d(N) - req)
+    zerof = (np.abs(rout) < 1.0 - 1.0e-10).astype(np.float64)
+    sf = 1.0 - (zerof * rout) ** 2
+    return warp / sf + warp * (zerof - 1)
+
+
+def tri_nodes(N):
+    """Warp & blend interpolation nodes of degree N (src/Basis2DTri.jl:197-233), reference ordering."""
+    alpopt = [0.0, 0.0, 1.4152, 0.1001, 0.2751, 0.98, 1.0999, 1.2832, 1.3648, 1.4773, 1.4959, 1.5743, 1.577, 1.6223, 1.6258]
+    alpha = alpopt[N - 1] if N < 16 else 5 / 3
+    L1, L3 = [], []
+    for n in range(N + 1):
+        for m in range(N + 1 - n):
+            L1.append(n / N)
+            L3.append(m / N)
+    L1, L3 = np.array(L1), np.array(L3)
+    L2 = 1.0 - L1 - L3
+    x, y = -L2 + L3, (-L2 - L3 + 2 * L1) / np.sqrt(3.0)
+    w1 = 4 * L2 * L3 * _warp_factor(N, L3 - L2) * (1 + (alpha * L1) ** 2)
+    w2 = 4 * L1 * L3 * _warp_factor(N, L1 - L3) * (1 + (alpha * L2) ** 2)
+    w3 = 4 * L1 * L2 * _warp_factor(N, L2 - L1) * (1 + (alpha * L3) ** 2)
+    x = x + w1 + np.cos(2 * np.pi / 3) * w2 + np.cos(4 * np.pi / 3) * w3
+    y = y + np.sin(2 * np.pi / 3) * w2 + np.sin(4 * np.pi / 3) * w3
+    l1 = (np.sqrt(3.0) * y + 1.0) / 3.0                       # equilateral -> reference right triangle
+    l2 = (-3.0 * x - np.sqrt(3.0) * y + 2.0) / 6.0
+    l3 = (3.0 * x - np.sqrt(3.0) * y + 2.0) / 6.0
+    return -l2 + l3 - l1, -l2 - l3 + l1
+
+
+def tri_cubature(degree):
+    """The reference's triangle cubature of the given (even) degree: src/QuadratureData/quad_nodes_tri_N*.txt, a
+    published rule (data, extracted once by oracle/tools/extract_tri_cubature.py; degrees 2..10 shipped)."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "tri_cubature.json")) as fh:
+        tab = json.load(fh)
+    if str(degree) not in tab:
+        raise ValueError(f"no triangle cubature of degree {degree} in the package (N <= 5)")
+    rsw = np.array(tab[str(degree)], dtype=np.float64)
+    return rsw[:, 0].copy(), rsw[:, 1].copy(), rsw[:, 2].copy()
+
+
+def reference_tri(N, lf_scale=.25):
+    """Modal triangle element of the Euler / CNS scripts: ``init_reference_tri`` (src/SetupDG.jl:151-201) + the operator
+    tuple of dg2D_euler_tri.jl:45-63 / dg2D_CNS_cavity_optimized.jl:61-89.  BASELINE config 2."""
+    r, s = tri_nodes(N)
+    V, Vr, Vs = _tri_basis(N, r, s)
+    Vinv = np.linalg.inv(V)
+    Dr, Ds = Vr @ Vinv, Vs @ Vinv
+    x1, w1 = gauss_1d(N)
+    e, z = np.ones_like(x1), np.zeros_like(x1)
+    rf, sf = np.concatenate([x1, -x1, -e]), np.concatenate([-e, x1, -x1])       # faces s=-1, r+s=0, r=-1 (:176-181)
+    wf = np.tile(w1, 3)
+    nrJ, nsJ = np.concatenate([z, e, -e]), np.concatenate([-e, e, z])
+    rq, sq, wq = tri_cubature(2 * N)
+    Vq = _tri_basis(N, rq, sq)[0] @ Vinv
+    Vf = _tri_basis(N, rf, sf)[0] @ Vinv
+    M = Vq.T @ (wq[:, None] * Vq)
+    Pq = np.linalg.solve(M, Vq.T * wq[None, :])
+    LIFT = np.linalg.solve(M, Vf.T * wf[None, :])
+    rd = SimpleNamespace(elem="tri", N=N, Nfaces=3, r=r, s=s, rq=rq, sq=sq, wq=wq, rf=rf, sf=sf, wf=wf, nrJ=nrJ, nsJ=nsJ,
+                         Dr=Dr, Ds=Ds, Vq=Vq, Pq=Pq, Vf=Vf, LIFT=LIFT, M=M)
+    Ef = Vf @ Pq
+    Qskew = _hybridize([Pq.T @ M @ Dr @ Pq, Pq.T @ M @ Ds @ Pq], Ef, wf, [nrJ, nsJ])
+    Vh = np.vstack([Vq, Vf])
+    ops = SimpleNamespace(elem="tri", N=N, Nfaces=3, wq=wq, Ef=Ef, Qskew=Qskew, Vh=Vh, Ph=np.linalg.solve(M, Vh.T),
+                          VhP=Vh @ Pq, Lf=LIFT, Vq=Vq, Pq=Pq, Vf=Vf, Dr=Dr, Ds=Ds, modal=True,
+                          volume_scale=2.0, lf_scale=lf_scale)
+    return rd, ops
+
+
+def uniform_tri_mesh_md(rd, Kx, Ky, domain=((-1.0, 1.0), (-1.0, 1.0)), periodic=(True, True)):
+    """MeshData of the uniform triangle mesh of src/UniformTriMesh.jl:25-42: every cell (i, j), x-fastest, is split along
+    its SW-NE diagonal into element 2c = (SW, SE, NE) and 2c + 1 = (NE, NW, SW).  Connectivity is analytic: a face always
+    meets the SAME face number of its neighbour (bottom/top edges are faces 1, right/left edges faces 2, the diagonal faces
+    3) with the point order reversed."""
+    n = rd.N + 1
+    Nfq = 3 * n
+    (x0, x1), (y0, y1) = domain
+    hx, hy = (x1 - x0) / Kx, (y1 - y0) / Ky
+    K = 2 * Kx * Ky
+    c = np.arange(Kx * Ky)
+    ci, cj = c % Kx, c // Kx
+    X0, Y0 = x0 + hx * ci, y0 + hy * cj
+    VX = np.empty((3, K))
+    VY = np.empty((3, K))
+    VX[:, 0::2] = [X0, X0 + hx, X0 + hx]
+    VY[:, 0::2] = [Y0, Y0, Y0 + hy]
+    VX[:, 1::2] = [X0 + hx, X0, X0]
+    VY[:, 1::2] = [Y0 + hy, Y0 + hy, Y0]
+
+    def affine(rr, ss):                        # vertex interpolation: (-(r+s)/2, (1+r)/2, (1+s)/2)
+        W = np.stack([-(rr + ss) / 2, (1 + rr) / 2, (1 + ss) / 2], axis=1)
+        return W @ VX, W @ VY
+
+    md = SimpleNamespace(K=K, dim=2)
+    md.x, md.y = affine(rd.r, rd.s)
+    md.xq, md.yq = affine(rd.rq, rd.sq)
+    md.xf, md.yf = affine(rd.rf, rd.sf)
+    xr, xs = (VX[1] - VX[0]) / 2, (VX[2] - VX[0]) / 2
+    yr, ys = (VY[1] - VY[0]) / 2, (VY[2] - VY[0]) / 2
+    one = np.ones((1, K))
+    md.rxJ, md.sxJ, md.ryJ, md.syJ = ys * one, -yr * one, -xs * one, xr * one
+    md.J = (xr * ys - xs * yr) * one
+    nr, ns = rd.nrJ[::n][:, None], rd.nsJ[::n][:, None]       # one row per face
+    md.nxJ = nr * md.rxJ + ns * md.sxJ
+    md.nyJ = nr * md.ryJ + ns * md.syJ
+    md.sJ = np.sqrt(md.nxJ ** 2 + md.nyJ ** 2)
+    q = np.arange(n)
+    mapP = np.empty((Nfq, K), dtype=np.int64)
+    self_idx = np.arange(Nfq)[:, None] + Nfq * np.arange(K)[None, :]
+    e0, e1 = 2 * c, 2 * c + 1
+
+    def link(face, ea, eb, ok):                # face `face` of elements ea <-> the same face of eb, points reversed
+        rows = face * n + q
+        tgt = (face * n + (n - 1 - q))[:, None] + Nfq * eb[None, :]
+        mapP[np.ix_(rows, ea)] = np.where(ok[None, :], tgt, self_idx[np.ix_(rows, ea)])
+
+    below = ci + Kx * ((cj - 1) % Ky)
+    above = ci + Kx * ((cj + 1) % Ky)
+    right = (ci + 1) % Kx + Kx * cj
+    left = (ci - 1) % Kx + Kx * cj
+    yes = np.ones(Kx * Ky, dtype=bool)
+    link(0, e0, 2 * below + 1, yes if periodic[1] else cj > 0)              # my bottom edge = top edge of the cell below
+    link(0, e1, 2 * above, yes if periodic[1] else cj < Ky - 1)
+    link(1, e0, 2 * right + 1, yes if periodic[0] else ci < Kx - 1)         # my right edge = left edge of the cell to the right
+    link(1, e1, 2 * left, yes if periodic[0] else ci > 0)
+    link(2, e0, e1, yes)                                                    # the diagonal
+    link(2, e1, e0, yes)
+    md.mapP = mapP
+    md.n_halo = 0
+    return md
 
 
 def cavity_bc_sets(md):

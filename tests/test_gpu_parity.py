@@ -530,3 +530,25 @@ def test_curved_package_mesh_line_kernel_vs_generic_and_affine_limit(monkeypatch
     d0 = max(np.abs(a - b).max() for a, b in zip(rc, ra)) / max(np.abs(x).max() for x in ra)
     print(f"amp = 0: curved kernel vs affine kernel {d0:.2e}")
     assert d0 < 5e-12
+
+
+@pytest.mark.parametrize("N", [2, 4])
+def test_triangle_setup_of_the_package_drives_the_same_result(N):
+    """setup_dg.reference_tri / uniform_tri_mesh_md (BASELINE config 2 without oracle-built operators): same rhs and entropy
+    residual as the oracle's setup through the same kernels, and parity with the oracle's rhs_tri."""
+    from oracle import solvers as SV
+    from esdg_cns_b200 import api, setup_dg as SD
+    rd, md, ops, Q = SV.setup_tri_vortex(N, 5, 4)
+    ref, rt_ref = SV.rhs_tri(Q, md, ops, rd, .25, True)
+    prd, pops = SD.reference_tri(N)
+    pmd = SD.uniform_tri_mesh_md(prd, 5, 4, domain=((0, 15), (-5, 5)))
+    rho, u, v, p = SD.vortex(pmd.x, pmd.y)
+    Qp = SD.primitive_to_conservative(rho, (u, v), p)
+    assert max(np.abs(a - b).max() for a, b in zip(Q, Qp)) < 1e-13
+    s = api.Solver(pmd, pops)
+    out, rt = s.rhs(Q, True)
+    err = _relerr(out, ref)
+    tol = parity_tol(lambda: SV.rhs_tri(Q, md, ops, rd, .25, False)[0], ref)
+    print(f"tri N={N} package setup: relerr {err:.2e} (tol {tol:.2e}); rhstest {rt:.3e} / {rt_ref:.3e}")
+    assert err < tol
+    assert abs(rt - rt_ref) < 1e-11 * max(1.0, abs(rt_ref))

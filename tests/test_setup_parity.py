@@ -105,3 +105,28 @@ def test_curved_hex_mesh_of_the_package_is_watertight_and_preserves_the_free_str
     Q = list(P.primitive_to_conservative(rho, (.3 + .1 * rng.random(one.shape), 1 + .1 * rng.random(one.shape), -.2 + 0 * one), p))
     _, rt = SV.rhs_collocated(Q, md, ops, rd, 0.0, True)
     assert abs(rt) < 1e-11
+
+
+@pytest.mark.parametrize("N,Kx,Ky", [(1, 3, 2), (2, 2, 3), (3, 4, 3), (4, 3, 3)])
+def test_tri_setup_matches_oracle(N, Kx, Ky):
+    """setup_dg.reference_tri / uniform_tri_mesh_md (own basis formulation, analytic connectivity) against the oracle's
+    literal restatement of init_reference_tri + the generic mesh pipeline (connect_mesh, build_node_maps, periodic maps)."""
+    rd, md, ops, _ = SV.setup_tri_vortex(N, Kx, Ky)
+    prd, pops = SD.reference_tri(N)
+    pmd = SD.uniform_tri_mesh_md(prd, Kx, Ky, domain=((0, 15), (-5, 5)))
+    for nm in ("r", "s", "rq", "sq", "wq", "rf", "sf", "wf", "nrJ", "nsJ", "Dr", "Ds", "Vq", "Pq", "Vf", "LIFT"):
+        assert np.abs(np.asarray(getattr(rd, nm)) - np.asarray(getattr(prd, nm))).max() < 1e-11, nm
+    for nm in ("Ph", "VhP", "Lf", "Vq"):
+        assert np.abs(getattr(ops, nm) - getattr(pops, nm)).max() < 1e-11, nm
+    for a, b in zip(ops.Qskew, pops.Qskew):
+        assert np.abs(a - b).max() < 1e-11
+    assert pops.volume_scale == ops.volume_scale and pops.lf_scale == ops.lf_scale
+    n = N + 1
+    for nm in ("x", "y", "xq", "yq", "xf", "yf"):
+        assert np.abs(getattr(md, nm) - getattr(pmd, nm)).max() < 1e-12, nm
+    for nm in ("rxJ", "sxJ", "ryJ", "syJ"):
+        assert np.abs(getattr(md, nm)[:1] - getattr(pmd, nm)).max() < 1e-12, nm
+    for nm in ("nxJ", "nyJ", "sJ"):
+        assert np.abs(getattr(md, nm) - np.repeat(getattr(pmd, nm), n, axis=0)).max() < 1e-12, nm
+    assert np.abs(md.J[:1] - pmd.J).max() < 1e-12
+    assert np.array_equal(md.mapP, pmd.mapP)
