@@ -45,27 +45,48 @@ __global__ void __launch_bounds__(CnsqDims<n>::THREADS, 512 / CnsqDims<n>::THREA
     const long long e0 = p.e_begin + (long long)blockIdx.x * EB;
     const int nb = (int)min((long long)EB, p.e_begin + p.e_count - e0);
     const long long gq0 = e0 * Nq, gf0 = e0 * Nfq;
-    for (int it = tid; it < nb * Nfq; it += NT) {
-        const int ip = p.mapP[gf0 + it];
+    // every independent request first (mapP indices, Q of this thread's nodes), their uses after
+    constexpr int FIT = (EF + NT - 1) / NT, AIT = (EN + NT - 1) / NT;
+    int ipv[FIT];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) cp_async8(sP + q * EF + it, p.Tcur + (1 + q) * p.t_stride + ip);
+    for (int k = 0; k < FIT; ++k) {
+        const int it = tid + k * NT;
+        ipv[k] = it < nb * Nfq ? p.mapP[gf0 + it] : 0;
+    }
+    double Ua[AIT][4];
+#pragma unroll
+    for (int k = 0; k < AIT; ++k) {
+        const int it = tid + k * NT;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) Ua[k][f] = it < nb * Nq ? p.Q[f * p.q_stride + gq0 + it] : 1.0;
+    }
+#pragma unroll
+    for (int k = 0; k < FIT; ++k) {
+        const int it = tid + k * NT;
+        if (it < nb * Nfq) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) cp_async8(sP + q * EF + it, p.Tcur + (1 + q) * p.t_stride + ipv[k]);
+        }
     }
     for (int it = tid; it < nb * QUAD_GEO; it += NT) cp_async8(sGeo + it, p.geo + e0 * QUAD_GEO + it);
     cp_async_commit();
     if (tid < n) { s_lm[tid] = p.lm[tid]; s_lp[tid] = p.lp[tid]; s_w[tid] = p.w[tid]; }
     bool bad = false;
     // ---- nodes: v2..v4 = (rho u, rho v, -rho) / rho e                                  (euler_variables.jl:79-92)
-    for (int it = tid; it < nb * Nq; it += NT) {
-        const long long g = gq0 + it;
-        VD<1> U[4], hu[2], beta, rhoe;
 #pragma unroll
-        for (int f = 0; f < 4; ++f) U[f][0] = p.Q[f * p.q_stride + g];
-        vol_prim2_v<1>(U, p.gamma, hu, beta, rhoe);
-        bad = bad || !(U[0][0] > 0.0) || !(rhoe[0] > 0.0);
-        const VD<1> ire = vrcp(rhoe);
-        sV[it] = U[1][0] * ire[0];
-        sV[EN + it] = U[2][0] * ire[0];
-        sV[2 * EN + it] = -(U[0][0] * ire[0]);
+    for (int k = 0; k < AIT; ++k) {
+        const int it = tid + k * NT;
+        if (it < nb * Nq) {
+            VD<1> U[4], hu[2], beta, rhoe;
+#pragma unroll
+            for (int f = 0; f < 4; ++f) U[f][0] = Ua[k][f];
+            vol_prim2_v<1>(U, p.gamma, hu, beta, rhoe);
+            bad = bad || !(U[0][0] > 0.0) || !(rhoe[0] > 0.0);
+            const VD<1> ire = vrcp(rhoe);
+            sV[it] = U[1][0] * ire[0];
+            sV[EN + it] = U[2][0] * ire[0];
+            sV[2 * EN + it] = -(U[0][0] * ire[0]);
+        }
     }
     cp_async_wait_all();
     __syncthreads();

@@ -52,6 +52,9 @@ struct QuadParams {
     double* partial_vrhs;    // per CTA: sum wJq VUq . visc_rhs             (:966)
 };
 
+#ifndef ESDG_QUAD_PF_AHEAD
+#define ESDG_QUAD_PF_AHEAD 222   // half a wave of CTAs ahead (3 x 148 resident): measured 0 / 222 / 444 / 888 -> 1.287 / 1.236 / 1.243 / 1.294 ms
+#endif
 #ifndef ESDG_QUAD_THREADS
 #define ESDG_QUAD_THREADS 128
 #endif
@@ -250,16 +253,38 @@ __global__ void __launch_bounds__(QuadDims<n>::THREADS, QuadDims<n>::MIN_CTAS) k
     const int nb = (int)min((long long)EB, p.e_begin + p.e_count - e0);
     const long long gq0 = e0 * Nq, gf0 = e0 * Nfq;
     // ---- loads: own traces, exterior traces (mapP gather), geometry by cp.async; A from global -----------------
-    for (int it = tid; it < nb * Nfq; it += NT) {
-        const int ip = p.mapP[gf0 + it];
+    // every independent request first (mapP indices, Q and the stashed logs of this thread's nodes), their uses after
+    constexpr int FIT = (EF + NT - 1) / NT, AIT = (EN + NT - 1) / NT;
+    int ipv[FIT];
 #pragma unroll
-        for (int q = 0; q < QUAD_TP; ++q) {
-            if (OWN_SMEM) cp_async8(sWF + q * EF + it, p.Tcur + q * p.t_stride + gf0 + it);
-            cp_async8(sP + q * EF + it, p.Tcur + q * p.t_stride + ip);
-        }
-        if (CNS) {
+    for (int k = 0; k < FIT; ++k) {
+        const int it = tid + k * NT;
+        ipv[k] = it < nb * Nfq ? p.mapP[gf0 + it] : 0;
+    }
+    double Ua[AIT][4], La[AIT][2];
 #pragma unroll
-            for (int q = 0; q < 6; ++q) cp_async8(sSP + q * EF + it, p.sig_tr + q * p.t_stride + ip);
+    for (int k = 0; k < AIT; ++k) {
+        const int it = tid + k * NT;
+        const bool on = it < nb * Nq;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) Ua[k][f] = on ? p.Q[f * p.q_stride + gq0 + it] : 1.0;
+        La[k][0] = on ? p.Lcur[gq0 + it] : 0.0;
+        La[k][1] = on ? p.Lcur[p.q_stride + gq0 + it] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < FIT; ++k) {
+        const int it = tid + k * NT;
+        if (it < nb * Nfq) {
+            const int ip = ipv[k];
+#pragma unroll
+            for (int q = 0; q < QUAD_TP; ++q) {
+                if (OWN_SMEM) cp_async8(sWF + q * EF + it, p.Tcur + q * p.t_stride + gf0 + it);
+                cp_async8(sP + q * EF + it, p.Tcur + q * p.t_stride + ip);
+            }
+            if (CNS) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) cp_async8(sSP + q * EF + it, p.sig_tr + q * p.t_stride + ip);
+            }
         }
     }
     for (int it = tid; it < nb * QUAD_GEO; it += NT) cp_async8(sGeo + it, p.geo + e0 * QUAD_GEO + it);
@@ -274,22 +299,36 @@ __global__ void __launch_bounds__(QuadDims<n>::THREADS, QuadDims<n>::MIN_CTAS) k
         constexpr int LPF = (EN * 8 + 127) / 128;
         for (int it = tid; it < 4 * LPF; it += NT) prefetch_l2(p.res + (it / LPF) * p.q_stride + gq0 + (it % LPF) * 16);
     }
+#if ESDG_QUAD_PF_AHEAD > 0
+    {   // pull the inputs of the batch that will run in this CTA's slot next (ESDG_QUAD_PF_AHEAD CTAs further on) into L2
+        const long long ea = e0 + (long long)ESDG_QUAD_PF_AHEAD * EB;
+        if (ea + EB <= p.e_begin + p.e_count) {
+            constexpr int LQ = (EN * 8 + 127) / 128, LF = (EF * 8 + 127) / 128;
+            for (int it = tid; it < 4 * LQ; it += NT) prefetch_l2(p.Q + (it / LQ) * p.q_stride + ea * Nq + (it % LQ) * 16);
+            for (int it = tid; it < 2 * LQ; it += NT) prefetch_l2(p.Lcur + (it / LQ) * p.q_stride + ea * Nq + (it % LQ) * 16);
+            for (int it = tid; it < QUAD_TP * LF; it += NT) prefetch_l2(p.Tcur + (it / LF) * p.t_stride + ea * Nfq + (it % LF) * 16);
+        }
+    }
+#endif
     if (tid < n) { s_lm[tid] = p.lm[tid]; s_lp[tid] = p.lp[tid]; s_w[tid] = p.w[tid]; }
     bool bad = false;
     const double c_igm = 1.0 / (2.0 * (p.gamma - 1.0));
-    for (int it = tid; it < nb * Nq; it += NT) {
-        const long long g = gq0 + it;
-        VD<1> U[4], hu[2], beta, rhoe;
 #pragma unroll
-        for (int f = 0; f < 4; ++f) U[f][0] = p.Q[f * p.q_stride + g];
-        vol_prim2_v<1>(U, p.gamma, hu, beta, rhoe);
-        bad = bad || !(U[0][0] > 0.0) || !(rhoe[0] > 0.0);
-        sWV[it] = U[0][0];
-        sWV[EN + it] = hu[0][0];
-        sWV[2 * EN + it] = hu[1][0];
-        sWV[3 * EN + it] = beta[0];
-        sWV[4 * EN + it] = p.Lcur[g];
-        sWV[5 * EN + it] = p.Lcur[p.q_stride + g];
+    for (int k = 0; k < AIT; ++k) {
+        const int it = tid + k * NT;
+        if (it < nb * Nq) {
+            VD<1> U[4], hu[2], beta, rhoe;
+#pragma unroll
+            for (int f = 0; f < 4; ++f) U[f][0] = Ua[k][f];
+            vol_prim2_v<1>(U, p.gamma, hu, beta, rhoe);
+            bad = bad || !(U[0][0] > 0.0) || !(rhoe[0] > 0.0);
+            sWV[it] = U[0][0];
+            sWV[EN + it] = hu[0][0];
+            sWV[2 * EN + it] = hu[1][0];
+            sWV[3 * EN + it] = beta[0];
+            sWV[4 * EN + it] = La[k][0];
+            sWV[5 * EN + it] = La[k][1];
+        }
     }
     cp_async_wait_all();
     __syncthreads();
