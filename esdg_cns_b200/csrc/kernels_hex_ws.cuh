@@ -76,6 +76,10 @@ __device__ unsigned long long g_phase_cycles[16];
 #endif
 
 __device__ __forceinline__ void bar_sync_points(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bar_sync_lines(int nthreads) { asm volatile("bar.sync 2, %0;" ::"r"(nthreads) : "memory"); }
+#ifndef ESDG_WS_PRIMS_ON_LINES
+#define ESDG_WS_PRIMS_ON_LINES 1   // item A (conservative -> primitive, in place) by the line team instead of the point team
+#endif
 
 template <int n, bool DIAG>
 __global__ void __launch_bounds__(WsDims<n>::THREADS, 1) k_hex_stage_ws(const __grid_constant__ HexParams p) {
@@ -125,6 +129,7 @@ __global__ void __launch_bounds__(WsDims<n>::THREADS, 1) k_hex_stage_ws(const __
         // exterior traces of this thread's two face points: indices read one batch ahead, copies issued as soon as the
         // thread is done with the previous ones (no other thread touches these shared-memory slots)
         int ipn[2] = {0, 0};
+        bool bad_l = false;
         {
             long long e0;
             int nb;
@@ -152,6 +157,13 @@ __global__ void __launch_bounds__(WsDims<n>::THREADS, 1) k_hex_stage_ws(const __
             mbar_wait(&full_wv[b], (it >> 1) & 1);
             WS_MARK(1);
             mbar_wait(&full_tp[b], (it >> 1) & 1);
+#if ESDG_WS_PRIMS_ON_LINES
+            {   // A: the point team is the busier one (profiles/r2_phase_timing.txt): the 256 line threads convert the batch
+                double* wv = const_cast<double*>(sWV);
+                for (int k = tid; k < nb * Nq; k += NLT) node_prims_inplace<n, EB>(k, p, wv, bad_l);
+                bar_sync_lines(NLT);
+            }
+#endif
             WS_MARK(2);
 #if defined(ESDG_WS_EXPERIMENT) && ESDG_WS_EXPERIMENT == 2   // timing experiment: point team alone
 #pragma unroll
@@ -171,6 +183,7 @@ __global__ void __launch_bounds__(WsDims<n>::THREADS, 1) k_hex_stage_ws(const __
             mbar_arrive(&full_a3);
             WS_MARK(5);
         }
+        if (bad_l) atomicOr(p.bad, 1);
     } else {
         // ================================ point warps ===============================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(D::PREGS));
@@ -267,9 +280,13 @@ __global__ void __launch_bounds__(WsDims<n>::THREADS, 1) k_hex_stage_ws(const __
             double* sGeo = sGeo3 + (j % 3) * D::GEO_DOUBLES;
             cp_async_wait_all();
             stage_geo_finish<EB>(pt, NPT, nb, sGeo);
+#if !ESDG_WS_PRIMS_ON_LINES
             mbar_wait(&full_tp[b], (j >> 1) & 1);          // Q and the stash have landed (with the traces)
             sWV += (e0 * Nq) & 1;
             for (int k = pt; k < nb * Nq; k += NPT) node_prims_inplace<n, EB>(k, p, sWV, bad);
+#else
+            (void)sWV;
+#endif
             mbar_arrive(&full_wv[b]);
         };
         const unsigned nloc = (unsigned)((nbatch - blockIdx.x + gridDim.x - 1) / gridDim.x);   // batches of this CTA
