@@ -250,10 +250,23 @@ __device__ __forceinline__ void hadamard_sym(const GenericParams& p, GenericSmem
         for (int q = 0; q < DIM * DIM; ++q) Gi[q] = Ge[q * p.Nh + r];
     }
     double* qf = s.QF + (size_t)eb * NF * p.Nh;
+    // partner and coefficients of a round are requested one round ahead (table reads from global memory / L1: their
+    // latency sat on the critical path of every round, profiles/r2_tri_generic_rhs_ncu_summary.txt)
+    int jn = act ? p.sym_dst[r] : -1;
+    double cn[DIM];
+#pragma unroll
+    for (int kk = 0; kk < DIM; ++kk) cn[kk] = act ? p.sym_c[(size_t)r * 3 + kk] : 0.0;
     for (int t = 0; t < p.sym_rounds; ++t) {
-        const int j = act ? p.sym_dst[t * p.Nh + r] : -1;
+        const int j = jn;
+        double cq[DIM];
+#pragma unroll
+        for (int kk = 0; kk < DIM; ++kk) cq[kk] = cn[kk];
+        if (act && t + 1 < p.sym_rounds) {
+            jn = p.sym_dst[(t + 1) * p.Nh + r];
+#pragma unroll
+            for (int kk = 0; kk < DIM; ++kk) cn[kk] = p.sym_c[(size_t)((t + 1) * p.Nh + r) * 3 + kk];
+        }
         if (j >= 0) {
-            const double* cq = p.sym_c + (size_t)(t * p.Nh + r) * 3;
             if (curved) {
 #pragma unroll
                 for (int q = 0; q < DIM * DIM; ++q) Gr[q] = .5 * (Gi[q] + Ge[q * p.Nh + j]);
