@@ -307,8 +307,14 @@ def run_ours(args):
 
     stream = torch.cuda.current_stream()
     s = api.Solver(md, pops, device=local_rank, n_halo=md.n_halo, stream=stream.cuda_stream)
-    # pinned host buffers (the user's arrays for the end-to-end leg)
-    pin = [torch.empty((K, Ns), dtype=torch.float64).pin_memory() for _ in range(nf)]
+    # pinned host buffers (the user's arrays for the end-to-end leg); at N = 1 the process is bound to the GPU's own CPUs only
+    # while they are allocated and first touched (NUMA placement), so that the CPU baseline keeps every host core
+    aff0 = os.sched_getaffinity(0) if world == 1 else None
+    if world == 1:
+        numa = bind_to_gpu_cpus(local_rank)
+    pin = [torch.zeros((K, Ns), dtype=torch.float64).pin_memory() for _ in range(nf)]
+    if aff0 is not None:
+        os.sched_setaffinity(0, aff0)
     host = [t.numpy().T for t in pin]                   # Ns x K column-major views
     for h, q in zip(host, Q0):
         h[...] = q

@@ -552,3 +552,40 @@ def test_triangle_setup_of_the_package_drives_the_same_result(N):
     print(f"tri N={N} package setup: relerr {err:.2e} (tol {tol:.2e}); rhstest {rt:.3e} / {rt_ref:.3e}")
     assert err < tol
     assert abs(rt - rt_ref) < 1e-11 * max(1.0, abs(rt_ref))
+
+
+@pytest.mark.parametrize("chunks", [None, 5])
+def test_pipelined_host_step_on_a_curved_mesh(chunks, monkeypatch):
+    """esdg_lsrk45_host on curved hexes (the one-shot curved line kernel over chunk ranges) == upload + lsrk45 + download, bitwise;
+    and the same through the C ABI for a quad context (tensor-product quad kernels, plain upload / steps / download)."""
+    import torch
+    if chunks is not None:
+        monkeypatch.setenv("ESDG_HOST_CHUNKS", str(chunks))
+    from esdg_cns_b200 import api, setup_dg as SD
+    N = 3
+    prd, pops = SD.reference_hex(N)
+    md = SD.curved_hex_mesh_md(prd, (20, 22, 21), domain=((-np.pi, np.pi),) * 3, amp=.1)
+    rho, u, v, w, p = SD.taylor_green(md.xq, md.yq, md.zq)
+    Q = SD.primitive_to_conservative(rho + .05 * np.sin(md.xq), (u + .3, v, w + .1 * np.sin(md.yq)), p)
+    s = api.Solver(md, pops)
+    assert s.kernel_path() == "hex_line_curved"
+    s.upload(Q)
+    s.lsrk45(1e-3, 2)
+    ref = s.download()
+    pin = [torch.empty((md.K, (N + 1) ** 3), dtype=torch.float64).pin_memory() for _ in range(5)]
+    host = [t.numpy().T for t in pin]
+    for h, q in zip(host, Q):
+        h[...] = q
+    out = s.lsrk45_host(host, 1e-3, 2)
+    assert all(np.array_equal(a, b) for a, b in zip(out, ref))
+    s.close()
+    rq, oq = SD.reference_quad(3)
+    mq = SD.uniform_quad_mesh_md(rq, 12, 9, domain=((0, 20), (-5, 5)))
+    Qq = SD.primitive_to_conservative(*(lambda r_, u_, v_, p_: (r_, (u_, v_), p_))(*SD.vortex(mq.xq, mq.yq)))
+    sq = api.Solver(mq, oq)
+    sq.upload(Qq)
+    sq.lsrk45(1e-2, 2)
+    refq = sq.download()
+    hq = [np.asfortranarray(q.copy()) for q in Qq]
+    outq = sq.lsrk45_host(hq, 1e-2, 2)
+    assert all(np.array_equal(a, b) for a, b in zip(outq, refq))
