@@ -27,7 +27,9 @@ namespace esdg {
 // must fit the CTA's register pool = (256 + NPT) x the launch count).  N = 4: the line problem needs ~184 registers
 // (n+2 nodes, 5n accumulators, three pairs in flight), which leaves room for 4 point warps at 136.  Measured on the
 // bench slab (profiles/r2_ws_variants.txt): 8 point warps at 72-88 registers 5.8-7.3 ms, 4 at 104: 7.6, 4 at 120: 4.27,
-// 4 at 136: 4.11, 4 at 152 (lines 176): 4.48.  N <= 3: the line problem is smaller, both teams get 8 warps.
+// 4 at 136: 4.11, 4 at 152 (lines 176): 4.48, 4 at 168 (lines 168): 5.15.  N <= 3: the line problem is smaller and the point team
+// is the busier one: 168 / 168 (no register hand-over at all) 2.27 ms per stage on 64^3 elements at N = 3 against 2.36 at 184 / 136;
+// 160 / 184: 2.74, 152 / 200: 3.29 (line spills); 8 point warps at 128 / 120: 2.92.
 #ifndef ESDG_WS_NPT5
 #define ESDG_WS_NPT5 128
 #endif
@@ -41,10 +43,10 @@ namespace esdg {
 #define ESDG_WS_NPT4 128
 #endif
 #ifndef ESDG_WS_LREGS4
-#define ESDG_WS_LREGS4 184
+#define ESDG_WS_LREGS4 168
 #endif
 #ifndef ESDG_WS_PREGS4
-#define ESDG_WS_PREGS4 136
+#define ESDG_WS_PREGS4 168
 #endif
 
 template <int n>
@@ -52,6 +54,7 @@ struct WsDims {
     using G = HexGeom<n>;
     static constexpr int NLT = 256, NPT = n == 5 ? ESDG_WS_NPT5 : ESDG_WS_NPT4, THREADS = NLT + NPT;
     static constexpr int LREGS = n == 5 ? ESDG_WS_LREGS5 : ESDG_WS_LREGS4, PREGS = n == 5 ? ESDG_WS_PREGS5 : ESDG_WS_PREGS4;
+    static constexpr int LAUNCH_REGS = (65536 / THREADS) / 8 * 8;   // what every thread holds at launch; the teams move up / down from it
     static constexpr int EB = NLT / G::NL;                  // n = 5: 3 elements (225 lines), 4: 5, 3: 9, 2: 21
     static constexpr int EN = EB * G::Nq, EF = EB * G::Nfq;
     static constexpr int ENP = wv_stride<n, EB>();                                 // plane stride of WV (even)
@@ -124,7 +127,8 @@ __global__ void __launch_bounds__(WsDims<n>::THREADS, 1) k_hex_stage_ws(const __
 
     if (tid < NLT) {
         // ================================ line warps ================================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(D::LREGS));
+        if constexpr (D::LREGS >= D::LAUNCH_REGS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(D::LREGS));
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(D::LREGS));
         const double c_igm = 1.0 / (2.0 * (p.gamma - 1.0));
         // exterior traces of this thread's two face points: indices read one batch ahead, copies issued as soon as the
         // thread is done with the previous ones (no other thread touches these shared-memory slots)
@@ -186,7 +190,8 @@ __global__ void __launch_bounds__(WsDims<n>::THREADS, 1) k_hex_stage_ws(const __
         if (bad_l) atomicOr(p.bad, 1);
     } else {
         // ================================ point warps ===============================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(D::PREGS));
+        if constexpr (D::PREGS > D::LAUNCH_REGS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(D::PREGS));
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(D::PREGS));
         const int pt = tid - NLT;
         constexpr int MAXF = (EF + NPT - 1) / NPT;
         const bool bulk = trace_runs_aligned(p);
