@@ -382,7 +382,7 @@ def run_ours(args):
     e2e_step()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, min(args.steps, 10))
     for _ in range(e2e_steps):
         e2e_step()
     barrier()
