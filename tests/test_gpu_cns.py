@@ -382,3 +382,34 @@ def test_cns_quad_nodal_line_kernels_match_modal_gemm_kernels(bctype, monkeypatc
     assert all(abs(x[1] - y[1]) < 1e-6 * max(1.0, abs(y[1])) and abs(x[2] - y[2]) < 1e-6 * y[2] for x, y in zip(a[4], b[4]))
     assert max(np.abs(x - y).max() for x, y in zip(a[5], b[5])) < 1e-8      # step sizes agree to ~1e-6 (error estimate partly round-off)
     assert a[6] < b[6]
+
+
+@pytest.mark.parametrize("elem", ["quad", "tri"])
+@pytest.mark.parametrize("bctype", [1, 3])
+def test_cns_on_a_sheared_cavity_mesh(elem, bctype):
+    """Parallelogram elements (all four geometric factors non-zero, oblique wall normals): the general metric terms of the
+    BR1 gradient / divergence, the stress and slip BCs with oblique normals -- quads on the Gauss-nodal line kernels, triangles
+    on the table-driven ones."""
+    from oracle import cns, setupdg as S, mesh as M
+    from esdg_cns_b200 import api
+    N, K1D = 3, 5
+    rd, md0, ops, bc0, _ = cns.setup_cavity(elem, N, K1D)
+    VX, VY, EToV = (M.uniform_quad_mesh if elem == "quad" else M.uniform_tri_mesh)(K1D, K1D)
+    md = S.init_mesh((VX + .25 * VY, VY + .1 * VX), EToV, rd)
+    for name in ("rxJ", "sxJ", "ryJ", "syJ"):
+        setattr(md, name, ops.Vh @ getattr(md, name))
+    assert np.array_equal(md.mapP, md0.mapP) and np.abs(md.sxJ).max() > 1e-3 and np.abs(md.ryJ).max() > 1e-3
+    bc = SimpleNamespace(lid=bc0.lid, wall=bc0.wall, boundary=bc0.boundary, mapB=bc0.mapB, vlid=bc0.vlid)
+    bc.nx = (md.nxJ / md.sJ).flatten(order="F")[bc.boundary]
+    bc.ny = (md.nyJ / md.sJ).flatten(order="F")[bc.boundary]
+    Q = _state(md0)
+    par = cns.cavity_params(Re=100.0, bctype=bctype)
+    ref, rt_ref, rtv_ref = cns.rhsRK(Q, md, ops, bc, par)
+    s = api.Solver(md, ops, cns=_cns_settings(par, bc, md))
+    assert s.kernel_path() == ("cns_quad_line" if elem == "quad" else "cns")
+    out, rt, rtv = s.rhs(Q, True)
+    tol = parity_tol(lambda: cns.rhsRK(Q, md, ops, bc, par)[0], ref)
+    err = relerr(out, ref)
+    print(f"sheared cavity {elem} bc={bctype}: relerr {err:.2e} tol {tol:.2e} rhstest {rt:.6e}/{rt_ref:.6e} visc {rtv:.6e}/{rtv_ref:.6e}")
+    assert err < tol
+    assert abs(rt - rt_ref) < 1e-11 * max(1.0, abs(rt_ref)) and abs(rtv - rtv_ref) < 1e-11 * max(1.0, abs(rtv_ref))
