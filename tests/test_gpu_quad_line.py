@@ -169,3 +169,49 @@ def test_quad_yslabs_with_halo_exchange_match_single_context(N, mesh, nslabs, ov
     print(f"quad N={N} {mesh} {nslabs} slabs overlap={overlap}: max |dQ| {diff:.2e}, rhstest {rt:.6e} vs {rt_ref:.6e}")
     assert diff == 0.0
     assert abs(rt - rt_ref) < 1e-12 * max(1.0, abs(rt_ref))
+
+
+def test_quad_line_walls_as_self_mapped_faces_and_resident_rhs(monkeypatch):
+    """A non-periodic quad mesh (boundary points map to themselves, as connect_mesh leaves them) on the line kernel against the
+    table-driven kernels; `rhs(None)` -- the rhs of the RESIDENT state -- equals `rhs(Q)` after upload, also for a Navier-Stokes
+    context whose state lives in the Gauss-nodal basis."""
+    from types import SimpleNamespace
+    from esdg_cns_b200 import api, setup_dg as SD
+    prd, pops = SD.reference_quad(3)
+    pmd = SD.uniform_quad_mesh_md(prd, 7, 6, domain=((0, 20), (-5, 5)), periodic=(False, True))
+    rho, u, v, p = SD.vortex(pmd.xq, pmd.yq)
+    Q = SD.primitive_to_conservative(rho, (u, v), p)
+    s = api.Solver(pmd, pops)
+    assert s.kernel_path() == "quad_line"
+    r1, rt1 = s.rhs(Q, True)
+    s.upload(Q)
+    r2, rt2 = s.rhs(None, True)
+    assert all(np.array_equal(a, b) for a, b in zip(r1, r2)) and rt1 == rt2
+    monkeypatch.setenv("ESDG_FORCE_GENERIC", "1")
+    g = api.Solver(pmd, pops)
+    assert g.kernel_path() == "generic"
+    r3, rt3 = g.rhs(Q, True)
+    monkeypatch.delenv("ESDG_FORCE_GENERIC")
+    sc = max(np.abs(x).max() for x in r3)
+    d = max(np.abs(a - b).max() for a, b in zip(r1, r3)) / sc
+    print(f"non-periodic quads: line vs generic {d:.2e}, rhstest {rt1:.6e} / {rt3:.6e}")
+    assert d < 5e-12 and abs(rt1 - rt3) < 1e-11 * max(1.0, abs(rt3))
+    # Navier-Stokes context: resident rhs in the nodal basis == rhs of the uploaded coefficients
+    rdm, opm = SD.reference_quad_modal(3)
+    mdm = SD.uniform_quad_mesh_md(rdm, 5, 5, periodic=(False, False))
+    bc = SD.cavity_bc_sets(mdm)
+    st = SimpleNamespace(Re=100.0, mu=.01, lam=-2 / 300, Pr=.71, bctype=1, inviscid_dissp=True, viscous_dissp=True,
+                         wall=bc.wall, lid=bc.lid, vlid=bc.vlid, mapB=bc.mapB)
+    x, y = mdm.x, mdm.y
+    Qm = SD.primitive_to_conservative(1 + .1 * np.sin(np.pi * x) * np.cos(np.pi * y), (.2 * np.sin(np.pi * x) * np.sin(np.pi * y), .1 * (1 - y * y) * np.cos(x)),
+                                      (1 / (.09 * 1.4)) * (1 + .05 * np.cos(np.pi * x)))
+    c = api.Solver(mdm, opm, cns=st)
+    assert c.kernel_path() == "cns_quad_line"
+    a1 = c.rhs(Qm, True)
+    c.upload(Qm)
+    a2 = c.rhs(None, True)
+    back = c.download()
+    scm = max(np.abs(x_).max() for x_ in a1[0])
+    assert max(np.abs(p_ - q_).max() for p_, q_ in zip(a1[0], a2[0])) / scm < 1e-13
+    assert abs(a1[1] - a2[1]) < 1e-12 and abs(a1[2] - a2[2]) < 1e-12
+    assert max(np.abs(p_ - q_).max() for p_, q_ in zip(back, Qm)) < 1e-13      # Vq then Pq: the caller's coefficients come back
