@@ -28,7 +28,7 @@ def _cns_settings(par, bc, md):
                            wall=bc.wall, lid=bc.lid, vlid=bc.vlid, mapB=md.mapB)
 
 
-@pytest.mark.parametrize("elem,N,K1D", [("quad", 3, 4), ("tri", 3, 4), ("tri", 2, 3), ("quad", 2, 5)])
+@pytest.mark.parametrize("elem,N,K1D", [("quad", 3, 4), ("tri", 3, 4), ("tri", 2, 3), ("quad", 2, 5), ("quad", 1, 6), ("quad", 4, 3)])
 @pytest.mark.parametrize("bctype", [1, 2, 3])
 @pytest.mark.parametrize("dissp", [(True, True), (False, False)])
 def test_cns_rhs_matches_oracle(elem, N, K1D, bctype, dissp):
